@@ -1,0 +1,168 @@
+/*
+ * sdt_b200.h -- C ABI of libsdt_b200.so: the B200 (sm_100a) implementation of
+ * SCAL-SDT's LoRA training-step hot path.
+ *
+ * The reference (MooerFoes/scal-sdt) is pure Python and has no FFI of its own;
+ * each entry point below replaces the arithmetic that sits under one reference
+ * call site (citations relative to /root/reference).  The Python host layer in
+ * scal_sdt_b200/ binds these symbols with ctypes and keeps the reference's
+ * module-injection / loss / EMA interfaces unchanged.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch), 16-byte
+ *     aligned and contiguous, unless the comment says "host";
+ *   - every call is asynchronous on `stream` (pass torch's current stream) and
+ *     is CUDA-graph capturable; the library never allocates tensor memory and
+ *     never synchronises;
+ *   - return value 0 = success, negative = error; sdt_last_error() returns the
+ *     thread-local message.  Unsupported dtype/shape is an ERROR, never a
+ *     fallback (there is no CPU path in this library);
+ *   - `void* stream` is a cudaStream_t.
+ */
+#ifndef SDT_B200_H_
+#define SDT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types */
+enum { SDT_F32 = 0, SDT_BF16 = 1 };
+/* prediction target, modules/model.py:306-314 */
+enum { SDT_TARGET_EPSILON = 0, SDT_TARGET_SAMPLE = 1, SDT_TARGET_V = 2 };
+/* error codes */
+enum { SDT_OK = 0, SDT_ERR_ARG = -1, SDT_ERR_UNSUPPORTED = -2, SDT_ERR_CUDA = -3, SDT_ERR_NCCL = -4 };
+
+int         sdt_version(void);
+const char* sdt_last_error(void);
+/* 0 when the current device is compute capability 10.x (B200), else SDT_ERR_UNSUPPORTED */
+int         sdt_device_check(void);
+
+/* ---- K1: fused LoRA projection, forward ---------------------------------------------------
+ * Replaces loralib.Linear.forward reached through get_lora (modules/lora.py:12-14):
+ *     Ts = scaling * (X A^T)            [M,r]   (kept on-chip; also written to t_save)
+ *     Y  = X W^T + bias + Ts B^T        [M,N]
+ * SDT_BF16: x[M,K], w[N,K], A[r,K], B[N,r], y[M,N], t_save[M,r] bf16, bias[N] f32 or NULL;
+ *           r in {16,32,64} (host layer zero-pads smaller ranks); K%8==0, N%8==0.
+ *           One tcgen05/TMEM/TMA kernel launch.
+ * SDT_F32 : all f32, any r >= 1; FFMA kernels (parity path for the reference's fp32 CPU config).
+ * A == NULL (r == 0) gives the plain frozen projection Y = X W^T + bias.
+ */
+int sdt_lora_linear_fwd(const void* x, const void* w, const float* bias, const void* A, const void* B,
+                        float scaling, void* y, void* t_save,
+                        int64_t M, int64_t K, int64_t N, int r, int dtype, void* stream);
+
+/* ---- K2: fused LoRA projection, backward ---------------------------------------------------
+ * Autograd of the above with W, bias frozen (modules/model.py:137):
+ *     G  = scaling * (dY B)             [M,r]   (on-chip; also written to g_ws)
+ *     dX = dY W + G A                   [M,K]   (skipped when dx == NULL)
+ *     dA (+)= G^T X                     [r_true,K] f32
+ *     dB (+)= dY^T Ts                   [N,r_true] f32
+ * SDT_BF16: dy[M,N], x[M,K], t_save[M,r], g_ws[M,r] bf16; wt = W^T [K,N] bf16 (cached copy of the
+ *           frozen weight); At = A^T [K,r] bf16; Bt = B^T [r,N] bf16 (from sdt_lora_pack).
+ *           dA/dB are f32 and are ACCUMULATED into (split-M partial sums use red.global.add):
+ *           zero them first unless accumulating across micro-batches.  r_true <= r is the
+ *           un-padded rank: only dA[:r_true,:] and dB[:, :r_true] (row stride r_true) are written.
+ * SDT_F32 : wt = W [N,K] (no transposed copy needed), At = A [r,K], Bt = B [N,r], r_true == r.
+ */
+int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt, const void* At, const void* Bt,
+                        const void* t_save, float scaling, void* dx, void* g_ws, float* dA, float* dB,
+                        int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* stream);
+
+/* ---- LoRA operand packing (multi-tensor, one launch for all sites) ---------------------------
+ * For every site i: from the f32 master lora_A[r_true,K], lora_B[N,r_true] write the four bf16
+ * operand layouts the tensor-core kernels read, zero-padded to rank r:
+ *     A_p[r,K]  At_p[K,r]  B_p[N,r]  Bt_p[r,N]
+ * `sites` is a DEVICE array of n_sites sdt_pack_site records (built once by the host layer).
+ */
+typedef struct {
+  const float* A;  const float* B;          /* f32 masters */
+  void* A_p; void* At_p; void* B_p; void* Bt_p;   /* bf16 outputs */
+  int32_t K, N, r_true, r;
+} sdt_pack_site;
+int sdt_lora_pack(const sdt_pack_site* sites, int n_sites, int64_t max_site_elems, void* stream);
+
+/* ---- K3: DDPM noising + prediction target --------------------------------------------------
+ * Replaces scheduler.add_noise / get_velocity (modules/model.py:302,312):
+ *     a = sqrt(abar[t_b]), s = sqrt(1 - abar[t_b])     (abar first cast to the sample dtype)
+ *     noisy  = a*x0 + s*eps
+ *     target = a*eps - s*x0      (mode V only; for EPSILON / SAMPLE pass target == NULL: the
+ *                                 reference aliases eps / x0, no copy is made)
+ * x0, eps, noisy, target: [B, chw] of `dtype`; t: int64[B]; alphas_cumprod: f32[T].
+ * Bit-exact with the torch op sequence (no FMA contraction).  t outside [0,T) is clamped on the
+ * device and reported through *oob_flag (int32, device, may be NULL), the async analogue of the
+ * reference's IndexError.
+ */
+int sdt_noise_target(const void* x0, const void* eps, const int64_t* t, const float* alphas_cumprod,
+                     int num_train_timesteps, void* noisy, void* target, int mode,
+                     int64_t B, int64_t chw, int dtype, int32_t* oob_flag, void* stream);
+
+/* ---- K4: MSE loss, two-segment mean, fused dPred ---------------------------------------------
+ * Replaces F.mse_loss(reduction="none") + chunk + mean (modules/model.py:316,338-342):
+ *     L = (pred - target)^2 in f32
+ *     split == B : loss = mean(L)
+ *     split <  B : loss = mean(L[:split]) + w_prior * mean(L[split:])   (instance | class halves)
+ * loss_out: f32[3] = {loss, mean(first segment), mean(second segment or 0)}.
+ * dpred (NULL or [B,chw] of pred_dtype) = grad_scale * dloss/dpred.
+ * loss_elem (NULL or f32[B,chw]) = L, for callers of the reference's per-element _denoise_loss.
+ * nan_flag (NULL or int32 device) is set to 1 if any L is NaN (async analogue of raise_if_nan).
+ * workspace: sdt_mse_loss_workspace_bytes() bytes, zero-initialised once by the caller; the kernel
+ * leaves it zeroed.  Deterministic two-stage reduction (no float atomics).
+ */
+size_t sdt_mse_loss_workspace_bytes(void);
+int sdt_mse_loss(const void* pred, int pred_dtype, const void* target, int target_dtype,
+                 float* loss_out, void* dpred, float* loss_elem, int32_t* nan_flag,
+                 int64_t B, int64_t chw, int64_t split, float w_prior, float grad_scale,
+                 void* workspace, void* stream);
+
+/* ---- K5: EMA update -----------------------------------------------------------------------------
+ * Replaces ExponentialMovingAverage.update's per-tensor loop (modules/ema.py:56-61):
+ *     tmp = s - p ; tmp *= (1-d) ; s -= tmp        (same three roundings, bit-exact in f32)
+ * flat : one contiguous arena of n elements.
+ * multi: n_tensors separate tensors; `chunks` is a device array of n_chunks {tensor, offset}
+ *        records covering every tensor in pieces of <= chunk_elems elements.
+ * one_minus_decay_dev: optional DEVICE f32 scalar that overrides the immediate (lets a captured
+ * CUDA graph follow the warm-up schedule min(d,(1+n)/(10+n)), modules/ema.py:47-54).
+ */
+typedef struct { int32_t tensor; int32_t pad; int64_t offset; } sdt_chunk;
+int sdt_ema_update_flat(void* shadow, const void* param, int64_t n, float one_minus_decay,
+                        const float* one_minus_decay_dev, int dtype, void* stream);
+int sdt_ema_update_multi(void* const* shadow_ptrs, const void* const* param_ptrs, const int64_t* numels,
+                         const sdt_chunk* chunks, int n_chunks, int chunk_elems, float one_minus_decay,
+                         const float* one_minus_decay_dev, int dtype, void* stream);
+
+/* ---- f1: fused AdamW over the flat LoRA arena (torch.optim.AdamW semantics) -------------------
+ * modules/model.py:33-64 builds one torch AdamW param group per site; over the flat arena this is
+ * a single pass.  hyper (host values) = {lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2};
+ * hyper_dev (optional device f32[7]) overrides it for graph replay.  grad_scale multiplies g first
+ * (1/world after a sum-allreduce, or 1).  If ema_shadow != NULL the EMA lerp of K5 is applied to the
+ * freshly updated parameter in the same pass.
+ */
+int sdt_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,
+                   const float* hyper_dev, float grad_scale, float* ema_shadow, float ema_one_minus_decay,
+                   const float* ema_one_minus_decay_dev, void* stream);
+
+/* ---- K6: data-parallel LoRA-gradient exchange (replaces Lightning DDP, train.py:98-109) -------
+ * One NCCL communicator per process (libnccl is resolved at run time with dlopen, so the library
+ * loads on machines without NCCL).  sdt_allreduce averages `count` elements in place.
+ */
+int sdt_comm_unique_id(void* out_128_bytes /* host */);
+int sdt_comm_init(const void* unique_id_128_bytes /* host */, int rank, int world);
+int sdt_comm_world(void);
+int sdt_allreduce(void* buf, int64_t count, int dtype, void* stream);
+int sdt_comm_destroy(void);
+
+/* ---- test support: slow SIMT GEMM used by the GPU tests as an on-device cross-check -----------
+ * C[M,N] = alpha * sum_k A[m*lda_m + k*lda_k] * B[n*ldb_n + k*ldb_k] (+ beta * C), f32.
+ */
+int sdt_simt_gemm_f32(const float* A, int64_t lda_m, int64_t lda_k, const float* B, int64_t ldb_n, int64_t ldb_k,
+                      float* C, int64_t ldc, const float* bias, float alpha, float beta,
+                      int64_t M, int64_t N, int64_t K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDT_B200_H_ */

@@ -1,0 +1,84 @@
+// Shared helpers for libsdt_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/sdt_b200.h"
+
+namespace sdt {
+
+void set_error(const char* fmt, ...);   // defined in api.cu (thread-local message)
+
+#define SDT_REQUIRE(cond, code, ...)                      \
+  do {                                                    \
+    if (!(cond)) {                                        \
+      ::sdt::set_error(__VA_ARGS__);                      \
+      return (code);                                      \
+    }                                                     \
+  } while (0)
+
+#define SDT_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::sdt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                       __LINE__);                                                          \
+      return SDT_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+// launch-error check that is legal during stream capture (no sync)
+#define SDT_LAUNCH_OK(what)                                                                 \
+  do {                                                                                      \
+    cudaError_t _e = cudaPeekAtLastError();                                                 \
+    if (_e != cudaSuccess) {                                                                \
+      (void)cudaGetLastError();                                                             \
+      ::sdt::set_error("launch of %s failed: %s", what, cudaGetErrorString(_e));            \
+      return SDT_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int num_sms();   // cached multiProcessorCount of the current device (api.cu)
+
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 128-bit accesses: data touched once, keep it out of L1
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// read-write arenas (EMA shadow): plain ld (not .nc) because the same kernel writes it
+__device__ __forceinline__ uint4 ld_rw(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t lo16) { return __uint_as_float(lo16 << 16); }
+__device__ __forceinline__ uint32_t f32_to_bf16_bits(float f) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  return f32_to_bf16_bits(lo) | (f32_to_bf16_bits(hi) << 16);
+}
+// round an f32 to the nearest bf16 value, result as f32 (what torch does after every bf16 op)
+__device__ __forceinline__ float round_bf16(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+
+}  // namespace sdt
