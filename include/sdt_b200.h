@@ -162,6 +162,9 @@ int sdt_simt_gemm_f32(const float* A, int64_t lda_m, int64_t lda_k, const float*
                       float* C, int64_t ldc, const float* bias, float alpha, float beta,
                       int64_t M, int64_t N, int64_t K, void* stream);
 
+/* test support: override shared-memory descriptor constants of the weight-gradient kernel (probing) */
+int sdt_debug_set(int key, uint64_t value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,62 @@
+"""Build ``libsdt_b200.so`` (the CUDA hot path + C ABI) in-tree with nvcc for sm_100a.
+
+The library is the product path; nothing here falls back to another backend.  ``nvcc`` cross-compiles
+without a GPU, so the same command serves the CPU-only build check and the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+BUILD_DIR = PKG_DIR / "_build"
+LIB_PATH = BUILD_DIR / "libsdt_b200.so"
+INCLUDE_DIR = PKG_DIR.parent / "include"
+
+SOURCES = ["api.cu", "elementwise.cu", "comm.cu", "simt_gemm.cu", "lora_gemm.cu", "lora_wgrad.cu", "lora_api.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
+]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found: libsdt_b200.so cannot be built (there is no non-CUDA path)")
+    return cand
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + list(INCLUDE_DIR.glob("*.h"))
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the library if it is missing or older than its sources; return its path."""
+    if not force and not _stale():
+        return LIB_PATH
+    BUILD_DIR.mkdir(parents=True, exist_ok=True)
+    tmp = BUILD_DIR / "libsdt_b200.so.tmp"
+    cmd = [_nvcc(), *NVCC_FLAGS, *(str(CSRC / s) for s in SOURCES), "-o", str(tmp)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,77 @@
+// C ABI of the LoRA projection (K1 forward, K2 backward): argument checks + dtype dispatch.
+//   SDT_BF16 -> tcgen05 / TMEM / TMA kernels (lora_gemm.cu, lora_wgrad.cu)
+//   SDT_F32  -> FFMA kernels (simt_gemm.cu): parity path of the reference's fp32 configuration
+#include "sdt_common.cuh"
+
+namespace sdt {
+int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
+                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, cudaStream_t st);
+int lora_wgrad_bf16(const void* u, const void* v, float* out, int64_t M, int64_t F, int r, int r_true, bool transposed,
+                    cudaStream_t st);
+int lora_fwd_f32(const float* x, const float* w, const float* bias, const float* A, const float* B, float scaling,
+                 float* y, float* t_save, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st);
+int lora_bwd_f32(const float* dy, const float* x, const float* w, const float* A, const float* B, const float* t_save,
+                 float scaling, float* dx, float* g_ws, float* dA, float* dB, int64_t M, int64_t K, int64_t N, int r,
+                 cudaStream_t st);
+void debug_set(int key, uint64_t value);
+}  // namespace sdt
+
+using namespace sdt;
+
+extern "C" int sdt_lora_linear_fwd(const void* x, const void* w, const float* bias, const void* A, const void* B,
+                                   float scaling, void* y, void* t_save, int64_t M, int64_t K, int64_t N, int r,
+                                   int dtype, void* stream) {
+  SDT_REQUIRE(x && w && y, SDT_ERR_ARG, "sdt_lora_linear_fwd: null pointer");
+  SDT_REQUIRE(M > 0 && K > 0 && N > 0 && r >= 0, SDT_ERR_ARG, "sdt_lora_linear_fwd: bad sizes M=%lld K=%lld N=%lld r=%d",
+              (long long)M, (long long)K, (long long)N, r);
+  SDT_REQUIRE((r == 0) == (A == nullptr) && (r == 0) == (B == nullptr), SDT_ERR_ARG,
+              "sdt_lora_linear_fwd: A and B must be given exactly when r > 0");
+  SDT_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(A) && aligned16(B) && aligned16(t_save),
+              SDT_ERR_ARG, "sdt_lora_linear_fwd: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SDT_BF16) {
+    SDT_REQUIRE(r == 0 || t_save != nullptr, SDT_ERR_ARG, "sdt_lora_linear_fwd: t_save is required when r > 0");
+    return lora_gemm_bf16(x, w, bias, A, B, scaling, y, t_save, M, K, N, r, true, st);
+  }
+  if (dtype == SDT_F32)
+    return lora_fwd_f32((const float*)x, (const float*)w, bias, (const float*)A, (const float*)B, scaling, (float*)y,
+                        (float*)t_save, M, K, N, r, st);
+  set_error("sdt_lora_linear_fwd: unsupported dtype %d (there is no fallback path)", dtype);
+  return SDT_ERR_UNSUPPORTED;
+}
+
+extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt, const void* At, const void* Bt,
+                                   const void* t_save, float scaling, void* dx, void* g_ws, float* dA, float* dB,
+                                   int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* stream) {
+  SDT_REQUIRE(dy, SDT_ERR_ARG, "sdt_lora_linear_bwd: null dy");
+  SDT_REQUIRE(M > 0 && K > 0 && N > 0 && r >= 0, SDT_ERR_ARG, "sdt_lora_linear_bwd: bad sizes");
+  SDT_REQUIRE(dx != nullptr || r > 0, SDT_ERR_ARG, "sdt_lora_linear_bwd: nothing to compute");
+  SDT_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(wt) && aligned16(At) && aligned16(Bt) && aligned16(t_save) &&
+                  aligned16(dx) && aligned16(g_ws), SDT_ERR_ARG, "sdt_lora_linear_bwd: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SDT_BF16) {
+    if (r > 0)
+      SDT_REQUIRE(x && At && Bt && t_save && g_ws && dA && dB, SDT_ERR_ARG,
+                  "sdt_lora_linear_bwd: x, At, Bt, t_save, g_ws, dA, dB are required when r > 0");
+    SDT_REQUIRE(dx == nullptr || wt != nullptr, SDT_ERR_ARG, "sdt_lora_linear_bwd: wt is required for dX");
+    // G = s dY B ; dX = dY W + G A   -- the forward kernel with (dY, W^T, B^T, A^T)
+    int rc = lora_gemm_bf16(dy, wt, nullptr, Bt, At, scaling, dx, g_ws, M, /*contraction*/ N, /*outputs*/ K, r,
+                            dx != nullptr, st);
+    if (rc != SDT_OK || r == 0) return rc;
+    rc = lora_wgrad_bf16(x, g_ws, dA, M, K, r, r_true, /*transposed=*/true, st);     // dA[j,k] += sum_m G[m,j] X[m,k]
+    if (rc != SDT_OK) return rc;
+    return lora_wgrad_bf16(dy, t_save, dB, M, N, r, r_true, /*transposed=*/false, st);   // dB[n,j] += sum_m dY[m,n] Ts[m,j]
+  }
+  if (dtype == SDT_F32) {
+    SDT_REQUIRE(r_true == r, SDT_ERR_ARG, "sdt_lora_linear_bwd(f32): r_true must equal r");
+    return lora_bwd_f32((const float*)dy, (const float*)x, (const float*)wt, (const float*)At, (const float*)Bt,
+                        (const float*)t_save, scaling, (float*)dx, (float*)g_ws, dA, dB, M, K, N, r, st);
+  }
+  set_error("sdt_lora_linear_bwd: unsupported dtype %d (there is no fallback path)", dtype);
+  return SDT_ERR_UNSUPPORTED;
+}
+
+extern "C" int sdt_debug_set(int key, uint64_t value) {
+  debug_set(key, value);
+  return SDT_OK;
+}

@@ -1,0 +1,202 @@
+// K2 (dA, dB): LoRA weight gradients = reductions over the token dimension on the tensor cores.
+//
+//     dA[j,k] += sum_m G[m,j]  X[m,k]         (G = scaling * dY B, written by the dX kernel)
+//     dB[n,j] += sum_m dY[m,n] Ts[m,j]        (Ts = scaling * X A^T, saved by the forward)
+//
+// Both are C[f,j] = sum_m U[m,f] V[m,j] with U = X or dY ([M,F], token-major as it lies in HBM) and
+// V = G or Ts ([M,R]).  The contraction runs over rows, so both operands are "MN-major" for UMMA: the
+// TMA boxes are taken from U and V exactly as stored (no transposes anywhere) and the MMA reads them
+// through MN-major shared-memory descriptors.  A CTA owns a 128-feature block and one slice of the
+// token range; partial sums leave through f32 red.global.add (the outputs are tiny: F x r_true).
+//
+// HBM-bound by construction: every element of U is read once for R multiply-adds.
+#include "sdt_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace sdt {
+
+using namespace ptx;
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                      uint32_t box_rows, uint32_t box_cols, TmapSwizzle swz);
+
+template <int R_>
+struct WgradCfg {
+  static constexpr int R = R_, BF = 128, BMK = 64;          // 128 features x 64 tokens per stage
+  static constexpr int kStages = 6;
+  static constexpr int U_BYTES = BMK * BF * 2;              // two [64 x 64] boxes, 8 KiB each
+  static constexpr int V_BYTES = ((BMK * R * 2 + 1023) / 1024) * 1024;
+  static constexpr int STAGE_BYTES = U_BYTES + V_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + 256;
+  static constexpr int TMEM_COLS = R < 32 ? 32 : R;
+};
+
+struct WgradParams {
+  float* out;             // dA [r_true,F] (transposed = 1) or dB [F,r_true] (transposed = 0)
+  int M, F, r_true, transposed;
+  int rows_per_split;     // multiple of 64
+  // descriptors are host-built so that the layout constants live in one place (and can be probed)
+  uint64_t a_desc_base, b_desc_base;
+  uint32_t a_step, b_step, idesc;
+};
+
+template <int R>
+__global__ void __launch_bounds__(128, 1)
+lora_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v, const WgradParams p) {
+  using C = WgradCfg<R>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* done = bars + 2 * C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f0 = blockIdx.x * C::BF;
+  const int m_begin = blockIdx.y * p.rows_per_split;
+  const int m_end = min(m_begin + p.rows_per_split, p.M);
+  const int nk = (m_end - m_begin + C::BMK - 1) / C::BMK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_u);
+    prefetch_tmap(&tm_v);
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % C::kStages;
+        mbar_wait(&empty[s], ((kb / C::kStages) & 1) ^ 1);
+        uint8_t* st = smem + s * C::STAGE_BYTES;
+        const int m = m_begin + kb * C::BMK;
+        mbar_arrive_expect_tx(&full[s], C::U_BYTES + C::BMK * R * 2);
+        tma_load_2d(st, &tm_u, f0, m, &full[s]);                    // features f0 .. f0+63
+        tma_load_2d(st + C::U_BYTES / 2, &tm_u, f0 + 64, m, &full[s]);   // features f0+64 .. f0+127
+        tma_load_2d(st + C::U_BYTES, &tm_v, 0, m, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % C::kStages;
+      mbar_wait(&full[s], (kb / C::kStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t ua = smem_u32(smem + s * C::STAGE_BYTES);
+        const uint32_t va = ua + C::U_BYTES;
+#pragma unroll
+        for (int k = 0; k < C::BMK / 16; ++k)
+          umma_f16_ss(tmem_base, smem_desc(p.a_desc_base, ua + k * p.a_step), smem_desc(p.b_desc_base, va + k * p.b_step),
+                      p.idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  }
+
+  // ---- epilogue: all four warps, thread = feature row ----
+  if (nk > 0) {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int f = f0 + warp * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c = 0; c < R / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld_x16(taddr + c * 16, v);
+      tmem_ld_wait();
+      if (f < p.F) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int jj = c * 16 + j;
+          if (jj < p.r_true) {
+            float* dst = p.transposed ? p.out + (size_t)jj * p.F + f : p.out + (size_t)f * p.r_true + jj;
+            atomicAdd(dst, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// debug overrides (sdt_debug_set): lets the GPU tests probe descriptor hypotheses without a rebuild
+static uint64_t g_dbg[16] = {0};
+void debug_set(int key, uint64_t value) { if (key >= 0 && key < 16) g_dbg[key] = value; }
+uint64_t debug_get(int key) { return (key >= 0 && key < 16) ? g_dbg[key] : 0; }
+
+template <int R>
+static int launch_wgrad(const void* u, const void* v, float* out, int64_t M, int64_t F, int r_true, bool transposed,
+                        cudaStream_t st) {
+  using C = WgradCfg<R>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDT_CUDA_OK(cudaFuncSetAttribute(lora_wgrad_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tm_u, tm_v;
+  int rc = make_tmap_2d_bf16(&tm_u, u, M, F, F * 2, C::BMK, 64, TMAP_SW_128);
+  if (rc != SDT_OK) return rc;
+  rc = make_tmap_2d_bf16(&tm_v, v, M, R, (uint64_t)R * 2, C::BMK, R, R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
+  if (rc != SDT_OK) return rc;
+  WgradParams p;
+  p.out = out;
+  p.M = (int)M; p.F = (int)F; p.r_true = r_true; p.transposed = transposed ? 1 : 0;
+  const int f_blocks = (int)((F + C::BF - 1) / C::BF);
+  const int m_chunks = (int)((M + C::BMK - 1) / C::BMK);
+  // enough CTAs for ~3 per SM, but at least 8 stages of work each
+  int splits = (3 * num_sms() + f_blocks - 1) / f_blocks;
+  if (splits > (m_chunks + 7) / 8) splits = (m_chunks + 7) / 8;
+  if (splits < 1) splits = 1;
+  const int chunks_per_split = (m_chunks + splits - 1) / splits;
+  p.rows_per_split = chunks_per_split * C::BMK;
+  splits = (m_chunks + chunks_per_split - 1) / chunks_per_split;
+  // A = U tile, MN-major, 128B swizzle: 64-feature blocks 8 KiB apart (LBO), 8-token groups 1 KiB apart (SBO),
+  //     16 tokens per MMA -> 2 KiB per k-step
+  // B = V tile, MN-major, rows of R*2 bytes with the matching swizzle: 8-token groups 8*R*2 B apart (SBO)
+  const uint32_t vlayout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
+  p.a_desc_base = make_smem_desc_base(C::U_BYTES / 2, 1024, kLayoutSW128);
+  p.b_desc_base = make_smem_desc_base(8 * R * 2, 8 * R * 2, vlayout);
+  p.a_step = 16 * 128;
+  p.b_step = 16 * R * 2;
+  p.idesc = make_idesc_bf16(128, R, 1, 1);
+  if (g_dbg[0]) p.a_desc_base = g_dbg[1];
+  if (g_dbg[2]) p.b_desc_base = g_dbg[3];
+  if (g_dbg[4]) p.a_step = (uint32_t)g_dbg[5];
+  if (g_dbg[6]) p.b_step = (uint32_t)g_dbg[7];
+  if (g_dbg[8]) p.idesc = (uint32_t)g_dbg[9];
+  lora_wgrad_kernel<R><<<dim3(f_blocks, splits), 128, C::SMEM_BYTES, st>>>(tm_u, tm_v, p);
+  SDT_LAUNCH_OK("lora_wgrad");
+  return SDT_OK;
+}
+
+int lora_wgrad_bf16(const void* u, const void* v, float* out, int64_t M, int64_t F, int r, int r_true, bool transposed,
+                    cudaStream_t st) {
+  SDT_REQUIRE(u && v && out, SDT_ERR_ARG, "lora_wgrad: null pointer");
+  SDT_REQUIRE(M > 0 && F > 0 && F % 8 == 0, SDT_ERR_ARG, "lora_wgrad: bad sizes M=%lld F=%lld", (long long)M, (long long)F);
+  SDT_REQUIRE(r_true >= 1 && r_true <= r, SDT_ERR_ARG, "lora_wgrad: r_true=%d outside [1,%d]", r_true, r);
+  switch (r) {
+    case 16: return launch_wgrad<16>(u, v, out, M, F, r_true, transposed, st);
+    case 32: return launch_wgrad<32>(u, v, out, M, F, r_true, transposed, st);
+    case 64: return launch_wgrad<64>(u, v, out, M, F, r_true, transposed, st);
+  }
+  set_error("lora_wgrad: padded rank must be 16, 32 or 64 (got %d)", r);
+  return SDT_ERR_UNSUPPORTED;
+}
+
+}  // namespace sdt

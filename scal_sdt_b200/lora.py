@@ -1,0 +1,287 @@
+"""LoRA module injection -- drop-in for the reference's ``modules/lora.py``.
+
+``get_lora(module, rank, alpha, dropout)`` keeps the reference signature and the attribute contract
+(``modules/lora.py:12-27``): the returned module aliases the source module's frozen ``weight`` / ``bias``
+Parameter objects, owns trainable fp32 ``lora_A [r,in]`` (kaiming-uniform, a=sqrt 5) and ``lora_B [out,r]``
+(zeros), carries ``lora_alpha`` as an int32 buffer and lives on ``module.weight.device``.  ``scaling`` is
+``alpha / rank`` fixed at construction (loralib 0.1).
+
+The arithmetic ``y = x W^T + b + (alpha/r) (x A^T) B^T`` and its backward (dX, dA, dB; W, b frozen) run in
+``libsdt_b200.so``: one fused tcgen05/TMEM/TMA kernel per direction for bf16, FFMA kernels for fp32.  There is
+no torch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import PackSite, SdtError
+
+MAX_TC_RANK = 64
+
+
+def padded_rank(rank: int) -> int:
+    """Rank as seen by the tensor-core kernels (UMMA K granule is 16; supported 16 / 32 / 64)."""
+    for r in (16, 32, 64):
+        if rank <= r:
+            return r
+    raise SdtError(f"LoRA rank {rank} > {MAX_TC_RANK} is not supported by the bf16 tensor-core path")
+
+
+def _pack_sites(sites: list[PackSite], max_elems: int, device) -> torch.Tensor:
+    arr = (PackSite * len(sites))(*sites)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    dev = host.to(device, non_blocking=False)
+    _lib.check(_lib.load().sdt_lora_pack(dev.data_ptr(), len(sites), max_elems, _lib.stream_ptr()), "sdt_lora_pack")
+    # `dev` must outlive the launch: the caching allocator keeps stream order for us
+    return dev
+
+
+class PackedOperands:
+    """bf16 tensor-core operand layouts of one site: A_p [R,K], At_p [K,R], B_p [N,R], Bt_p [R,N]."""
+
+    def __init__(self, K: int, N: int, r_true: int, device, storage: Optional[torch.Tensor] = None):
+        self.K, self.N, self.r_true, self.R = K, N, r_true, padded_rank(r_true)
+        n = self.numel(K, N, r_true)
+        if storage is None:
+            storage = torch.zeros(n, dtype=torch.bfloat16, device=device)
+        assert storage.numel() == n and storage.dtype == torch.bfloat16
+        R = self.R
+        self.storage = storage
+        o = 0
+        self.A_p = storage[o:o + R * K].view(R, K); o += R * K
+        self.At_p = storage[o:o + K * R].view(K, R); o += K * R
+        self.B_p = storage[o:o + N * R].view(N, R); o += N * R
+        self.Bt_p = storage[o:o + R * N].view(R, N)
+        self.versions = (-1, -1)
+
+    @staticmethod
+    def numel(K: int, N: int, r_true: int) -> int:
+        return 2 * padded_rank(r_true) * (K + N)
+
+    def site(self, lora_A: torch.Tensor, lora_B: torch.Tensor) -> PackSite:
+        return PackSite(lora_A.data_ptr(), lora_B.data_ptr(), self.A_p.data_ptr(), self.At_p.data_ptr(),
+                        self.B_p.data_ptr(), self.Bt_p.data_ptr(), self.K, self.N, self.r_true, self.R)
+
+
+class _LoRAProjection(torch.autograd.Function):
+    """y[M,N] = x[M,K] W^T + b + s (x A^T) B^T through the C ABI; W and b are frozen (model.py:137)."""
+
+    @staticmethod
+    def forward(ctx, x2, lora_A, lora_B, mod):
+        lib = _lib.load()
+        M, K = x2.shape
+        N = mod.out_features
+        code = _lib.dtype_code(x2.dtype)
+        st = _lib.stream_ptr()
+        y = torch.empty(M, N, dtype=x2.dtype, device=x2.device)
+        if code == _lib.SDT_BF16:
+            ops = mod._packed_operands()
+            w = mod._weight_bf16()
+            t_save = torch.empty(M, ops.R, dtype=torch.bfloat16, device=x2.device)
+            _lib.check(lib.sdt_lora_linear_fwd(x2.data_ptr(), w.data_ptr(), _lib.ptr(mod._bias_f32()), ops.A_p.data_ptr(),
+                                               ops.B_p.data_ptr(), mod.scaling, y.data_ptr(), t_save.data_ptr(), M, K, N,
+                                               ops.R, code, st), "sdt_lora_linear_fwd")
+        else:
+            if mod.weight.dtype != torch.float32:
+                raise SdtError("fp32 activations need fp32 frozen weights")
+            r = mod.r
+            t_save = torch.empty(M, r, dtype=torch.float32, device=x2.device)
+            _lib.check(lib.sdt_lora_linear_fwd(x2.data_ptr(), mod.weight.data_ptr(), _lib.ptr(mod._bias_f32()),
+                                               lora_A.data_ptr(), lora_B.data_ptr(), mod.scaling, y.data_ptr(),
+                                               t_save.data_ptr(), M, K, N, r, code, st), "sdt_lora_linear_fwd")
+        ctx.mod = mod
+        ctx.code = code
+        ctx.need_dx = x2.requires_grad
+        ctx.need_w = lora_A.requires_grad or lora_B.requires_grad
+        ctx.save_for_backward(x2, t_save, lora_A, lora_B)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        mod = ctx.mod
+        x2, t_save, lora_A, lora_B = ctx.saved_tensors
+        M, K = x2.shape
+        N = mod.out_features
+        st = _lib.stream_ptr()
+        dy = dy.contiguous()
+        if dy.dtype != x2.dtype:
+            dy = dy.to(x2.dtype)
+        dx = torch.empty_like(x2) if ctx.need_dx else None
+        # gradient destinations: the flat arena when one is attached (no per-site copies), else fresh zeros
+        direct = mod._grad_A is not None
+        if direct:
+            dA, dB = mod._grad_A, mod._grad_B
+        else:
+            dA = torch.zeros(mod.r, K, dtype=torch.float32, device=x2.device)
+            dB = torch.zeros(N, mod.r, dtype=torch.float32, device=x2.device)
+        if ctx.code == _lib.SDT_BF16:
+            ops = mod._packed_operands()
+            wt = mod._weight_t_bf16() if ctx.need_dx else None
+            g_ws = torch.empty(M, ops.R, dtype=torch.bfloat16, device=x2.device)
+            _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), _lib.ptr(wt), ops.At_p.data_ptr(),
+                                               ops.Bt_p.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
+                                               g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, ops.R, mod.r,
+                                               ctx.code, st), "sdt_lora_linear_bwd")
+        else:
+            g_ws = torch.empty(M, mod.r, dtype=torch.float32, device=x2.device)
+            _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), mod.weight.data_ptr(), lora_A.data_ptr(),
+                                               lora_B.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
+                                               g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, mod.r, mod.r,
+                                               ctx.code, st), "sdt_lora_linear_bwd")
+        if direct:
+            return dx, None, None, None
+        return dx, dA, dB, None
+
+
+class _LoRABase(nn.Module):
+    """State shared by the Linear and 1x1-Conv2d LoRA modules."""
+
+    def _init_lora(self, in_features: int, out_features: int, rank: int, alpha, dropout: float):
+        if rank <= 0:
+            raise SdtError("LoRA rank must be positive")
+        self.in_features, self.out_features, self.r = in_features, out_features, rank
+        self.scaling = alpha / rank          # python float fixed at construction (loralib 0.1)
+        self.lora_dropout_p = float(dropout)
+        self.lora_A = nn.Parameter(torch.zeros(rank, in_features))
+        self.lora_B = nn.Parameter(torch.zeros(out_features, rank))
+        nn.init.kaiming_uniform_(self.lora_A, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_B)
+        # runtime caches (not state): bf16 copies of the frozen weight and the packed LoRA operands
+        self._w_cache = None
+        self._wt_cache = None
+        self._b_cache = None
+        self._ops: Optional[PackedOperands] = None
+        self._ops_external = False           # True when a LoraArena owns (and refreshes) the packed operands
+        self._grad_A = None
+        self._grad_B = None
+
+    # ---- frozen operand caches ------------------------------------------------------------------
+    def _weight_2d(self) -> torch.Tensor:
+        return self.weight.view(self.out_features, self.in_features)
+
+    def _weight_bf16(self) -> torch.Tensor:
+        w = self.weight
+        key = (w.data_ptr(), w._version)
+        if self._w_cache is None or self._w_cache[0] != key:
+            self._w_cache = (key, self._weight_2d().detach().to(torch.bfloat16).contiguous())
+        return self._w_cache[1]
+
+    def _weight_t_bf16(self) -> torch.Tensor:
+        w = self.weight
+        key = (w.data_ptr(), w._version)
+        if self._wt_cache is None or self._wt_cache[0] != key:
+            self._wt_cache = (key, self._weight_2d().detach().to(torch.bfloat16).t().contiguous())
+        return self._wt_cache[1]
+
+    def _bias_f32(self) -> Optional[torch.Tensor]:
+        b = self.bias
+        if b is None:
+            return None
+        if b.dtype == torch.float32:
+            return b.detach()
+        key = (b.data_ptr(), b._version)
+        if self._b_cache is None or self._b_cache[0] != key:
+            self._b_cache = (key, b.detach().float())
+        return self._b_cache[1]
+
+    def _packed_operands(self) -> PackedOperands:
+        if self._ops_external:
+            return self._ops       # refreshed by LoraArena.pack() after every optimizer step
+        A, B = self.lora_A, self.lora_B
+        if self._ops is None or self._ops.storage.device != A.device:
+            self._ops = PackedOperands(self.in_features, self.out_features, self.r, A.device)
+        ver = (A._version, B._version)
+        if self._ops.versions != ver:
+            _pack_sites([self._ops.site(A.detach(), B.detach())], self._ops.R * (self.in_features + self.out_features), A.device)
+            self._ops.versions = ver
+        return self._ops
+
+    def _project(self, x2: torch.Tensor) -> torch.Tensor:
+        _lib.require_cuda(x2, self.weight, self.lora_A)
+        _lib.device_check()
+        if self.training and self.lora_dropout_p > 0.0:
+            raise SdtError("lora dropout > 0 is not implemented in the fused kernel (every shipped optim_target uses 0.)")
+        if torch.is_autocast_enabled():
+            x2 = x2.to(torch.get_autocast_dtype("cuda"))
+        if x2.dtype == torch.float16:
+            raise SdtError("fp16 is not implemented: use bf16 (trainer.precision=bf16) or fp32")
+        return _LoRAProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self)
+
+    def extra_repr(self) -> str:
+        return f"in={self.in_features}, out={self.out_features}, r={self.r}, scaling={self.scaling}"
+
+
+class LoRALinear(_LoRABase):
+    """Replacement for ``loralib.Linear`` as adapted by ``get_lora`` (``modules/lora.py:13-14``)."""
+
+    def __init__(self, in_features: int, out_features: int, rank=4, alpha=1, dropout=0.0):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_features, in_features), requires_grad=False)
+        self.bias = None
+        self._init_lora(in_features, out_features, rank, alpha, dropout)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lead = x.shape[:-1]
+        y = self._project(x.reshape(-1, self.in_features))
+        return y.view(*lead, self.out_features)
+
+
+class LoRAConv2d(_LoRABase):
+    """Replacement for ``loralib.Conv2d`` with ``kernel_size == 1`` (``modules/lora.py:15-16``), the shape of
+    SD1.x ``proj_in`` / ``proj_out``.  loralib materialises ``W + s (B A).view(W.shape)`` and convolves with default
+    stride / padding; for a 1x1 kernel that is the same projection applied per pixel, so the channels-last token
+    matrix goes through the same fused kernel and the result is returned as an NCHW tensor in channels-last memory.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int, rank=4, alpha=1, dropout=0.0):
+        super().__init__()
+        if kernel_size != 1:
+            raise SdtError(f"LoRA Conv2d with kernel_size={kernel_size} is not implemented (SD proj_in/proj_out are 1x1)")
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, 1, 1), requires_grad=False)
+        self.bias = None
+        self._init_lora(in_channels, out_channels, rank, alpha, dropout)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        b, c, h, w = x.shape
+        tokens = x.permute(0, 2, 3, 1).reshape(b * h * w, c)        # a view when x is channels-last
+        y = self._project(tokens)
+        return y.view(b, h, w, self.out_channels).permute(0, 3, 1, 2)
+
+
+def get_lora(module: nn.Linear | nn.Conv2d, rank=4, alpha=1, dropout=0.):
+    """``modules/lora.py:12-27`` with the CUDA-backed modules in place of loralib's."""
+    if isinstance(module, nn.Linear):
+        lora = LoRALinear(module.in_features, module.out_features, rank, alpha, dropout)
+    elif isinstance(module, nn.Conv2d):
+        lora = LoRAConv2d(module.in_channels, module.out_channels, module.kernel_size[0], rank, alpha, dropout)
+    else:
+        raise Exception("Unexpected module type")
+
+    lora.weight = module.weight
+    lora.bias = module.bias
+    lora.lora_A.requires_grad = True
+    lora.lora_B.requires_grad = True
+    lora.register_buffer("lora_alpha", torch.tensor(alpha, dtype=torch.int32))
+
+    return lora.to(module.weight.device)
+
+
+def get_linears(module: nn.Module):
+    """``modules/lora.py:6-9`` (unused by the reference; kept for API completeness)."""
+    for name, sub in module.named_children():
+        if isinstance(sub, nn.Linear):
+            yield name, sub
+
+
+def lora_modules(module: nn.Module):
+    for name, sub in module.named_modules():
+        if isinstance(sub, _LoRABase):
+            yield name, sub

@@ -1,0 +1,182 @@
+"""GPU parity: noising / target / loss / EMA / AdamW kernels through the C ABI vs the CPU oracle.
+fp32 results are bit-exact (the kernels reproduce torch's op-by-op rounding); bf16 likewise."""
+import pytest
+import torch
+
+from oracle import diffusion_ref, ema_ref
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _inputs(B, C, H, W, dtype, seed=114514):
+    g = torch.Generator().manual_seed(seed)
+    x0 = torch.randn(B, C, H, W, generator=g).to(dtype)
+    eps = torch.randn(B, C, H, W, generator=g).to(dtype)
+    t = torch.randint(0, 1000, (B,), generator=g, dtype=torch.int64)
+    return x0, eps, t
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(8, 4, 64, 64), (2, 4, 96, 128), (3, 4, 5, 7), (1, 4, 64, 64)])
+@pytest.mark.parametrize("ptype", ["epsilon", "sample", "v"])
+def test_noise_target_bit_exact(sdt_lib, dtype, shape, ptype):
+    from scal_sdt_b200 import NoiseScheduler
+    x0, eps, t = _inputs(*shape, dtype)
+    sched = NoiseScheduler(prediction_type=ptype)
+    noisy, target = sched.noise_and_target(x0.to(DEV), eps.to(DEV), t.to(DEV), check_range=True)
+    ac = diffusion_ref.ref_alphas_cumprod()
+    assert torch.equal(ac, sched.alphas_cumprod)
+    ref_noisy = diffusion_ref.ref_add_noise(ac, x0, eps, t)
+    ref_target = diffusion_ref.ref_target(ptype, ac, x0, eps, t)
+    assert torch.equal(noisy.cpu(), ref_noisy)
+    assert torch.equal(target.cpu(), ref_target)
+
+
+def test_noise_target_extreme_timesteps_and_oob(sdt_lib):
+    from scal_sdt_b200 import NoiseScheduler
+    x0, eps, _ = _inputs(4, 4, 8, 8, torch.float32)
+    t = torch.tensor([0, 999, 500, 1], dtype=torch.int64)
+    sched = NoiseScheduler(prediction_type="v")
+    noisy, v = sched.noise_and_target(x0.to(DEV), eps.to(DEV), t.to(DEV), check_range=True)
+    ac = diffusion_ref.ref_alphas_cumprod()
+    assert torch.equal(noisy.cpu(), diffusion_ref.ref_add_noise(ac, x0, eps, t))
+    assert torch.equal(v.cpu(), diffusion_ref.ref_get_velocity(ac, x0, eps, t))
+    with pytest.raises(IndexError):
+        sched.noise_and_target(x0.to(DEV), eps.to(DEV), torch.tensor([0, 1000, 1, 2]).to(DEV), check_range=True)
+    with pytest.raises(Exception, match="Unknown prediction type"):
+        sched.noise_and_target(x0.to(DEV), eps.to(DEV), t.to(DEV), prediction_type="v_prediction")
+
+
+@pytest.mark.parametrize("pdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(8, 4, 64, 64), (4, 4, 96, 128), (2, 3, 5, 7)])
+@pytest.mark.parametrize("prior", [False, True])
+def test_mse_loss_and_grad(sdt_lib, pdtype, shape, prior):
+    from scal_sdt_b200 import DenoiseLoss
+    g = torch.Generator().manual_seed(1)
+    pred = torch.randn(*shape, generator=g).to(pdtype)
+    target = torch.randn(*shape, generator=g)
+    crit = DenoiseLoss(DEV, prior_preservation=prior, prior_loss_weight=0.7)
+    p = pred.to(DEV).requires_grad_(True)
+    loss, elem = crit(p, target.to(DEV), want_elementwise=True)
+    loss.backward()
+    # oracle (fp64 arbiter for the scalar; fp32 elementwise bit-exact)
+    pr = pred.clone().float().requires_grad_(True)
+    ref_elem = diffusion_ref.ref_elementwise_loss(pr, target)
+    ref_loss = diffusion_ref.ref_reduce_loss(ref_elem, prior, 0.7)
+    ref_loss.backward()
+    assert torch.equal(elem.cpu(), ref_elem.detach())
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    tol = 1e-5 if pdtype == torch.float32 else 2e-2
+    gr, rr = p.grad.float().cpu(), pr.grad
+    assert (gr - rr).norm() <= tol * rr.norm()
+    crit.raise_if_nan()
+
+
+def test_mse_nan_guard(sdt_lib):
+    from scal_sdt_b200 import DenoiseLoss
+    crit = DenoiseLoss(DEV)
+    p = torch.randn(2, 4, 8, 8, device=DEV)
+    p[1, 2, 3, 4] = float("nan")
+    crit(p, torch.zeros_like(p))
+    with pytest.raises(Exception, match="NaN element discovered in loss"):
+        crit.raise_if_nan()
+
+
+def _mlp(seed=0):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Linear(33, 65), torch.nn.GELU(), torch.nn.Linear(65, 17), torch.nn.LayerNorm(17))
+
+
+def test_ema_multi_tensor_bit_exact(sdt_lib):
+    from scal_sdt_b200 import ExponentialMovingAverage
+    m_ref, m_gpu = _mlp(), _mlp().to(DEV)
+    ref = ema_ref.RefEMA(m_ref, 0.995)
+    ema = ExponentialMovingAverage(m_gpu, 0.995)
+    g = torch.Generator().manual_seed(3)
+    for step in range(12):
+        with torch.no_grad():
+            for pr, pg in zip(m_ref.parameters(), m_gpu.parameters()):
+                d = torch.randn(pr.shape, generator=g) * 0.1
+                pr.add_(d)
+                pg.add_(d.to(DEV))
+        ref.update()
+        ema.update()
+        assert ema.num_updates == ref.num_updates
+    for name, s in ref.shadow_params.items():
+        assert torch.equal(ema.shadow_params[name].cpu(), s), name
+    sd = ema.state_dict()
+    assert set(sd) == {"decay", "num_updates", "shadow_params"} and sd["num_updates"] == 12
+
+
+def test_ema_partially_frozen_and_flat_arena(sdt_lib):
+    """LoRA-like: only some parameters train (the reference's own class raises KeyError here)."""
+    from scal_sdt_b200 import ExponentialMovingAverage, ParamArena
+    m_ref, m_gpu = _mlp(1), _mlp(1).to(DEV)
+    for m in (m_ref, m_gpu):
+        m[0].weight.requires_grad_(False)
+        m[3].bias.requires_grad_(False)
+    arena = ParamArena([{"params": [p for p in m_gpu.parameters() if p.requires_grad]}])
+    ref = ema_ref.RefEMA(m_ref, 0.9)
+    ema = ExponentialMovingAverage(m_gpu, 0.9)
+    assert ema._flat is not None
+    g = torch.Generator().manual_seed(4)
+    for _ in range(5):
+        with torch.no_grad():
+            for pr, pg in zip(m_ref.parameters(), m_gpu.parameters()):
+                if pr.requires_grad:
+                    d = torch.randn(pr.shape, generator=g)
+                    pr.add_(d)
+                    pg.add_(d.to(DEV))
+        ref.update()
+        ema.update()
+    assert set(ema.shadow_params) == set(ref.shadow_params)
+    for name, s in ref.shadow_params.items():
+        assert torch.equal(ema.shadow_params[name].cpu(), s), name
+    with ema.average_parameters():
+        for (n, p) in m_gpu.named_parameters():
+            if n in ema.shadow_params:
+                assert torch.equal(p, ema.shadow_params[n])
+    assert arena.numel >= sum(p.numel() for p in m_gpu.parameters() if p.requires_grad)
+
+
+def test_ema_large_flat_bf16_and_f32(sdt_lib):
+    from scal_sdt_b200 import _lib
+    lib = _lib.load()
+    for dtype, code in ((torch.float32, 0), (torch.bfloat16, 1)):
+        n = 3 * 1024 * 1024 + 5
+        g = torch.Generator().manual_seed(7)
+        s = torch.randn(n, generator=g).to(dtype)
+        p = torch.randn(n, generator=g).to(dtype)
+        sd, pd = s.to(DEV), p.to(DEV)
+        omd = 1.0 - 0.995
+        _lib.check(lib.sdt_ema_update_flat(sd.data_ptr(), pd.data_ptr(), n, omd, None, code, 0))
+        torch.cuda.synchronize()
+        tmp = s - p
+        tmp.mul_(omd)
+        s.sub_(tmp)
+        assert torch.equal(sd.cpu(), s)
+
+
+def test_flat_adamw_matches_torch(sdt_lib):
+    from scal_sdt_b200 import FlatAdamW, ParamArena
+    m_ref, m_gpu = _mlp(2), _mlp(2).to(DEV)
+    groups_ref = [{"params": list(m_ref[0].parameters()), "lr": 5e-4, "weight_decay": 2e-2},
+                  {"params": list(m_ref[2].parameters()) + list(m_ref[3].parameters()), "lr": 5e-3, "weight_decay": 2e-3}]
+    groups_gpu = [{"params": list(m_gpu[0].parameters()), "lr": 5e-4, "weight_decay": 2e-2},
+                  {"params": list(m_gpu[2].parameters()) + list(m_gpu[3].parameters()), "lr": 5e-3, "weight_decay": 2e-3}]
+    opt_ref = torch.optim.AdamW(groups_ref, lr=1e-3, betas=(0.9, 0.999), eps=1e-7, weight_decay=1e-2)
+    arena = ParamArena(groups_gpu)
+    opt = FlatAdamW(arena, lr=1e-3, betas=(0.9, 0.999), eps=1e-7, weight_decay=1e-2)
+    g = torch.Generator().manual_seed(5)
+    for _ in range(10):
+        for pr, pg in zip(m_ref.parameters(), m_gpu.parameters()):
+            gr = torch.randn(pr.shape, generator=g)
+            pr.grad = gr.clone()
+            pg.grad.copy_(gr.to(DEV))
+        opt_ref.step()
+        opt.step()
+    for (n, pr), pg in zip(m_ref.named_parameters(), m_gpu.parameters()):
+        err = (pg.cpu() - pr).abs().max().item()
+        assert err <= 2e-6 * max(1.0, pr.abs().max().item()), (n, err)

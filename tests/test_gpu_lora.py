@@ -1,0 +1,130 @@
+"""GPU parity of the LoRA projection (K1 forward, K2 backward) through the C ABI and through ``get_lora``.
+
+Tolerances are the ones north_star states: 1e-5 relative for fp32, 2e-2 for bf16, on outputs and LoRA gradients,
+measured as ||ours - ref||_F / ||ref||_F against the oracle (``oracle/lora_ref.py``) evaluated in fp64/fp32 on the
+same (bf16-rounded, for the bf16 case) inputs.  lora_B is non-zero, otherwise dA and the LoRA part of dX vanish."""
+import pytest
+import torch
+from torch import nn
+
+from oracle import lora_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-300)).item()
+
+
+def make_pair(kind, cin, cout, rank, alpha, bias, seed, dtype):
+    """(reference module on CPU, ours on GPU) with identical frozen weights and non-zero LoRA factors."""
+    torch.manual_seed(seed)
+    base = nn.Linear(cin, cout, bias=bias) if kind == "linear" else nn.Conv2d(cin, cout, 1, bias=bias)
+    ref = lora_ref.ref_get_lora(base, rank, alpha)
+    with torch.no_grad():
+        ref.lora_B.normal_(0, 0.2)
+    import copy
+    from scal_sdt_b200 import get_lora
+    base_gpu = copy.deepcopy(base).to(DEV)
+    base_gpu.requires_grad_(False)
+    ours = get_lora(base_gpu, rank, alpha)
+    with torch.no_grad():
+        ours.lora_A.copy_(ref.lora_A)
+        ours.lora_B.copy_(ref.lora_B)
+    if dtype == torch.bfloat16:      # compare on identical (bf16-representable) operands
+        with torch.no_grad():
+            for m in (ref, ours):
+                m.weight.copy_(m.weight.bfloat16().float())
+                m.lora_A.copy_(m.lora_A.bfloat16().float())
+                m.lora_B.copy_(m.lora_B.bfloat16().float())
+    return ref.double(), ours
+
+
+CASES = [
+    # kind, shape of x, cin, cout, rank, alpha, bias
+    ("linear", (2, 77, 768), 768, 320, 4, 1, False),       # cross-attention to_k, SD1.5, rank 4 (cfg1)
+    ("linear", (2, 256, 320), 320, 320, 16, 1, True),      # to_out.0 rank 16 (cfg2)
+    ("linear", (1, 1000, 640), 640, 5120, 16, 8, True),    # ff.net.0.proj, ragged M
+    ("linear", (2, 64, 1280), 1280, 1280, 64, 64, False),  # rank 64 (cfg3)
+    ("linear", (3, 50, 1024), 1024, 640, 32, 16, False),   # SD2.x-shaped context, BN=128 path
+    ("conv", (2, 320, 16, 16), 320, 320, 16, 1, True),     # proj_in 1x1 conv
+]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 2e-2), (torch.float32, 1e-5)])
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-{c[2]}x{c[3]}-r{c[4]}" for c in CASES])
+def test_get_lora_forward_backward(sdt_lib, case, dtype, tol):
+    kind, xshape, cin, cout, rank, alpha, bias = case
+    ref, ours = make_pair(kind, cin, cout, rank, alpha, bias, 7, dtype)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(*xshape, generator=g).to(dtype).float()
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    dy = torch.randn(yr.shape, generator=g).to(dtype).float()
+    yr.backward(dy.double())
+    xo = x.to(DEV).to(dtype).requires_grad_(True)
+    yo = ours(xo)
+    assert yo.shape == yr.shape and yo.dtype == dtype
+    yo.backward(dy.to(DEV).to(dtype))
+    assert rel(yo, yr) <= tol, ("y", rel(yo, yr))
+    assert rel(xo.grad, xr.grad) <= tol, ("dx", rel(xo.grad, xr.grad))
+    assert rel(ours.lora_A.grad, ref.lora_A.grad) <= tol, ("dA", rel(ours.lora_A.grad, ref.lora_A.grad))
+    assert rel(ours.lora_B.grad, ref.lora_B.grad) <= tol, ("dB", rel(ours.lora_B.grad, ref.lora_B.grad))
+    assert ours.weight.grad is None and (ours.bias is None or ours.bias.grad is None)
+
+
+def test_get_lora_contract(sdt_lib):
+    """Attribute / state-dict contract of modules/lora.py:12-27."""
+    from scal_sdt_b200 import get_lora
+    base = nn.Linear(64, 32).to(DEV)
+    m = get_lora(base, rank=4, alpha=2)
+    assert m.weight is base.weight and m.bias is base.bias
+    assert m.lora_A.shape == (4, 64) and m.lora_B.shape == (32, 4)
+    assert m.lora_A.requires_grad and m.lora_B.requires_grad and m.lora_A.dtype == torch.float32
+    assert m.lora_alpha.dtype == torch.int32 and int(m.lora_alpha) == 2 and m.scaling == 0.5
+    assert torch.count_nonzero(m.lora_B) == 0 and m.lora_A.abs().max() <= 1 / 8 + 1e-6
+    assert set(m.state_dict()) == {"weight", "bias", "lora_A", "lora_B", "lora_alpha"}
+    assert m.lora_A.device == base.weight.device
+    with pytest.raises(Exception, match="Unexpected module type"):
+        get_lora(nn.LayerNorm(8))
+
+
+def test_zero_init_lora_equals_base(sdt_lib):
+    """With lora_B = 0 (the reference's init) the injected module reproduces the frozen projection."""
+    from scal_sdt_b200 import get_lora
+    torch.manual_seed(0)
+    base = nn.Linear(320, 640).to(DEV).to(torch.bfloat16)
+    m = get_lora(base, rank=16, alpha=1)
+    x = torch.randn(4, 100, 320, device=DEV, dtype=torch.bfloat16)
+    y = m(x)
+    ref = torch.nn.functional.linear(x.float(), base.weight.float(), base.bias.float())
+    assert rel(y, ref) <= 4e-3      # one bf16 rounding of the output
+
+
+def test_arena_direct_gradients_and_pack(sdt_lib):
+    """LoraArena: backward accumulates straight into the flat gradient arena; pack() refreshes bf16 operands."""
+    from scal_sdt_b200 import FlatAdamW, LoraArena, config_module
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(64, 128), nn.GELU(), nn.Linear(128, 64)).to(DEV)
+    groups = config_module(net, [{"index": ["0", "2"], "lora": {"rank": 8, "alpha": 4}, "optimizer": {"lr": 1e-2}}])
+    arena = LoraArena(net, groups)
+    with torch.no_grad():
+        for _, m in arena.sites:
+            m.lora_B.normal_(0, 0.1)
+    arena.pack()
+    opt = FlatAdamW(arena, lr=1e-3)
+    x = torch.randn(32, 64, device=DEV, dtype=torch.bfloat16)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        y = net(x)
+        loss = y.float().pow(2).mean()
+        loss.backward()
+        assert net[0].lora_A.grad.data_ptr() == arena.grad_view(net[0].lora_A).data_ptr()
+        assert arena.grads.abs().sum() > 0
+        opt.step()
+        arena.pack()
+        losses.append(loss.item())
+    assert losses[2] < losses[0]
