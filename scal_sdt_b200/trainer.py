@@ -1,0 +1,146 @@
+"""Training step of the hot path -- the shape of ``LatentDiffusionModel.training_step`` /
+``_denoise_loss`` / ``on_train_batch_end`` (``modules/model.py:289-348,399-412``) without Lightning.
+
+``LatentDiffusionTrainer`` owns: the UNet with injected LoRA modules, the flat parameter/gradient arena, the fused
+AdamW(+EMA) step, the noising / loss kernels and the data-parallel gradient exchange.  One optimisation step is
+
+    noise_and_target (1 launch) -> UNet forward (LoRA sites: 1 fused launch each) -> mse_loss (1 launch, emits dPred)
+    -> backward (LoRA sites: dX + dA + dB launches) -> all-reduce of the gradient arena (1 NCCL call)
+    -> AdamW + EMA over the arena (1 launch per hyper-parameter group) -> repack bf16 LoRA operands (1 launch)
+
+and involves no host synchronisation: the loss value and the NaN flag stay on the device until asked for.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Optional
+
+import torch
+from torch import nn
+
+from .arena import LoraArena, ParamArena
+from .comm import GradExchange
+from .diffusion import DenoiseLoss, NoiseScheduler
+from .ema import ExponentialMovingAverage
+from .lora import lora_modules
+from .module_config import config_module, freeze_permanently
+from .optim import FlatAdamW
+
+
+def scale_lr(param_groups: list[dict], defaults: dict, batch_size: int, devices: int, nodes: int = 1, accumulate: int = 1,
+             method: str = "sqrt") -> float:
+    """``get_optimizer`` LR auto-scale (``modules/model.py:44-62``): lr *= c, weight_decay /= c,
+    c = accumulate * batch * nodes * devices (sqrt of it for ``method == 'sqrt'``)."""
+    coeff = accumulate * batch_size * nodes * devices
+    if method == "sqrt":
+        coeff = math.sqrt(coeff)
+    elif method != "linear":
+        raise ValueError(method)
+    for g in param_groups:
+        if "lr" in g:
+            g["lr"] *= coeff
+        if "weight_decay" in g:
+            g["weight_decay"] /= coeff
+    return coeff
+
+
+class LatentDiffusionTrainer:
+    def __init__(self, unet: nn.Module, scheduler: NoiseScheduler, unet_targets: Optional[list] = None, *,
+                 optimizer_params: Optional[dict] = None, lr_scale: Optional[dict] = None, batch_size: int = 1,
+                 prior_preservation: Optional[dict] = None, ema: Optional[dict] = None,
+                 exchange: Optional[GradExchange] = None, seed: Optional[int] = None):
+        self.unet = unet
+        self.scheduler = scheduler
+        self.exchange = exchange or GradExchange(0, 1)
+        self.device = next(unet.parameters()).device
+        # ---- module injection / target selection (model.py:224-242) ----
+        if unet_targets is not None:
+            param_groups = config_module(unet, unet_targets)
+        else:
+            param_groups = [{"params": [p for p in unet.parameters() if p.requires_grad]}]
+        if not any(len(g["params"]) for g in param_groups):
+            freeze_permanently(unet)
+            raise ValueError("no trainable parameters selected")
+        self.param_groups_config = param_groups
+        has_lora = any(True for _ in lora_modules(unet))
+        self.arena: ParamArena = LoraArena(unet, param_groups) if has_lora else ParamArena(param_groups)
+        # ---- optimizer (model.py:33-64) ----
+        op = dict(optimizer_params or {"lr": 5e-4, "beta1": 0.9, "beta2": 0.999, "weight_decay": 2e-2, "eps": 1e-7})
+        betas = (op.pop("beta1", 0.9), op.pop("beta2", 0.999))
+        self.optimizer = FlatAdamW(self.arena, lr=op.get("lr", 1e-3), betas=op.get("betas", betas), eps=op.get("eps", 1e-8),
+                                   weight_decay=op.get("weight_decay", 1e-2))
+        if lr_scale and lr_scale.get("enabled", False):
+            scale_lr(self.optimizer.param_groups, self.optimizer.defaults, batch_size, self.exchange.world,
+                     method=lr_scale.get("method", "sqrt"))
+        # ---- loss / EMA ----
+        pp = prior_preservation or {}
+        self.criterion = DenoiseLoss(self.device, bool(pp.get("enabled", False)), float(pp.get("prior_loss_weight", 1.0)))
+        self.unet_ema: Optional[ExponentialMovingAverage] = None
+        if ema and ema.get("enabled", False):
+            # the reference keeps EMA on global rank 0 only (model.py:399-401); parameters are identical on every rank
+            # after the step, so computing it everywhere is equivalent and keeps ranks symmetric
+            self.unet_ema = ExponentialMovingAverage(unet, float(ema.get("decay", 0.995)))
+        self.generator = torch.Generator(device=self.device)
+        if seed is not None:
+            self.generator.manual_seed(seed + self.exchange.rank)
+        self.global_step = 0
+
+    # ---- modules/model.py:289-316 ----------------------------------------------------------------------
+    def _denoise_loss(self, latents, conds, noise=None, timesteps=None, want_elementwise=False):
+        if noise is None:
+            noise = torch.randn(latents.shape, dtype=latents.dtype, device=latents.device, generator=self.generator)
+        if timesteps is None:
+            timesteps = torch.randint(0, self.scheduler.config.num_train_timesteps, (latents.shape[0],), dtype=torch.int64,
+                                      device=latents.device, generator=self.generator)
+        noisy, target = self.scheduler.noise_and_target(latents, noise, timesteps)
+        pred = self.unet(noisy, timesteps, conds).sample
+        return self.criterion(pred.contiguous(), target, want_elementwise=want_elementwise)
+
+    # ---- modules/model.py:318-348 ----------------------------------------------------------------------
+    def training_step(self, batch: dict, batch_idx: int = 0, noise=None, timesteps=None) -> torch.Tensor:
+        if "latents" not in batch or "conds" not in batch:
+            raise NotImplementedError("this path consumes cached latents/conds (the VAE / text encoder are out of scope)")
+        return self._denoise_loss(batch["latents"], batch["conds"], noise, timesteps)
+
+    def optimizer_step(self) -> None:
+        self.exchange.all_reduce_mean_(self.arena.grads)
+        if self.unet_ema is not None and self.unet_ema._shadow_flat is not None:
+            ema = self.unet_ema
+            if ema.num_updates is not None:
+                ema.num_updates += 1
+            self.optimizer.step(ema_shadow=ema._shadow_flat, ema_one_minus_decay=ema.current_one_minus_decay())
+        else:
+            self.optimizer.step()
+            if self.unet_ema is not None:
+                self.unet_ema.update()
+        if isinstance(self.arena, LoraArena):
+            self.arena.pack()
+
+    def step(self, batch: dict, noise=None, timesteps=None) -> torch.Tensor:
+        """zero_grad -> training_step -> backward -> exchange -> optimizer (+EMA) -> repack.  Returns the loss tensor
+        (device resident; call ``.item()`` only when logging)."""
+        self.optimizer.zero_grad()
+        loss = self.training_step(batch, self.global_step, noise, timesteps)
+        loss.backward()
+        self.optimizer_step()
+        self.global_step += 1
+        return loss
+
+    # ---- modules/model.py:378-397 ----------------------------------------------------------------------
+    def checkpoint_state_dict(self) -> dict[str, Any]:
+        """Trainable-only state dict with the reference's keys (``unet.<path>.lora_A`` ..., plus ``unet_ema``)."""
+        sd: dict[str, Any] = {f"unet.{n}": p.detach() for n, p in self.unet.named_parameters() if p.requires_grad}
+        if self.unet_ema is not None:
+            sd["unet_ema"] = self.unet_ema.state_dict()
+        return sd
+
+    def load_checkpoint_state_dict(self, sd: dict) -> None:
+        if self.unet_ema is not None and "unet_ema" in sd:
+            self.unet_ema.load_state_dict(sd["unet_ema"])
+        own = dict(self.unet.named_parameters())
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k.startswith("unet.") and k[5:] in own:
+                    own[k[5:]].copy_(v)
+        if isinstance(self.arena, LoraArena):
+            self.arena.pack()
