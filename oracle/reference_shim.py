@@ -114,7 +114,9 @@ def load_reference_samplers():
     import copy
     import random
 
-    from torch.utils.data import Sampler
+    class Sampler:  # torch >= 2.x Sampler.__init__ no longer accepts data_source; the reference passes it
+        def __init__(self, *args, **kwargs):
+            pass
 
     bucket = load_reference_bucket()
     tree = ast.parse((REFERENCE_ROOT / "modules" / "dataset" / "samplers.py").read_text())
