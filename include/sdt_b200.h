@@ -40,6 +40,8 @@ int         sdt_version(void);
 const char* sdt_last_error(void);
 /* 0 when the current device is compute capability 10.x (B200), else SDT_ERR_UNSUPPORTED */
 int         sdt_device_check(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches) */
+long long   sdt_launch_count(void);
 
 /* ---- K1: fused LoRA projection, forward ---------------------------------------------------
  * Replaces loralib.Linear.forward reached through get_lora (modules/lora.py:12-14):

@@ -33,6 +33,7 @@ SIGNATURES = {
     "sdt_version": (c_int, []),
     "sdt_last_error": (c_char_p, []),
     "sdt_device_check": (c_int, []),
+    "sdt_launch_count": (ctypes.c_longlong, []),
     "sdt_lora_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sdt_lora_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,

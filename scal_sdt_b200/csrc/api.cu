@@ -1,6 +1,7 @@
 // Library-wide state of libsdt_b200.so: thread-local error message, device queries.
 #include "sdt_common.cuh"
 
+#include <atomic>
 #include <mutex>
 
 namespace sdt {
@@ -13,6 +14,10 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached[64];
@@ -31,6 +36,8 @@ int num_sms() {
 }  // namespace sdt
 
 extern "C" int sdt_version(void) { return 100; }  // round 1
+
+extern "C" long long sdt_launch_count(void) { return sdt::launch_count(); }
 
 extern "C" const char* sdt_last_error(void) { return sdt::g_err; }
 

@@ -11,6 +11,7 @@
 namespace sdt {
 
 void set_error(const char* fmt, ...);   // defined in api.cu (thread-local message)
+void count_launch();                    // api.cu: process-wide count of kernels this library launched
 
 #define SDT_REQUIRE(cond, code, ...)                      \
   do {                                                    \
@@ -39,6 +40,7 @@ void set_error(const char* fmt, ...);   // defined in api.cu (thread-local messa
       ::sdt::set_error("launch of %s failed: %s", what, cudaGetErrorString(_e));            \
       return SDT_ERR_CUDA;                                                                  \
     }                                                                                       \
+    ::sdt::count_launch();                                                                  \
   } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -24,6 +24,16 @@ from ._lib import PackSite, SdtError
 
 MAX_TC_RANK = 64
 
+# bench.py sets this to a list to time every projection launch with CUDA events on the launching stream:
+# records are (kind, M, K, N, R, [need_dx,] start_event, end_event)
+PROFILE = None
+
+
+def _ev():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
 
 def padded_rank(rank: int) -> int:
     """Rank as seen by the tensor-core kernels (UMMA K granule is 16; supported 16 / 32 / 64)."""
@@ -80,10 +90,13 @@ class _LoRAProjection(torch.autograd.Function):
         code = _lib.dtype_code(x2.dtype)
         st = _lib.stream_ptr()
         y = torch.empty(M, N, dtype=x2.dtype, device=x2.device)
+        ev0 = None
         if code == _lib.SDT_BF16:
             ops = mod._packed_operands()
             w = mod._weight_bf16()
             t_save = torch.empty(M, ops.R, dtype=torch.bfloat16, device=x2.device)
+            if PROFILE is not None:
+                ev0 = _ev()
             _lib.check(lib.sdt_lora_linear_fwd(x2.data_ptr(), w.data_ptr(), _lib.ptr(mod._bias_f32()), ops.A_p.data_ptr(),
                                                ops.B_p.data_ptr(), mod.scaling, y.data_ptr(), t_save.data_ptr(), M, K, N,
                                                ops.R, code, st), "sdt_lora_linear_fwd")
@@ -95,6 +108,8 @@ class _LoRAProjection(torch.autograd.Function):
             _lib.check(lib.sdt_lora_linear_fwd(x2.data_ptr(), mod.weight.data_ptr(), _lib.ptr(mod._bias_f32()),
                                                lora_A.data_ptr(), lora_B.data_ptr(), mod.scaling, y.data_ptr(),
                                                t_save.data_ptr(), M, K, N, r, code, st), "sdt_lora_linear_fwd")
+        if ev0 is not None:
+            PROFILE.append(("fwd", M, K, N, ops.R, ev0, _ev()))
         ctx.mod = mod
         ctx.code = code
         ctx.need_dx = x2.requires_grad
@@ -125,10 +140,13 @@ class _LoRAProjection(torch.autograd.Function):
             ops = mod._packed_operands()
             wt = mod._weight_t_bf16() if ctx.need_dx else None
             g_ws = torch.empty(M, ops.R, dtype=torch.bfloat16, device=x2.device)
+            ev0 = _ev() if PROFILE is not None else None
             _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), _lib.ptr(wt), ops.At_p.data_ptr(),
                                                ops.Bt_p.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
                                                g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, ops.R, mod.r,
                                                ctx.code, st), "sdt_lora_linear_bwd")
+            if ev0 is not None:
+                PROFILE.append(("bwd", M, K, N, ops.R, ctx.need_dx, ev0, _ev()))
         else:
             g_ws = torch.empty(M, mod.r, dtype=torch.float32, device=x2.device)
             _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), mod.weight.data_ptr(), lora_A.data_ptr(),
