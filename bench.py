@@ -49,7 +49,7 @@ def load_peaks():
 # clocks during the timed region (pynvml polling thread)
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int, period_s: float = 0.2):
+    def __init__(self, index: int, period_s: float = 0.05):
         self.index, self.period = index, period_s
         self.samples, self.reasons = [], set()
         self.max_mhz = None
@@ -281,6 +281,15 @@ def ours_main(args):
         tr.step(dev[i % len(dev)])
     barrier()
 
+    if args.profile_step:
+        torch.cuda.profiler.start()
+        tr.step(dev[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled": "one training step", "workload": WORKLOAD["name"]}), flush=True)
+        exchange.close()
+        return 0
+
     # ---- value: device-resident inputs, no host sync inside the region ----
     launches0 = lib.sdt_launch_count()
     with ClockSampler(local_rank) as clocks:
@@ -370,6 +379,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_main(args)
