@@ -7,14 +7,18 @@
 // Linear.forward) and the input-gradient half of the backward (dY, W^T, B^T, A^T -> dX, G), because
 // dX = dY (W^T)^T + (s dY (B^T)^T) (A^T)^T has exactly the same shape of computation.
 //
-// Structure (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer: X / W / lora-down k-blocks into a kStages-deep 128B-swizzled smem ring,
-//               plus the [BN,R] lora-up tile once per output tile
-//   warp 1      tcgen05.mma issuer (one elected lane): main accumulator [128,BN] f32 (double buffered
-//               in TMEM) and the rank-R accumulator [128,R]; after the K loop the rank-R intermediate
-//               comes back as a bf16 A-operand in shared memory and one more UMMA adds Ts B^T
-//   warps 2..5  epilogue: TMEM -> registers -> (+bias, bf16) -> smem transpose -> coalesced 16 B stores;
-//               also scale + convert the rank-R intermediate (never leaves the SM except as t_save)
+// Structure (one persistent CTA per SM, 14 warps):
+//   warp 0        TMA producer: X / W / lora-down k-blocks into a kStages-deep 128B-swizzled smem ring,
+//                 plus the [BN,R] lora-up tile once per output tile
+//   warp 1        tcgen05.mma issuer (one elected lane).  Main accumulator [128,BN] f32, double buffered
+//                 in TMEM; rank accumulator [128,R], double buffered.  The "tail" of a tile -- Ts B^T and the
+//                 bias, both as UMMAs -- is issued a few k-blocks INTO the next tile, so the tensor pipe
+//                 never waits for the rank-R round trip through the side warps.
+//   warps 2..5    side warps: rank accumulator TMEM -> scale -> bf16 -> shared-memory A operand (+ t_save),
+//                 and the per-tile bias operand (bias as hi+lo bf16 pair against a constant ones operand:
+//                 the bias add costs one K=16 UMMA instead of per-element epilogue work)
+//   warps 6..13   epilogue: TMEM -> registers -> bf16 -> 64B-swizzled staging -> TMA store (two warps per
+//                 TMEM lane quarter, alternating 32-column chunks)
 // Work items are (m-tile, n-group); the n-tiles of a group reuse the rank-R intermediate, so the
 // down projection is computed once per group, not once per output tile.
 #include "sdt_common.cuh"
@@ -36,22 +40,26 @@ struct LoraGemmCfg {
   static constexpr int LA_BYTES = R * BK * 2;              // lora-down k-block [R,64]
   static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + LA_BYTES;
   static constexpr int LB_BYTES = ((BN * R * 2 + 1023) / 1024) * 1024;   // lora-up tile [BN,R]
-  static constexpr int T_BYTES = BM * R * 2;               // rank-R intermediate as UMMA A operand
-  static constexpr int STG_ROW = 80;                       // 64 B of payload + 16 B pad: conflict-free transposes
-  static constexpr int STG_BYTES = 4 * 32 * STG_ROW;
+  static constexpr int KEXT = R + 16;                      // rank-R intermediate + the "ones" k-step (bias)
+  static constexpr int T_SBO = (KEXT / 8) * 128;           // bytes between 8-row groups of the A operand
+  static constexpr int T_BYTES = (BM / 8) * T_SBO;
+  static constexpr int BIAS_BYTES = ((BN * 32 + 1023) / 1024) * 1024;    // [BN,16] bf16, un-swizzled cores
+  static constexpr int STG_BYTES = 8 * 2 * 2048;           // 8 epilogue warps x 2 buffers x [32 rows x 64 B]
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + LB_BYTES + T_BYTES + STG_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES =
+      1024 /*align slack*/ + kStages * STAGE_BYTES + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int ACC1_COL = BN, T_COL = 2 * BN;
-  static_assert(2 * BN + R <= 512, "TMEM budget");
+  static constexpr int ACC1_COL = BN, T_COL = 2 * BN;      // rank accumulators at T_COL and T_COL + R
+  static_assert(2 * BN + 2 * R <= 512, "TMEM budget");
   static_assert(BN % 32 == 0 && BN <= 256, "BN");
   static_assert(R == 0 || R == 16 || R == 32 || R == 64, "rank must be padded to 16/32/64");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
+constexpr int kGemmThreads = 14 * 32;
+
 struct LoraGemmParams {
   const float* bias;      // [N] or null
-  __nv_bfloat16* y;       // [M,N] or null when !main
   __nv_bfloat16* t_out;   // [M,R] or null
   float scaling;
   int M, N, K;
@@ -60,37 +68,40 @@ struct LoraGemmParams {
 };
 
 template <int BN, int R>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                  const __grid_constant__ CUtensorMap tm_la, const __grid_constant__ CUtensorMap tm_lb,
-                 const LoraGemmParams p) {
+                 const __grid_constant__ CUtensorMap tm_y, const LoraGemmParams p) {
   using C = LoraGemmCfg<BN, R>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* lb_smem = smem + C::kStages * C::STAGE_BYTES;
-  uint8_t* t_smem = lb_smem + C::LB_BYTES;
-  uint8_t* stg_smem = t_smem + C::T_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_smem + C::STG_BYTES);
+  uint8_t* stg_smem = lb_smem + C::LB_BYTES;
+  uint8_t* t_smem = stg_smem + C::STG_BYTES;
+  uint8_t* bias_smem = t_smem + C::T_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + C::BIAS_BYTES);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
   uint64_t* acc_full = bars + 2 * C::kStages;  // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint64_t* t_full = acc_empty + 2;
-  uint64_t* t_ready = t_full + 1;
-  uint64_t* lb_full = t_ready + 1;
-  uint64_t* lb_empty = lb_full + 1;
+  uint64_t* t_full = acc_empty + 2;            // rank accumulator complete (MMA -> side warps)
+  uint64_t* t_ready = t_full + 1;              // A operand (+ bias operand) of the tail is in smem (side warps -> MMA)
+  uint64_t* lb_full = t_ready + 1;             // lora-up tile landed (TMA -> MMA)
+  uint64_t* lb_empty = lb_full + 1;            // tail MMAs of a tile completed (MMA -> producer, side warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lb_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (p.K + C::BK - 1) / C::BK;
   const bool has_main = p.main != 0;
+  const bool has_bias = has_main && p.bias != nullptr;
+  const bool has_tail = has_main && (R > 0 || has_bias);   // UMMAs issued after the K loop of a tile
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_x);
-    if (has_main) prefetch_tmap(&tm_w);
+    if (has_main) { prefetch_tmap(&tm_w); prefetch_tmap(&tm_y); }
     if (R > 0) { prefetch_tmap(&tm_la); if (has_main) prefetch_tmap(&tm_lb); }
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     mbar_init(t_full, 1);
     mbar_init(t_ready, 4);
     mbar_init(lb_full, 1);
@@ -98,6 +109,17 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp >= 2 && warp < 6) {
+    // constant part of the tail's A operand: k-step R/16 is [1, 1, 0, ..., 0] per row (pairs with bias hi/lo)
+    const int row = (warp - 2) * 32 + lane;
+    uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(trow + (R / 8) * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // bf16 1.0, 1.0
+    *reinterpret_cast<uint4*>(trow + (R / 8 + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
+    // zero the second K chunk of the bias operand once (the first chunk is rewritten per tile)
+    for (int n = row; n < BN; n += 128)
+      *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + 128 + (n & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -136,17 +158,48 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
+    constexpr int RR = R > 0 ? R : 16;
     constexpr uint32_t idesc_main = make_idesc_bf16(128, BN, 0, 0);
-    constexpr uint32_t idesc_t = make_idesc_bf16(128, R > 0 ? R : 16, 0, 0);
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, RR, 0, 0);
     constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
     // lora-up tile [BN,R], K-major, rows of R*2 bytes written by TMA with the matching swizzle
     constexpr uint32_t lb_layout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
-    constexpr uint64_t d_lb = make_smem_desc_base(16, 8 * (R > 0 ? R : 16) * 2, lb_layout);
-    // rank-R intermediate [128,R], K-major, un-swizzled core matrices (8 rows x 16 B, 128 B each):
-    // K-adjacent cores 128 B apart (LBO), 8-row groups (R/8)*128 B apart (SBO)
-    constexpr uint64_t d_t = make_smem_desc_base(128, ((R > 0 ? R : 16) / 8) * 128, kLayoutNone);
-    uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_ctr) {
+    constexpr uint64_t d_lb = make_smem_desc_base(16, 8 * RR * 2, lb_layout);
+    // tail A operand [128,R+16] and bias operand [BN,16]: K-major, un-swizzled core matrices (8 rows x 16 B = 128 B):
+    // K-adjacent cores 128 B apart (LBO), 8-row groups SBO apart
+    constexpr uint64_t d_t = make_smem_desc_base(128, C::T_SBO, kLayoutNone);
+    constexpr uint64_t d_bias = make_smem_desc_base(128, 256, kLayoutNone);
+    uint32_t it = 0, tile_ctr = 0, first_ctr = 0, ready_ctr = 0;
+    // a finished K loop whose tail UMMAs (Ts B^T, bias) have not been issued yet
+    bool pending = false, pend_needs_ready = false;
+    uint32_t pend_tile = 0, pend_ready = 0;
+
+    auto tail_ready = [&]() -> bool {
+      // all 32 lanes probe the same barriers, so the result is warp-uniform
+      if (R > 0 && !mbar_test(lb_full, pend_tile & 1)) return false;
+      if (pend_needs_ready && !mbar_test(t_ready, pend_ready & 1)) return false;
+      return true;
+    };
+    auto issue_tail = [&]() {
+      // tail of tile pend_tile: acc += Ts B^T (R/16 k-steps) + ones x bias (1 k-step); then hand the accumulator over
+      if (R > 0) mbar_wait(lb_full, pend_tile & 1);
+      if (pend_needs_ready) mbar_wait(t_ready, pend_ready & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = tmem_base + (pend_tile & 1) * C::ACC1_COL;
+        const uint32_t ta = smem_u32(t_smem), ba = smem_u32(lb_smem);
+#pragma unroll
+        for (int k = 0; k < R / 16; ++k)
+          umma_f16_ss(d, smem_desc(d_t, ta + k * 256), smem_desc(d_lb, ba + k * 32), idesc_main, 1u);
+        if (has_bias) umma_f16_ss(d, smem_desc(d_t, ta + (R / 16) * 256), smem_desc(d_bias, smem_u32(bias_smem)), idesc_main, 1u);
+        umma_commit(lb_empty);
+        umma_commit(&acc_full[pend_tile & 1]);
+      }
+      __syncwarp();
+      pending = false;
+    };
+
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int g = item % p.n_groups;
       const int nt0 = g * p.group_size;
       const int nt1 = min(nt0 + p.group_size, p.n_tiles);
@@ -154,9 +207,13 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const bool first = (nt == nt0) && R > 0;
         const uint32_t buf = tile_ctr & 1;
         const uint32_t d_main = tmem_base + buf * C::ACC1_COL;
-        const uint32_t d_tacc = tmem_base + C::T_COL;
+        const uint32_t d_tacc = tmem_base + C::T_COL + (first_ctr & 1) * RR;
         if (has_main) {
           mbar_wait(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1);
+          tc_fence_after();
+        } else if (first_ctr >= 1) {
+          // rank-only mode: the side warps must have drained the previous item's rank accumulator
+          mbar_wait(t_ready, (first_ctr - 1) & 1);
           tc_fence_after();
         }
         for (int kb = 0; kb < nk; ++kb, ++it) {
@@ -176,125 +233,161 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             umma_commit(&empty[s]);
           }
           __syncwarp();
+          // the previous tile's tail goes out as soon as its operands are in place -- at the latest before this
+          // tile's K loop ends (its accumulator hand-over must not wait for a whole tile)
+          if (pending && (kb == nk - 1 || tail_ready())) issue_tail();
         }
         if (first) {
           if (elect_one()) umma_commit(t_full);
           __syncwarp();
-          // without the up-projection below nothing else orders the next item's rank-R MMAs after the
-          // epilogue's read of this item's rank-R accumulator
-          if (!has_main) mbar_wait(t_ready, item_ctr & 1);
-        }
-        if (R > 0 && has_main) {
-          mbar_wait(lb_full, tile_ctr & 1);
-          if (first) mbar_wait(t_ready, item_ctr & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t ta = smem_u32(t_smem), ba = smem_u32(lb_smem);
-#pragma unroll
-            for (int k = 0; k < R / 16; ++k)
-              umma_f16_ss(d_main, smem_desc(d_t, ta + k * 256), smem_desc(d_lb, ba + k * 32), idesc_main, 1u);
-            umma_commit(lb_empty);
-          }
-          __syncwarp();
+          ++first_ctr;
         }
         if (has_main) {
-          if (elect_one()) umma_commit(&acc_full[buf]);
-          __syncwarp();
+          if (has_tail) {
+            pending = true;
+            pend_tile = tile_ctr;
+            pend_needs_ready = first || has_bias;
+            pend_ready = ready_ctr;
+            if (pend_needs_ready) ++ready_ctr;
+            if (tail_ready()) issue_tail();      // non-first tiles: operands are usually already there
+          } else {
+            if (elect_one()) umma_commit(&acc_full[buf]);
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (pending) issue_tail();
+  } else if (warp < 6) {
+    // ===================================== side warps ========================================
+    // per tile: (a) bias operand of the tail, (b) on the first tile of an item: rank-R intermediate
+    constexpr int RR = R > 0 ? R : 16;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tid = (warp - 2) * 32 + lane;       // 0..127
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t tile_ctr = 0, first_ctr = 0;
+    if (has_tail || (!has_main && R > 0)) {
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int m0 = (item / p.n_groups) * C::BM;
+        const int g = item % p.n_groups;
+        const int nt0 = g * p.group_size;
+        const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+        for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
+          const bool first = (nt == nt0) && R > 0;
+          if (has_bias) {
+            // the previous tile's tail must have finished reading the bias operand
+            if (tile_ctr > 0) mbar_wait(lb_empty, (tile_ctr - 1) & 1);
+            const int n0 = nt * C::BN;
+            for (int n = tid; n < BN; n += 128) {
+              const float b = (n0 + n < p.N) ? __ldg(p.bias + n0 + n) : 0.f;
+              const float hi = round_bf16(b);
+              *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) =
+                  make_uint4(pack_bf16x2(hi, b - hi), 0u, 0u, 0u);
+            }
+          }
+          if (first) {
+            mbar_wait(t_full, first_ctr & 1);
+            tc_fence_after();
+            uint32_t packed[RR / 2];
+#pragma unroll
+            for (int c = 0; c < RR / 16; ++c) {
+              uint32_t v[16];
+              tmem_ld_x16(lane_addr + C::T_COL + (first_ctr & 1) * RR + c * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                packed[c * 8 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling);
+            }
+            if (has_main) {
+              uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
+#pragma unroll
+              for (int kc = 0; kc < RR / 8; ++kc)
+                *reinterpret_cast<uint4*>(trow + kc * 128) =
+                    make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
+            }
+            if (p.t_out != nullptr && g == 0 && m0 + row < p.M) {
+              uint4* dst = reinterpret_cast<uint4*>(p.t_out + (size_t)(m0 + row) * RR);
+#pragma unroll
+              for (int kc = 0; kc < RR / 8; ++kc)
+                dst[kc] = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
+            }
+            ++first_ctr;
+          }
+          if (first || has_bias) {
+            fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_ready);
+          }
         }
       }
     }
   } else {
     // ===================================== epilogue warps ====================================
+    const int e = warp - 6;                       // 0..7
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;                // row inside the 128-row tile
+    const int half = e >> 2;                      // which of the two warps of this quarter
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* stg = stg_smem + q * 32 * C::STG_ROW;
-    uint32_t tile_ctr = 0, item_ctr = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_ctr) {
-      const int m0 = (item / p.n_groups) * C::BM;
-      const int g = item % p.n_groups;
-      const int nt0 = g * p.group_size;
-      const int nt1 = min(nt0 + p.group_size, p.n_tiles);
-      for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
-        const bool first = (nt == nt0) && R > 0;
-        if (first) {
-          // ---- rank-R intermediate: TMEM f32 -> scale -> bf16 -> smem A operand (+ t_save) ----
-          mbar_wait(t_full, item_ctr & 1);
+    uint8_t* stg = stg_smem + e * 4096;
+    uint32_t tile_ctr = 0, stores = 0;
+    if (has_main) {
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int m0 = (item / p.n_groups) * C::BM;
+        const int g = item % p.n_groups;
+        const int nt0 = g * p.group_size;
+        const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+        for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
+          const uint32_t buf = tile_ctr & 1;
+          const int n0 = nt * C::BN;
+          const bool rows_live = m0 + q * 32 < p.M;
+          mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
           tc_fence_after();
-          constexpr int RR = R > 0 ? R : 16;
-          uint32_t packed[RR / 2];
-#pragma unroll
-          for (int c = 0; c < RR / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld_x16(lane_addr + C::T_COL + c * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              packed[c * 8 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling);
-          }
-          uint8_t* trow = t_smem + (row >> 3) * ((RR / 8) * 128) + (row & 7) * 16;
-#pragma unroll
-          for (int kc = 0; kc < RR / 8; ++kc)
-            *reinterpret_cast<uint4*>(trow + kc * 128) =
-                make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
-          if (p.t_out != nullptr && g == 0 && m0 + row < p.M) {
-            uint4* dst = reinterpret_cast<uint4*>(p.t_out + (size_t)(m0 + row) * RR);
-#pragma unroll
-            for (int kc = 0; kc < RR / 8; ++kc)
-              dst[kc] = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
-          }
-          fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t_ready);
-        }
-        if (!has_main) continue;
-        // ---- main accumulator: TMEM -> (+bias) -> bf16 -> transpose through smem -> global ----
-        const uint32_t buf = tile_ctr & 1;
-        mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
-        tc_fence_after();
-        const int n0 = nt * C::BN;
-#pragma unroll 1
-        for (int c = 0; c < C::BN / 32; ++c) {
-          const int col0 = n0 + c * 32;
-          if (col0 >= p.N) break;                // warp-uniform
+          // chunks c with (c + tile_ctr + half) even belong to this warp: the odd chunk count of BN=160 alternates
+          int c = (tile_ctr + half) & 1;
           uint32_t v[32];
-          tmem_ld_x32(lane_addr + buf * C::ACC1_COL + c * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int cc = col0 + 2 * j;
-              const float b0 = cc < p.N ? __ldg(p.bias + cc) : 0.f, b1 = cc + 1 < p.N ? __ldg(p.bias + cc + 1) : 0.f;
-              pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + b0, __uint_as_float(v[2 * j + 1]) + b1);
-            }
-          } else {
+          bool have = c < C::BN / 32 && n0 + c * 32 < p.N;
+          if (have) tmem_ld_x32(lane_addr + buf * C::ACC1_COL + c * 32, v);
+          while (have) {
+            tmem_ld_wait();
+            uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          }
-          uint8_t* srow = stg + lane * C::STG_ROW;
+            const int col0 = n0 + c * 32;
+            c += 2;
+            have = c < C::BN / 32 && n0 + c * 32 < p.N;
+            if (have) tmem_ld_x32(lane_addr + buf * C::ACC1_COL + c * 32, v);   // overlaps the store below
+            if (rows_live) {
+              uint8_t* sb = stg + (stores & 1) * 2048;
+              if (stores >= 2) {            // the TMA store that last read this buffer must have drained it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+              }
+              // 64B-swizzled [32 rows x 64 B]: 16 B chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+              uint8_t* srow = sb + lane * 64;
+              const int sw = (lane >> 1) & 3;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(srow + j * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          __syncwarp();
-          // lane l stores the 16 B chunk (l & 3) of rows (l >> 2) + 8 j: each row segment is 64 contiguous bytes
-          const int ch = lane & 3;
-          const int colc = col0 + ch * 8;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int r = (lane >> 2) + 8 * j;
-            const int grow = m0 + q * 32 + r;
-            const uint4 val = *reinterpret_cast<const uint4*>(stg + r * C::STG_ROW + ch * 16);
-            if (grow < p.M && colc < p.N)
-              *reinterpret_cast<uint4*>(p.y + (size_t)grow * p.N + colc) = val;
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                 reinterpret_cast<uint64_t>(&tm_y)),
+                             "r"(col0), "r"(m0 + q * 32), "r"(smem_u32(sb))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              ++stores;
+            }
           }
+          // every tcgen05.ld of this buffer has completed (wait::ld above): release it to the MMA warp
+          tc_fence_before();
           __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
 
@@ -326,8 +419,36 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// Tensor maps are pure functions of (base, shape, pitch, box, swizzle); weights, packed operands and -- thanks to the
+// caching allocator -- most activations keep their addresses from step to step, so the encode (a driver call) is cached.
+struct TmapKey {
+  uint64_t base, rows, cols, pitch;
+  uint32_t box_rows, box_cols, swz;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && pitch == o.pitch && box_rows == o.box_rows &&
+           box_cols == o.box_cols && swz == o.swz;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = k.base * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (((uint64_t)k.box_rows << 40) ^ ((uint64_t)k.box_cols << 8) ^ k.swz) + (h << 6) + (h >> 2);
+    return (size_t)h;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmaps_mu;
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                       uint32_t box_rows, uint32_t box_cols, TmapSwizzle swz) {
+  const TmapKey key{reinterpret_cast<uint64_t>(base), rows, cols, pitch_bytes, box_rows, box_cols, (uint32_t)swz};
+  {
+    std::lock_guard<std::mutex> lk(g_tmaps_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) { *out = it->second; return SDT_OK; }
+  }
   PFN_encodeTiled enc = get_encode();
   SDT_REQUIRE(enc != nullptr, SDT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   SDT_REQUIRE(aligned16(base) && pitch_bytes % 16 == 0, SDT_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte row pitch");
@@ -345,7 +466,29 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   SDT_REQUIRE(r == CUDA_SUCCESS, SDT_ERR_CUDA,
               "cuTensorMapEncodeTiled failed (%d) for [%llu x %llu] pitch %llu box [%u x %u]", (int)r,
               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes, box_rows, box_cols);
+  {
+    std::lock_guard<std::mutex> lk(g_tmaps_mu);
+    if (g_tmaps.size() > 16384) g_tmaps.clear();
+    g_tmaps.emplace(key, *out);
+  }
   return SDT_OK;
+}
+
+// Pick the number of n-groups per m-tile: fewer groups = less recomputation of the rank-R projection, more groups =
+// more work items to balance over the SMs.  Cost of a schedule ~ rounds * (columns per item + per-item overhead).
+static void choose_groups(int m_tiles, int n_tiles, int BN, int R, int sms, int* group_size, int* n_groups) {
+  if (R == 0) { *group_size = 1; *n_groups = n_tiles; return; }
+  double best = 1e30;
+  int best_gs = 1;
+  for (int gs = 1; gs <= n_tiles; ++gs) {
+    const int groups = (n_tiles + gs - 1) / gs;
+    const long items = (long)m_tiles * groups;
+    const long rounds = (items + sms - 1) / sms;
+    const double cost = (double)rounds * (gs * (double)BN + R + 48.0);
+    if (cost < best - 1e-9) { best = cost; best_gs = gs; }
+  }
+  *group_size = best_gs;
+  *n_groups = (n_tiles + best_gs - 1) / best_gs;
 }
 
 template <int BN, int R>
@@ -357,14 +500,17 @@ static int launch_lora_gemm(const void* x, const void* w, const float* bias, con
     SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_kernel<BN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  CUtensorMap tm_x, tm_w, tm_la, tm_lb;
+  CUtensorMap tm_x, tm_w, tm_la, tm_lb, tm_y;
   int rc = make_tmap_2d_bf16(&tm_x, x, M, K, K * 2, C::BM, C::BK, TMAP_SW_128);
   if (rc != SDT_OK) return rc;
   if (main) {
     rc = make_tmap_2d_bf16(&tm_w, w, N, K, K * 2, BN, C::BK, TMAP_SW_128);
     if (rc != SDT_OK) return rc;
+    rc = make_tmap_2d_bf16(&tm_y, y, M, N, N * 2, 32, 32, TMAP_SW_64);
+    if (rc != SDT_OK) return rc;
   } else {
     tm_w = tm_x;
+    tm_y = tm_x;
   }
   if (R > 0) {
     rc = make_tmap_2d_bf16(&tm_la, la, R, K, K * 2, R, C::BK, TMAP_SW_128);
@@ -382,32 +528,22 @@ static int launch_lora_gemm(const void* x, const void* w, const float* bias, con
   }
   LoraGemmParams p;
   p.bias = bias;
-  p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.t_out = reinterpret_cast<__nv_bfloat16*>(t_out);
   p.scaling = scaling;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.main = main ? 1 : 0;
   const int m_tiles = (int)((M + C::BM - 1) / C::BM);
   p.n_tiles = main ? (int)((N + BN - 1) / BN) : 1;
-  // n-groups: as few as possible (the rank-R projection is recomputed once per group) while still
-  // giving every SM a couple of work items
   const int sms = num_sms();
-  int n_groups = 1;
-  if (R > 0) {
-    while (n_groups < p.n_tiles && m_tiles * n_groups < 2 * sms) ++n_groups;
-  } else {
-    n_groups = p.n_tiles;
-  }
-  p.group_size = (p.n_tiles + n_groups - 1) / n_groups;
-  p.n_groups = (p.n_tiles + p.group_size - 1) / p.group_size;
+  choose_groups(m_tiles, p.n_tiles, BN, R, sms, &p.group_size, &p.n_groups);
   p.n_items = m_tiles * p.n_groups;
   const int grid = p.n_items < sms ? p.n_items : sms;
-  lora_gemm_kernel<BN, R><<<grid, 192, C::SMEM_BYTES, st>>>(tm_x, tm_w, tm_la, tm_lb, p);
+  lora_gemm_kernel<BN, R><<<grid, kGemmThreads, C::SMEM_BYTES, st>>>(tm_x, tm_w, tm_la, tm_lb, tm_y, p);
   SDT_LAUNCH_OK("lora_gemm");
   return SDT_OK;
 }
 
-// bf16 entry used by sdt_lora_linear_fwd / sdt_lora_linear_bwd (api in lora_api.cu)
+// bf16 entry used by sdt_lora_linear_fwd / sdt_lora_linear_bwd (lora_api.cu)
 int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
                    void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, cudaStream_t st) {
   SDT_REQUIRE(M > 0 && K > 0 && N > 0, SDT_ERR_ARG, "lora_gemm: bad sizes M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
