@@ -6,8 +6,8 @@
 namespace sdt {
 int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
                    void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, cudaStream_t st);
-int lora_wgrad_bf16(const void* u, const void* v, float* out, int64_t M, int64_t F, int r, int r_true, bool transposed,
-                    cudaStream_t st);
+int lora_wgrad_pair_bf16(const void* x, const void* g, float* dA, int64_t K, const void* dy, const void* ts, float* dB,
+                         int64_t N, int64_t M, int r, int r_true, cudaStream_t st);
 int lora_fwd_f32(const float* x, const float* w, const float* bias, const float* A, const float* B, float scaling,
                  float* y, float* t_save, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st);
 int lora_bwd_f32(const float* dy, const float* x, const float* w, const float* A, const float* B, const float* t_save,
@@ -58,9 +58,8 @@ extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt
     int rc = lora_gemm_bf16(dy, wt, nullptr, Bt, At, scaling, dx, g_ws, M, /*contraction*/ N, /*outputs*/ K, r,
                             dx != nullptr, st);
     if (rc != SDT_OK || r == 0) return rc;
-    rc = lora_wgrad_bf16(x, g_ws, dA, M, K, r, r_true, /*transposed=*/true, st);     // dA[j,k] += sum_m G[m,j] X[m,k]
-    if (rc != SDT_OK) return rc;
-    return lora_wgrad_bf16(dy, t_save, dB, M, N, r, r_true, /*transposed=*/false, st);   // dB[n,j] += sum_m dY[m,n] Ts[m,j]
+    // dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]: one launch for both reductions
+    return lora_wgrad_pair_bf16(x, g_ws, dA, K, dy, t_save, dB, N, M, r, r_true, st);
   }
   if (dtype == SDT_F32) {
     SDT_REQUIRE(r_true == r, SDT_ERR_ARG, "sdt_lora_linear_bwd(f32): r_true must equal r");

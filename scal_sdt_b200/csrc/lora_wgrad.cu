@@ -31,9 +31,13 @@ struct WgradCfg {
   static constexpr int TMEM_COLS = R < 32 ? 32 : R;
 };
 
-struct WgradParams {
+struct WgradProblem {
   float* out;             // dA [r_true,F] (transposed = 1) or dB [F,r_true] (transposed = 0)
-  int M, F, r_true, transposed;
+  int F, transposed, f_blocks;
+};
+struct WgradParams {
+  WgradProblem prob[2];   // one launch covers dA (problem 0) and dB (problem 1): blockIdx.x < prob[0].f_blocks -> problem 0
+  int M, r_true;
   int rows_per_split;     // multiple of 64
   // descriptors are host-built so that the layout constants live in one place (and can be probed)
   uint64_t a_desc_base, b_desc_base;
@@ -42,7 +46,8 @@ struct WgradParams {
 
 template <int R>
 __global__ void __launch_bounds__(128, 1)
-lora_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v, const WgradParams p) {
+lora_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__ CUtensorMap tm_v0,
+                  const __grid_constant__ CUtensorMap tm_u1, const __grid_constant__ CUtensorMap tm_v1, const WgradParams p) {
   using C = WgradCfg<R>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -53,14 +58,21 @@ lora_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f0 = blockIdx.x * C::BF;
+  const int which = (int)blockIdx.x >= p.prob[0].f_blocks ? 1 : 0;
+  WgradProblem pr;        // explicit selects: dynamic indexing of the param struct would spill it to local memory
+  pr.out = which ? p.prob[1].out : p.prob[0].out;
+  pr.F = which ? p.prob[1].F : p.prob[0].F;
+  pr.transposed = which ? p.prob[1].transposed : p.prob[0].transposed;
+  const CUtensorMap* tm_u = which ? &tm_u1 : &tm_u0;
+  const CUtensorMap* tm_v = which ? &tm_v1 : &tm_v0;
+  const int f0 = ((int)blockIdx.x - (which ? p.prob[0].f_blocks : 0)) * C::BF;
   const int m_begin = blockIdx.y * p.rows_per_split;
   const int m_end = min(m_begin + p.rows_per_split, p.M);
   const int nk = (m_end - m_begin + C::BMK - 1) / C::BMK;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm_u);
-    prefetch_tmap(&tm_v);
+    prefetch_tmap(tm_u);
+    prefetch_tmap(tm_v);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(done, 1);
     fence_mbar_init();
@@ -79,9 +91,9 @@ lora_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constan
         uint8_t* st = smem + s * C::STAGE_BYTES;
         const int m = m_begin + kb * C::BMK;
         mbar_arrive_expect_tx(&full[s], C::U_BYTES + C::BMK * R * 2);
-        tma_load_2d(st, &tm_u, f0, m, &full[s]);                    // features f0 .. f0+63
-        tma_load_2d(st + C::U_BYTES / 2, &tm_u, f0 + 64, m, &full[s]);   // features f0+64 .. f0+127
-        tma_load_2d(st + C::U_BYTES, &tm_v, 0, m, &full[s]);
+        tma_load_2d(st, tm_u, f0, m, &full[s]);                    // features f0 .. f0+63
+        tma_load_2d(st + C::U_BYTES / 2, tm_u, f0 + 64, m, &full[s]);   // features f0+64 .. f0+127
+        tma_load_2d(st + C::U_BYTES, tm_v, 0, m, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -115,12 +127,12 @@ lora_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constan
       uint32_t v[16];
       tmem_ld_x16(taddr + c * 16, v);
       tmem_ld_wait();
-      if (f < p.F) {
+      if (f < pr.F) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int jj = c * 16 + j;
           if (jj < p.r_true) {
-            float* dst = p.transposed ? p.out + (size_t)jj * p.F + f : p.out + (size_t)f * p.r_true + jj;
+            float* dst = pr.transposed ? pr.out + (size_t)jj * pr.F + f : pr.out + (size_t)f * p.r_true + jj;
             atomicAdd(dst, __uint_as_float(v[j]));
           }
         }
@@ -141,26 +153,40 @@ void debug_set(int key, uint64_t value) { if (key >= 0 && key < 16) g_dbg[key] =
 uint64_t debug_get(int key) { return (key >= 0 && key < 16) ? g_dbg[key] : 0; }
 
 template <int R>
-static int launch_wgrad(const void* u, const void* v, float* out, int64_t M, int64_t F, int r_true, bool transposed,
-                        cudaStream_t st) {
+static int launch_wgrad_pair(const void* u0, const void* v0, float* out0, int64_t F0, bool tr0,
+                             const void* u1, const void* v1, float* out1, int64_t F1, bool tr1,
+                             int64_t M, int r_true, cudaStream_t st) {
   using C = WgradCfg<R>;
   static bool attr_set = false;
   if (!attr_set) {
     SDT_CUDA_OK(cudaFuncSetAttribute(lora_wgrad_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  CUtensorMap tm_u, tm_v;
-  int rc = make_tmap_2d_bf16(&tm_u, u, M, F, F * 2, C::BMK, 64, TMAP_SW_128);
+  const TmapSwizzle vsw = R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32);
+  CUtensorMap tm_u0, tm_v0, tm_u1, tm_v1;
+  int rc = make_tmap_2d_bf16(&tm_u0, u0, M, F0, F0 * 2, C::BMK, 64, TMAP_SW_128);
   if (rc != SDT_OK) return rc;
-  rc = make_tmap_2d_bf16(&tm_v, v, M, R, (uint64_t)R * 2, C::BMK, R, R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
+  rc = make_tmap_2d_bf16(&tm_v0, v0, M, R, (uint64_t)R * 2, C::BMK, R, vsw);
   if (rc != SDT_OK) return rc;
+  if (u1 != nullptr) {
+    rc = make_tmap_2d_bf16(&tm_u1, u1, M, F1, F1 * 2, C::BMK, 64, TMAP_SW_128);
+    if (rc != SDT_OK) return rc;
+    rc = make_tmap_2d_bf16(&tm_v1, v1, M, R, (uint64_t)R * 2, C::BMK, R, vsw);
+    if (rc != SDT_OK) return rc;
+  } else {
+    tm_u1 = tm_u0;
+    tm_v1 = tm_v0;
+  }
   WgradParams p;
-  p.out = out;
-  p.M = (int)M; p.F = (int)F; p.r_true = r_true; p.transposed = transposed ? 1 : 0;
-  const int f_blocks = (int)((F + C::BF - 1) / C::BF);
+  p.prob[0].out = out0; p.prob[0].F = (int)F0; p.prob[0].transposed = tr0 ? 1 : 0;
+  p.prob[0].f_blocks = (int)((F0 + C::BF - 1) / C::BF);
+  p.prob[1].out = out1; p.prob[1].F = (int)F1; p.prob[1].transposed = tr1 ? 1 : 0;
+  p.prob[1].f_blocks = u1 != nullptr ? (int)((F1 + C::BF - 1) / C::BF) : 0;
+  p.M = (int)M; p.r_true = r_true;
+  const int f_blocks = p.prob[0].f_blocks + p.prob[1].f_blocks;
   const int m_chunks = (int)((M + C::BMK - 1) / C::BMK);
-  // enough CTAs for ~3 per SM, but at least 8 stages of work each
-  int splits = (3 * num_sms() + f_blocks - 1) / f_blocks;
+  // enough CTAs for ~2 per SM, but at least 8 stages of work each
+  int splits = (2 * num_sms() + f_blocks - 1) / f_blocks;
   if (splits > (m_chunks + 7) / 8) splits = (m_chunks + 7) / 8;
   if (splits < 1) splits = 1;
   const int chunks_per_split = (m_chunks + splits - 1) / splits;
@@ -180,20 +206,22 @@ static int launch_wgrad(const void* u, const void* v, float* out, int64_t M, int
   if (g_dbg[4]) p.a_step = (uint32_t)g_dbg[5];
   if (g_dbg[6]) p.b_step = (uint32_t)g_dbg[7];
   if (g_dbg[8]) p.idesc = (uint32_t)g_dbg[9];
-  lora_wgrad_kernel<R><<<dim3(f_blocks, splits), 128, C::SMEM_BYTES, st>>>(tm_u, tm_v, p);
+  lora_wgrad_kernel<R><<<dim3(f_blocks, splits), 128, C::SMEM_BYTES, st>>>(tm_u0, tm_v0, tm_u1, tm_v1, p);
   SDT_LAUNCH_OK("lora_wgrad");
   return SDT_OK;
 }
 
-int lora_wgrad_bf16(const void* u, const void* v, float* out, int64_t M, int64_t F, int r, int r_true, bool transposed,
-                    cudaStream_t st) {
-  SDT_REQUIRE(u && v && out, SDT_ERR_ARG, "lora_wgrad: null pointer");
-  SDT_REQUIRE(M > 0 && F > 0 && F % 8 == 0, SDT_ERR_ARG, "lora_wgrad: bad sizes M=%lld F=%lld", (long long)M, (long long)F);
+// dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]  in ONE launch
+int lora_wgrad_pair_bf16(const void* x, const void* g, float* dA, int64_t K, const void* dy, const void* ts, float* dB,
+                         int64_t N, int64_t M, int r, int r_true, cudaStream_t st) {
+  SDT_REQUIRE(x && g && dA && dy && ts && dB, SDT_ERR_ARG, "lora_wgrad: null pointer");
+  SDT_REQUIRE(M > 0 && K > 0 && N > 0 && K % 8 == 0 && N % 8 == 0, SDT_ERR_ARG, "lora_wgrad: bad sizes M=%lld K=%lld N=%lld",
+              (long long)M, (long long)K, (long long)N);
   SDT_REQUIRE(r_true >= 1 && r_true <= r, SDT_ERR_ARG, "lora_wgrad: r_true=%d outside [1,%d]", r_true, r);
   switch (r) {
-    case 16: return launch_wgrad<16>(u, v, out, M, F, r_true, transposed, st);
-    case 32: return launch_wgrad<32>(u, v, out, M, F, r_true, transposed, st);
-    case 64: return launch_wgrad<64>(u, v, out, M, F, r_true, transposed, st);
+    case 16: return launch_wgrad_pair<16>(x, g, dA, K, true, dy, ts, dB, N, false, M, r_true, st);
+    case 32: return launch_wgrad_pair<32>(x, g, dA, K, true, dy, ts, dB, N, false, M, r_true, st);
+    case 64: return launch_wgrad_pair<64>(x, g, dA, K, true, dy, ts, dB, N, false, M, r_true, st);
   }
   set_error("lora_wgrad: padded rank must be 16, 32 or 64 (got %d)", r);
   return SDT_ERR_UNSUPPORTED;
