@@ -147,6 +147,14 @@ int sdt_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, cons
                    const float* hyper_dev, float grad_scale, float* ema_shadow, float ema_one_minus_decay,
                    const float* ema_one_minus_decay_dev, void* stream);
 
+/* ---- f2: GEGLU, the activation after ff.net.0.proj (diffusers GEGLU: proj = [h | gate], out = h * gelu_erf(gate)) ----
+ * backward == 0: out_or_dproj [M,I]  = h * gelu(gate)                         (dout ignored)
+ * backward == 1: out_or_dproj [M,2I] = [dout * gelu(gate) | dout * h * gelu'(gate)]
+ * proj [M,2I]; dtype SDT_BF16 (128-bit vectorised, I % 8 == 0) or SDT_F32.  HBM-bound: 3 I (fwd) / 5 I (bwd) elements per row.
+ */
+int sdt_geglu(const void* proj, const void* dout, void* out_or_dproj, int64_t M, int64_t I, int backward, int dtype,
+              void* stream);
+
 /* ---- K6: data-parallel LoRA-gradient exchange (replaces Lightning DDP, train.py:98-109) -------
  * One NCCL communicator per process (libnccl is resolved at run time with dlopen, so the library
  * loads on machines without NCCL).  sdt_allreduce averages `count` elements in place.

@@ -427,6 +427,86 @@ lora_pack_kernel(const sdt_pack_site* __restrict__ sites) {
   }
 }
 
+// =============================================================================================
+// f2: GEGLU (the activation that follows ff.net.0.proj): out = h * gelu(gate), proj = [h | gate]
+// =============================================================================================
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// proj [M, 2I] bf16 -> out [M, I] bf16; one 16-byte vector (8 elements) of h and of gate per thread per iteration
+__global__ void __launch_bounds__(kThreads)
+geglu_fwd_bf16_kernel(const uint16_t* __restrict__ proj, uint16_t* __restrict__ out, int64_t M, int64_t I8) {
+  const int64_t total = M * I8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / I8, c = i - row * I8;
+    const uint4* base = reinterpret_cast<const uint4*>(proj) + row * 2 * I8;
+    const uint4 hv = ld_stream(base + c), gv = ld_stream(base + I8 + c);
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
+    uint4 ov;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float h0 = bf16_bits_to_f32(hw[j] & 0xffffu), h1 = bf16_bits_to_f32(hw[j] >> 16);
+      const float g0 = bf16_bits_to_f32(gw[j] & 0xffffu), g1 = bf16_bits_to_f32(gw[j] >> 16);
+      ow[j] = pack_bf16x2(h0 * gelu_erf(g0), h1 * gelu_erf(g1));
+    }
+    st_stream(reinterpret_cast<uint4*>(out) + i, ov);
+  }
+}
+
+// dproj[:, :I] = dout * gelu(gate) ; dproj[:, I:] = dout * h * gelu'(gate)
+__global__ void __launch_bounds__(kThreads)
+geglu_bwd_bf16_kernel(const uint16_t* __restrict__ proj, const uint16_t* __restrict__ dout, uint16_t* __restrict__ dproj,
+                      int64_t M, int64_t I8) {
+  const int64_t total = M * I8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / I8, c = i - row * I8;
+    const uint4* base = reinterpret_cast<const uint4*>(proj) + row * 2 * I8;
+    const uint4 hv = ld_stream(base + c), gv = ld_stream(base + I8 + c);
+    const uint4 dv = ld_stream(reinterpret_cast<const uint4*>(dout) + i);
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
+    const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv);
+    uint4 dhv, dgv;
+    uint32_t* dhw = reinterpret_cast<uint32_t*>(&dhv);
+    uint32_t* dgw = reinterpret_cast<uint32_t*>(&dgv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float h0 = bf16_bits_to_f32(hw[j] & 0xffffu), h1 = bf16_bits_to_f32(hw[j] >> 16);
+      const float g0 = bf16_bits_to_f32(gw[j] & 0xffffu), g1 = bf16_bits_to_f32(gw[j] >> 16);
+      const float d0 = bf16_bits_to_f32(dw[j] & 0xffffu), d1 = bf16_bits_to_f32(dw[j] >> 16);
+      dhw[j] = pack_bf16x2(d0 * gelu_erf(g0), d1 * gelu_erf(g1));
+      dgw[j] = pack_bf16x2(d0 * h0 * gelu_erf_grad(g0), d1 * h1 * gelu_erf_grad(g1));
+    }
+    uint4* obase = reinterpret_cast<uint4*>(dproj) + row * 2 * I8;
+    st_stream(obase + c, dhv);
+    st_stream(obase + I8 + c, dgv);
+  }
+}
+
+// f32 variant (parity path), scalar
+__global__ void __launch_bounds__(kThreads)
+geglu_f32_kernel(const float* __restrict__ proj, const float* __restrict__ dout, float* __restrict__ out_or_dproj,
+                 int64_t M, int64_t I, int backward) {
+  const int64_t total = M * I;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / I, c = i - row * I;
+    const float h = proj[row * 2 * I + c], g = proj[row * 2 * I + I + c];
+    if (!backward) {
+      out_or_dproj[i] = h * gelu_erf(g);
+    } else {
+      const float d = dout[i];
+      out_or_dproj[row * 2 * I + c] = d * gelu_erf(g);
+      out_or_dproj[row * 2 * I + I + c] = d * h * gelu_erf_grad(g);
+    }
+  }
+}
+
 }  // namespace sdt
 
 // =============================================================================================
@@ -578,5 +658,27 @@ extern "C" int sdt_lora_pack(const sdt_pack_site* sites, int n_sites, int64_t ma
   if (gx > 64) gx = 64;
   lora_pack_kernel<<<dim3(gx, n_sites), kThreads, 0, (cudaStream_t)stream>>>(sites);
   SDT_LAUNCH_OK("lora_pack");
+  return SDT_OK;
+}
+
+extern "C" int sdt_geglu(const void* proj, const void* dout, void* out_or_dproj, int64_t M, int64_t I, int backward,
+                         int dtype, void* stream) {
+  SDT_REQUIRE(proj && out_or_dproj && (!backward || dout), SDT_ERR_ARG, "sdt_geglu: null pointer");
+  SDT_REQUIRE(M > 0 && I > 0, SDT_ERR_ARG, "sdt_geglu: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SDT_BF16) {
+    SDT_REQUIRE(I % 8 == 0 && aligned16(proj) && aligned16(out_or_dproj) && aligned16(dout), SDT_ERR_UNSUPPORTED,
+                "sdt_geglu(bf16): inner width must be a multiple of 8 and pointers 16-byte aligned");
+    const int grid = grid_for(M * (I / 8), kThreads, 8);
+    if (!backward) geglu_fwd_bf16_kernel<<<grid, kThreads, 0, st>>>((const uint16_t*)proj, (uint16_t*)out_or_dproj, M, I / 8);
+    else geglu_bwd_bf16_kernel<<<grid, kThreads, 0, st>>>((const uint16_t*)proj, (const uint16_t*)dout, (uint16_t*)out_or_dproj, M, I / 8);
+  } else if (dtype == SDT_F32) {
+    const int grid = grid_for(M * I, kThreads, 8);
+    geglu_f32_kernel<<<grid, kThreads, 0, st>>>((const float*)proj, (const float*)dout, (float*)out_or_dproj, M, I, backward);
+  } else {
+    set_error("sdt_geglu: unsupported dtype %d", dtype);
+    return SDT_ERR_UNSUPPORTED;
+  }
+  SDT_LAUNCH_OK("geglu");
   return SDT_OK;
 }

@@ -180,3 +180,21 @@ def test_flat_adamw_matches_torch(sdt_lib):
     for (n, pr), pg in zip(m_ref.named_parameters(), m_gpu.parameters()):
         err = (pg.cpu() - pr).abs().max().item()
         assert err <= 2e-6 * max(1.0, pr.abs().max().item()), (n, err)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-2), (torch.float32, 1e-5)])
+def test_geglu_forward_backward(sdt_lib, dtype, tol):
+    from scal_sdt_b200.fused import geglu
+    g = torch.Generator().manual_seed(9)
+    proj = torch.randn(3, 37, 2 * 1280, generator=g).to(dtype)
+    dout = torch.randn(3, 37, 1280, generator=g).to(dtype)
+    pr = proj.double().requires_grad_(True)
+    h, gate = pr.chunk(2, dim=-1)
+    ref = h * torch.nn.functional.gelu(gate)
+    ref.backward(dout.double())
+    po = proj.to(DEV).requires_grad_(True)
+    out = geglu(po)
+    out.backward(dout.to(DEV))
+    assert out.shape == ref.shape and out.dtype == dtype
+    assert (out.double().cpu() - ref).norm() <= tol * ref.norm()
+    assert (po.grad.double().cpu() - pr.grad).norm() <= tol * pr.grad.norm()
