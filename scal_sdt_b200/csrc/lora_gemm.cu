@@ -31,6 +31,14 @@ namespace sdt {
 
 using namespace ptx;
 
+// debug timeline of CTA 0: slot <- clock64 (only when a trace buffer was installed with sdt_debug_set(10, ptr))
+#define SDT_TRACE(slot)                                                              \
+  do {                                                                               \
+    if (p.trace != nullptr && blockIdx.x == 0 && (slot) < 128) p.trace[(slot)] = clock64(); \
+  } while (0)
+
+uint64_t debug_get(int key);
+
 template <int BN_, int R_>
 struct LoraGemmCfg {
   static constexpr int BM = 128, BN = BN_, BK = 64, R = R_;
@@ -65,6 +73,7 @@ struct LoraGemmParams {
   int M, N, K;
   int n_tiles, n_groups, group_size, n_items;
   int main;               // 0: only the rank-R projection is computed (t_out), no base GEMM
+  long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
 };
 
 template <int BN, int R>
@@ -96,6 +105,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const bool has_bias = has_main && p.bias != nullptr;
   const bool has_tail = has_main && (R > 0 || has_bias);   // UMMAs issued after the K loop of a tile
 
+  if (threadIdx.x == 0) SDT_TRACE(0);
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_x);
     if (has_main) { prefetch_tmap(&tm_w); prefetch_tmap(&tm_y); }
@@ -124,6 +134,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SDT_TRACE(1);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -144,6 +155,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             mbar_wait(&empty[s], ((it / C::kStages) & 1) ^ 1);
             uint8_t* st = smem + s * C::STAGE_BYTES;
             mbar_arrive_expect_tx(&full[s], tx);
+            if (it == 0) SDT_TRACE(2);
             tma_load_2d(st, &tm_x, kb * C::BK, m0, &full[s]);
             if (has_main) tma_load_2d(st + C::X_BYTES, &tm_w, kb * C::BK, n0, &full[s]);
             if (first) tma_load_2d(st + C::X_BYTES + C::W_BYTES, &tm_la, kb * C::BK, 0, &full[s]);
@@ -196,6 +208,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         umma_commit(&acc_full[pend_tile & 1]);
       }
       __syncwarp();
+      if (lane == 0 && pend_tile < 6) SDT_TRACE(11 + 4 * pend_tile);
       pending = false;
     };
 
@@ -216,9 +229,11 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           mbar_wait(t_ready, (first_ctr - 1) & 1);
           tc_fence_after();
         }
+        if (lane == 0 && tile_ctr < 6) SDT_TRACE(8 + 4 * tile_ctr);
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % C::kStages;
           mbar_wait(&full[s], (it / C::kStages) & 1);
+          if (lane == 0 && tile_ctr < 6 && kb == 0) SDT_TRACE(9 + 4 * tile_ctr);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
@@ -237,6 +252,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           // tile's K loop ends (its accumulator hand-over must not wait for a whole tile)
           if (pending && (kb == nk - 1 || tail_ready())) issue_tail();
         }
+        if (lane == 0 && tile_ctr < 6) SDT_TRACE(10 + 4 * tile_ctr);
         if (first) {
           if (elect_one()) umma_commit(t_full);
           __syncwarp();
@@ -319,6 +335,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_ready);
+            if (warp == 2 && lane == 0 && tile_ctr < 6) SDT_TRACE(40 + tile_ctr);
           }
         }
       }
@@ -342,6 +359,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const int n0 = nt * C::BN;
           const bool rows_live = m0 + q * 32 < p.M;
           mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
+          if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE(48 + 2 * tile_ctr);
           tc_fence_after();
           // chunks c with (c + tile_ctr + half) even belong to this warp: the odd chunk count of BN=160 alternates
           int c = (tile_ctr + half) & 1;
@@ -385,17 +403,21 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE(49 + 2 * tile_ctr);
         }
       }
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (warp == 6 && lane == 0) SDT_TRACE(62);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) SDT_TRACE(63);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (lane == 0) SDT_TRACE(64);
   }
 }
 
@@ -532,6 +554,7 @@ static int launch_lora_gemm(const void* x, const void* w, const float* bias, con
   p.scaling = scaling;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.main = main ? 1 : 0;
+  p.trace = reinterpret_cast<long long*>(debug_get(10));
   const int m_tiles = (int)((M + C::BM - 1) / C::BM);
   p.n_tiles = main ? (int)((N + BN - 1) / BN) : 1;
   const int sms = num_sms();

@@ -1,0 +1,51 @@
+"""Debug timeline of CTA 0 of lora_gemm_kernel (clock64 stamps; see SDT_TRACE in csrc/lora_gemm.cu)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from scal_sdt_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+dev = torch.device("cuda:0")
+NAMES = {0: "entry", 1: "prologue done", 2: "first TMA issued", 62: "epi: stores drained", 63: "all warps done", 64: "dealloc done"}
+for t in range(6):
+    NAMES[8 + 4 * t] = f"mma t{t}: acc_empty ok"
+    NAMES[9 + 4 * t] = f"mma t{t}: first k-block landed"
+    NAMES[10 + 4 * t] = f"mma t{t}: K loop issued"
+    NAMES[11 + 4 * t] = f"mma t{t}: tail issued"
+    NAMES[40 + t] = f"side t{t}: tail operands ready"
+    NAMES[48 + 2 * t] = f"epi t{t}: acc_full"
+    NAMES[49 + 2 * t] = f"epi t{t}: drained"
+
+
+def run(M, K, N, R, bias=True):
+    x = torch.randn(M, K, device=dev).bfloat16()
+    w = torch.randn(N, K, device=dev).bfloat16()
+    b = torch.randn(N, device=dev) if bias else None
+    A = torch.randn(R, K, device=dev).bfloat16()
+    B = torch.randn(N, R, device=dev).bfloat16()
+    y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    t = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
+    trace = torch.zeros(128, dtype=torch.int64, device=dev)
+
+    def call():
+        _lib.check(lib.sdt_lora_linear_fwd(x.data_ptr(), w.data_ptr(), _lib.ptr(b), A.data_ptr(), B.data_ptr(), 0.5, y.data_ptr(),
+                                           t.data_ptr(), M, K, N, R, 1, torch.cuda.current_stream().cuda_stream))
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    lib.sdt_debug_set(10, trace.data_ptr())
+    call()
+    torch.cuda.synchronize()
+    lib.sdt_debug_set(10, 0)
+    tr = trace.cpu().tolist()
+    t0 = tr[0]
+    print(f"--- M={M} K={K} N={N} R={R} bias={bias} (cycles since entry, CTA 0)")
+    for slot, v in sorted(((s, v) for s, v in enumerate(tr) if v), key=lambda kv: kv[1]):
+        print(f"{v - t0:8d}  {NAMES.get(slot, slot)}")
+
+
+for shape in [(32768, 320, 320, 16), (2048, 1280, 1280, 16), (8192, 640, 5120, 16)]:
+    run(*shape)
