@@ -181,7 +181,11 @@ def build_trainer(device, exchange):
     torch.manual_seed(SEED)                                   # identical init on every rank (DDP broadcast equivalent)
     with torch.device(device):
         unet = UNet2DConditionModel(UNetConfig.sd15())
-    unet = unet.to(torch.bfloat16).to(memory_format=torch.channels_last)    # frozen base held in bf16
+    unet = unet.to(torch.bfloat16)                                          # frozen base held in bf16
+    if os.environ.get("SDT_UNET_FORMAT", "nhwc") == "nhwc":
+        unet = unet.to(memory_format=torch.channels_last)
+    else:
+        unet.channels_last = False
     sched = NoiseScheduler(prediction_type="epsilon")
     tr = LatentDiffusionTrainer(unet, sched, lora_unet_targets(WORKLOAD["rank"], WORKLOAD["alpha"]),
                                 optimizer_params={"lr": 5e-4, "beta1": 0.9, "beta2": 0.999, "weight_decay": 2e-2, "eps": 1e-7},

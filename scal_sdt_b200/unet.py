@@ -285,6 +285,7 @@ class UNet2DConditionModel(nn.Module):
             prev, cout = cout, c
             cin = rev[min(i + 1, len(ch) - 1)]
             self.up_blocks.append(UpBlock(cfg, cin, cout, prev, temb_dim, heads_for(cout), up_attn[i], i < len(ch) - 1))
+        self.channels_last = True          # activation memory format of the convolutional trunk
         self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, ch[0], eps=1e-5)
         self.conv_out = nn.Conv2d(ch[0], cfg.out_channels, 3, padding=1)
 
@@ -301,7 +302,8 @@ class UNet2DConditionModel(nn.Module):
         dt = self.dtype
         temb = self.time_embedding(timestep_embedding(timesteps, self.config.block_out_channels[0]).to(dt))
         ctx = encoder_hidden_states.to(dt)
-        x = self.conv_in(sample.to(dt).contiguous(memory_format=torch.channels_last))
+        fmt = torch.channels_last if self.channels_last else torch.contiguous_format
+        x = self.conv_in(sample.to(dt).contiguous(memory_format=fmt))
         skips = [x]
         for blk in self.down_blocks:
             x, outs = blk(x, temb, ctx)
