@@ -131,10 +131,13 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     fence_proxy_async_smem();
   }
   tc_fence_before();
-  __syncthreads();
+  // The producer only needs the mbarriers it initialised itself: it arrives without waiting, so the first TMA loads
+  // are in flight while the other warps finish the TMEM allocation and the constant operands.
+  if (warp == 0) asm volatile("bar.arrive 1, %0;" ::"n"(kGemmThreads) : "memory");
+  else           asm volatile("bar.sync 1, %0;" ::"n"(kGemmThreads) : "memory");
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) SDT_TRACE(1);
+  const uint32_t tmem_base = warp == 0 ? 0u : *tmem_slot;
+  if (threadIdx.x == 32) SDT_TRACE(1);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -406,7 +409,9 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE(49 + 2 * tile_ctr);
         }
       }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      // the staging buffers must stay alive until the bulk stores have read them; the writes themselves are
+      // complete (and visible) at kernel end
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       if (warp == 6 && lane == 0) SDT_TRACE(62);
     }
   }
