@@ -1,0 +1,501 @@
+// K1 / K2(dX), CTA-pair variant: the same fused LoRA projection as lora_gemm.cu, but two SMs of one TPC work on
+// one 256 x BN tile with tcgen05 `cta_group::2`.
+//
+// Why: the single-CTA kernel is bound by shared-memory FILL bandwidth (L2 -> SM), not by the tensor pipe: a 128 x 160
+// tile ingests (128 + 160) x 64 x 2 B per k-block for 2.6 MFLOP, ~71 FLOP/B, and an SM ingests ~50 B/clk (timeline in
+// profiles/).  With cta_group::2 each CTA still owns 128 rows of X but only HALF of the W tile (the tensor core reads
+// the other half from the peer's shared memory), so the same math needs (128 + 80) x 64 x 2 B per SM: ~100 FLOP/B.
+//
+// Roles per CTA are those of lora_gemm.cu (producer / MMA issuer / 4 side warps / 8 epilogue warps) with these changes:
+//   * both CTAs' TMA loads complete on the LEADER's (cluster rank 0) full barrier; only the leader issues UMMAs
+//     (M = 256) and multicasts its tcgen05.commit arrivals to both CTAs;
+//   * side and epilogue warps of both CTAs arrive remotely on the leader's t_ready / acc_empty barriers;
+//   * every B-type operand (W, lora-down, lora-up, bias) is split by rows between the two CTAs.
+#include "sdt_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace sdt {
+
+using namespace ptx;
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                      uint32_t box_rows, uint32_t box_cols, TmapSwizzle swz);
+uint64_t debug_get(int key);
+
+namespace pair {
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a local shared-memory object) inside CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
+  uint32_t out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(p)), "r"(rank));
+  return out;
+}
+__device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-D tile load into OWN shared memory; the bytes complete on the barrier at `bar_cluster_addr` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, int c_inner, int c_row, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(c_inner), "r"(c_row), "r"(bar_cluster_addr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same offset in BOTH CTAs when all prior UMMAs of this thread have completed
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+}  // namespace pair
+
+using namespace pair;
+
+template <int BN_, int R_>
+struct PairCfg {
+  static constexpr int BM = 128, BN = BN_, BK = 64, R = R_, HN = BN_ / 2, HR = R_ / 2;
+  static constexpr int X_BYTES = BM * BK * 2;                       // own 128 rows of X
+  static constexpr int W_BYTES = HN * BK * 2;                       // own half of the W tile
+  static constexpr int LA_BYTES = ((HR * BK * 2 + 1023) / 1024) * 1024;   // own half of the lora-down k-block
+  static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + LA_BYTES;
+  static constexpr int LB_BYTES = ((HN * R * 2 + 1023) / 1024) * 1024;    // own half of the lora-up tile [BN/2, R]
+  static constexpr int KEXT = R + 16;
+  static constexpr int T_SBO = (KEXT / 8) * 128;
+  static constexpr int T_BYTES = (BM / 8) * T_SBO;
+  static constexpr int BIAS_BYTES = ((HN * 32 + 1023) / 1024) * 1024;     // own half of the bias operand [BN/2, 16]
+  static constexpr int STG_BYTES = 8 * 2 * 2048;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int FIXED_BYTES = 1024 + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
+  static constexpr int kStagesMax = (232448 - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
+  static constexpr int SMEM_BYTES = FIXED_BYTES + kStages * STAGE_BYTES;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int ACC1_COL = BN, T_COL = 2 * BN;
+  static_assert(2 * BN + 2 * R <= 512, "TMEM budget");
+  static_assert(BN % 32 == 0 && HN % 8 == 0 && BN <= 256, "BN");
+  static_assert(R == 0 || R == 16 || R == 32 || R == 64, "rank must be padded to 16/32/64");
+  static_assert(kStages >= 3, "pipeline depth");
+  static_assert(W_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
+};
+
+constexpr int kPairThreads = 14 * 32;
+
+struct PairParams {
+  const float* bias;
+  __nv_bfloat16* t_out;
+  float scaling;
+  int M, N, K;
+  int n_tiles, n_groups, group_size, n_items;   // items are (256-row tile, n-group)
+};
+
+template <int BN, int R>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                      const __grid_constant__ CUtensorMap tm_la, const __grid_constant__ CUtensorMap tm_lb,
+                      const __grid_constant__ CUtensorMap tm_y, const PairParams p) {
+  using C = PairCfg<BN, R>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* lb_smem = smem + C::kStages * C::STAGE_BYTES;
+  uint8_t* stg_smem = lb_smem + C::LB_BYTES;
+  uint8_t* t_smem = stg_smem + C::STG_BYTES;
+  uint8_t* bias_smem = t_smem + C::T_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + C::BIAS_BYTES);
+  uint64_t* full = bars;                       // [kStages]  leader's is the live one
+  uint64_t* empty = bars + C::kStages;         // [kStages]  both (multicast commit)
+  uint64_t* acc_full = bars + 2 * C::kStages;  // [2]        both
+  uint64_t* acc_empty = acc_full + 2;          // [2]        leader's (16 remote/local arrivals)
+  uint64_t* t_full = acc_empty + 2;            //            both
+  uint64_t* t_ready = t_full + 1;              //            leader's (8 arrivals)
+  uint64_t* lb_full = t_ready + 1;             //            leader's
+  uint64_t* lb_empty = lb_full + 1;            //            both
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lb_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int nk = (p.K + C::BK - 1) / C::BK;
+  const bool has_bias = p.bias != nullptr;
+  const bool has_tail = R > 0 || has_bias;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_x);
+    prefetch_tmap(&tm_w);
+    prefetch_tmap(&tm_y);
+    if (R > 0) { prefetch_tmap(&tm_la); prefetch_tmap(&tm_lb); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 16); }
+    mbar_init(t_full, 1);
+    mbar_init(t_ready, 8);
+    mbar_init(lb_full, 1);
+    mbar_init(lb_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, C::TMEM_COLS);
+  if (warp >= 2 && warp < 6) {
+    const int row = (warp - 2) * 32 + lane;
+    uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(trow + (R / 8) * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // bf16 1.0, 1.0
+    *reinterpret_cast<uint4*>(trow + (R / 8 + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
+    for (int n = row; n < C::HN; n += 128)
+      *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + 128 + (n & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    if (lane == 0) {
+      const uint32_t lb_full_leader = map_to_rank(lb_full, 0);
+      uint32_t it = 0, tile_ctr = 0;
+      for (int item = pair_id; item < p.n_items; item += n_pairs) {
+        const int m0 = (item / p.n_groups) * 2 * C::BM + (int)rank * C::BM;
+        const int g = item % p.n_groups;
+        const int nt0 = g * p.group_size;
+        const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+        for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
+          const bool first = (nt == nt0) && R > 0;
+          const int n0 = nt * C::BN + (int)rank * C::HN;
+          const uint32_t tx = 2u * (C::X_BYTES + C::W_BYTES + (first ? C::HR * C::BK * 2 : 0));
+          for (int kb = 0; kb < nk; ++kb, ++it) {
+            const int s = it % C::kStages;
+            mbar_wait(&empty[s], ((it / C::kStages) & 1) ^ 1);
+            uint8_t* st = smem + s * C::STAGE_BYTES;
+            const uint32_t full_leader = map_to_rank(&full[s], 0);
+            if (leader) mbar_arrive_expect_tx(&full[s], tx);
+            tma_load_2d_pair(st, &tm_x, kb * C::BK, m0, full_leader);
+            tma_load_2d_pair(st + C::X_BYTES, &tm_w, kb * C::BK, n0, full_leader);
+            if (first) tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES, &tm_la, kb * C::BK, (int)rank * C::HR, full_leader);
+          }
+          if (R > 0) {
+            mbar_wait(lb_empty, (tile_ctr & 1) ^ 1);
+            if (leader) mbar_arrive_expect_tx(lb_full, 2u * C::HN * R * 2);
+            tma_load_2d_pair(lb_smem, &tm_lb, 0, n0, lb_full_leader);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =================================
+    if (leader) {
+      constexpr int RR = R > 0 ? R : 16;
+      constexpr uint32_t idesc_main = make_idesc_bf16(256, BN, 0, 0);
+      constexpr uint32_t idesc_t = make_idesc_bf16(256, RR, 0, 0);
+      constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
+      constexpr uint32_t lb_layout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
+      constexpr uint64_t d_lb = make_smem_desc_base(16, 8 * RR * 2, lb_layout);
+      constexpr uint64_t d_t = make_smem_desc_base(128, C::T_SBO, kLayoutNone);
+      constexpr uint64_t d_bias = make_smem_desc_base(128, 256, kLayoutNone);
+      uint32_t it = 0, tile_ctr = 0, first_ctr = 0, ready_ctr = 0;
+      bool pending = false, pend_needs_ready = false;
+      uint32_t pend_tile = 0, pend_ready = 0;
+
+      auto tail_ready = [&]() -> bool {
+        if (R > 0 && !mbar_test(lb_full, pend_tile & 1)) return false;
+        if (pend_needs_ready && !mbar_test(t_ready, pend_ready & 1)) return false;
+        return true;
+      };
+      auto issue_tail = [&]() {
+        if (R > 0) mbar_wait(lb_full, pend_tile & 1);
+        if (pend_needs_ready) mbar_wait(t_ready, pend_ready & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d = tmem_base + (pend_tile & 1) * C::ACC1_COL;
+          const uint32_t ta = smem_u32(t_smem), ba = smem_u32(lb_smem);
+#pragma unroll
+          for (int k = 0; k < R / 16; ++k)
+            umma2_f16_ss(d, smem_desc(d_t, ta + k * 256), smem_desc(d_lb, ba + k * 32), idesc_main, 1u);
+          if (has_bias) umma2_f16_ss(d, smem_desc(d_t, ta + (R / 16) * 256), smem_desc(d_bias, smem_u32(bias_smem)), idesc_main, 1u);
+          umma2_commit_both(lb_empty);
+          umma2_commit_both(&acc_full[pend_tile & 1]);
+        }
+        __syncwarp();
+        pending = false;
+      };
+
+      for (int item = pair_id; item < p.n_items; item += n_pairs) {
+        const int g = item % p.n_groups;
+        const int nt0 = g * p.group_size;
+        const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+        for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
+          const bool first = (nt == nt0) && R > 0;
+          const uint32_t buf = tile_ctr & 1;
+          const uint32_t d_main = tmem_base + buf * C::ACC1_COL;
+          const uint32_t d_tacc = tmem_base + C::T_COL + (first_ctr & 1) * RR;
+          mbar_wait(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < nk; ++kb, ++it) {
+            const int s = it % C::kStages;
+            mbar_wait(&full[s], (it / C::kStages) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
+              const uint32_t wa = xa + C::X_BYTES;
+              const uint32_t la = wa + C::W_BYTES;
+#pragma unroll
+              for (int k = 0; k < C::BK / 16; ++k) {
+                const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
+                umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), idesc_main, (kb | k) != 0);
+                if (first) umma2_f16_ss(d_tacc, a_desc, smem_desc(d_sw128, la + k * 32), idesc_t, (kb | k) != 0);
+              }
+              umma2_commit_both(&empty[s]);
+            }
+            __syncwarp();
+            if (pending && (kb == nk - 1 || tail_ready())) issue_tail();
+          }
+          if (first) {
+            if (elect_one()) umma2_commit_both(t_full);
+            __syncwarp();
+            ++first_ctr;
+          }
+          if (has_tail) {
+            pending = true;
+            pend_tile = tile_ctr;
+            pend_needs_ready = first || has_bias;
+            pend_ready = ready_ctr;
+            if (pend_needs_ready) ++ready_ctr;
+            if (tail_ready()) issue_tail();
+          } else {
+            if (elect_one()) umma2_commit_both(&acc_full[buf]);
+            __syncwarp();
+          }
+        }
+      }
+      if (pending) issue_tail();
+    }
+  } else if (warp < 6) {
+    // ===================================== side warps (both CTAs) ========================================
+    constexpr int RR = R > 0 ? R : 16;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tid = (warp - 2) * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_ready_leader = map_to_rank(t_ready, 0);
+    uint32_t tile_ctr = 0, first_ctr = 0;
+    if (has_tail) {
+      for (int item = pair_id; item < p.n_items; item += n_pairs) {
+        const int m0 = (item / p.n_groups) * 2 * C::BM + (int)rank * C::BM;
+        const int g = item % p.n_groups;
+        const int nt0 = g * p.group_size;
+        const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+        for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
+          const bool first = (nt == nt0) && R > 0;
+          if (has_bias) {
+            if (tile_ctr > 0) mbar_wait(lb_empty, (tile_ctr - 1) & 1);
+            const int n0 = nt * C::BN + (int)rank * C::HN;
+            for (int n = tid; n < C::HN; n += 128) {
+              const float b = (n0 + n < p.N) ? __ldg(p.bias + n0 + n) : 0.f;
+              const float hi = round_bf16(b);
+              *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) = make_uint4(pack_bf16x2(hi, b - hi), 0u, 0u, 0u);
+            }
+          }
+          if (first) {
+            mbar_wait(t_full, first_ctr & 1);
+            tc_fence_after();
+            uint32_t packed[RR / 2];
+#pragma unroll
+            for (int c = 0; c < RR / 16; ++c) {
+              uint32_t v[16];
+              tmem_ld_x16(lane_addr + C::T_COL + (first_ctr & 1) * RR + c * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                packed[c * 8 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling);
+            }
+            uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
+#pragma unroll
+            for (int kc = 0; kc < RR / 8; ++kc)
+              *reinterpret_cast<uint4*>(trow + kc * 128) = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
+            if (p.t_out != nullptr && g == 0 && m0 + row < p.M) {
+              uint4* dst = reinterpret_cast<uint4*>(p.t_out + (size_t)(m0 + row) * RR);
+#pragma unroll
+              for (int kc = 0; kc < RR / 8; ++kc)
+                dst[kc] = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
+            }
+            ++first_ctr;
+          }
+          if (first || has_bias) {
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) remote_arrive(t_ready_leader);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue warps (both CTAs) ====================================
+    const int e = warp - 6;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* stg = stg_smem + e * 4096;
+    uint32_t acc_empty_leader[2] = {map_to_rank(&acc_empty[0], 0), map_to_rank(&acc_empty[1], 0)};
+    uint32_t tile_ctr = 0, stores = 0;
+    for (int item = pair_id; item < p.n_items; item += n_pairs) {
+      const int m0 = (item / p.n_groups) * 2 * C::BM + (int)rank * C::BM;
+      const int g = item % p.n_groups;
+      const int nt0 = g * p.group_size;
+      const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+      for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
+        const uint32_t buf = tile_ctr & 1;
+        const int n0 = nt * C::BN;
+        const bool rows_live = m0 + q * 32 < p.M;
+        mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
+        tc_fence_after();
+        int c = (tile_ctr + half) & 1;
+        uint32_t v[32];
+        bool have = c < C::BN / 32 && n0 + c * 32 < p.N;
+        if (have) tmem_ld_x32(lane_addr + buf * C::ACC1_COL + c * 32, v);
+        while (have) {
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          const int col0 = n0 + c * 32;
+          c += 2;
+          have = c < C::BN / 32 && n0 + c * 32 < p.N;
+          if (have) tmem_ld_x32(lane_addr + buf * C::ACC1_COL + c * 32, v);
+          if (rows_live) {
+            uint8_t* sb = stg + (stores & 1) * 2048;
+            if (stores >= 2) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
+            }
+            uint8_t* srow = sb + lane * 64;
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tm_y)),
+                           "r"(col0), "r"(m0 + q * 32), "r"(smem_u32(sb))
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++stores;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) remote_arrive(acc_empty_leader[buf]);
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+
+  // neither CTA may leave (or free TMEM) while the other can still touch its shared memory / barriers / TMEM
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, C::TMEM_COLS);
+  }
+}
+
+static void choose_groups_pair(int m_tiles, int n_tiles, int BN, int R, int pairs, int* group_size, int* n_groups) {
+  if (R == 0) { *group_size = 1; *n_groups = n_tiles; return; }
+  double best = 1e30;
+  int best_gs = 1;
+  for (int gs = 1; gs <= n_tiles; ++gs) {
+    const int groups = (n_tiles + gs - 1) / gs;
+    const long items = (long)m_tiles * groups;
+    const long rounds = (items + pairs - 1) / pairs;
+    const double cost = (double)rounds * (gs * (double)BN + R + 48.0);
+    if (cost < best - 1e-9) { best = cost; best_gs = gs; }
+  }
+  *group_size = best_gs;
+  *n_groups = (n_tiles + best_gs - 1) / best_gs;
+}
+
+template <int BN, int R>
+static int launch_pair(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling,
+                       void* y, void* t_out, int64_t M, int64_t K, int64_t N, cudaStream_t st) {
+  using C = PairCfg<BN, R>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tm_x, tm_w, tm_la, tm_lb, tm_y;
+  int rc = make_tmap_2d_bf16(&tm_x, x, M, K, K * 2, C::BM, C::BK, TMAP_SW_128);
+  if (rc != SDT_OK) return rc;
+  rc = make_tmap_2d_bf16(&tm_w, w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);
+  if (rc != SDT_OK) return rc;
+  rc = make_tmap_2d_bf16(&tm_y, y, M, N, N * 2, 32, 32, TMAP_SW_64);
+  if (rc != SDT_OK) return rc;
+  if (R > 0) {
+    rc = make_tmap_2d_bf16(&tm_la, la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
+    if (rc != SDT_OK) return rc;
+    rc = make_tmap_2d_bf16(&tm_lb, lb, N, R, (uint64_t)R * 2, C::HN, R, R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
+    if (rc != SDT_OK) return rc;
+  } else {
+    tm_la = tm_x;
+    tm_lb = tm_x;
+  }
+  PairParams p;
+  p.bias = bias;
+  p.t_out = reinterpret_cast<__nv_bfloat16*>(t_out);
+  p.scaling = scaling;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  const int m_tiles = (int)((M + 2 * C::BM - 1) / (2 * C::BM));
+  p.n_tiles = (int)((N + BN - 1) / BN);
+  const int pairs_max = num_sms() / 2;
+  choose_groups_pair(m_tiles, p.n_tiles, BN, R, pairs_max, &p.group_size, &p.n_groups);
+  p.n_items = m_tiles * p.n_groups;
+  const int pairs = p.n_items < pairs_max ? p.n_items : pairs_max;
+  lora_gemm_pair_kernel<BN, R><<<2 * pairs, kPairThreads, C::SMEM_BYTES, st>>>(tm_x, tm_w, tm_la, tm_lb, tm_y, p);
+  SDT_LAUNCH_OK("lora_gemm_pair");
+  return SDT_OK;
+}
+
+// CTA-pair entry; same contract as lora_gemm_bf16 with main == true
+int lora_gemm_pair_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
+                        void* t_out, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st) {
+  const bool bn160 = (N % 160 == 0) || (N % 128 != 0 && N > 128);
+#define SDT_PAIR(BN, R) return launch_pair<BN, R>(x, w, bias, la, lb, scaling, y, t_out, M, K, N, st)
+  if (bn160) {
+    switch (r) { case 0: SDT_PAIR(160, 0); case 16: SDT_PAIR(160, 16); case 32: SDT_PAIR(160, 32); default: SDT_PAIR(160, 64); }
+  } else {
+    switch (r) { case 0: SDT_PAIR(128, 0); case 16: SDT_PAIR(128, 16); case 32: SDT_PAIR(128, 32); default: SDT_PAIR(128, 64); }
+  }
+#undef SDT_PAIR
+}
+
+}  // namespace sdt
