@@ -583,9 +583,10 @@ int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* 
   SDT_REQUIRE(r == 0 || r == 16 || r == 32 || r == 64, SDT_ERR_UNSUPPORTED,
               "lora_gemm: padded rank must be 0, 16, 32 or 64 (got %d)", r);
   SDT_REQUIRE(main || r > 0, SDT_ERR_ARG, "lora_gemm: nothing to compute");
-  // CTA-pair (cta_group::2) kernel whenever there is a base GEMM and at least one full pair of row tiles;
+  // CTA-pair (cta_group::2) kernel when there is a base GEMM, at least one full pair of row tiles and a K loop long
+  // enough (>= 8 k-blocks) to amortise the cross-CTA hand-shakes (measured: K = 320 is faster on the single-CTA kernel);
   // sdt_debug_set(11, 1) forces the single-CTA kernel (A/B measurements)
-  if (main && M >= 256 && debug_get(11) == 0)
+  if (main && M >= 256 && K >= 512 && debug_get(11) == 0)
     return lora_gemm_pair_bf16(x, w, bias, la, lb, scaling, y, t_out, M, K, N, r, st);
   const bool bn160 = !main || (N % 160 == 0) || (N % 128 != 0 && N > 128);
 #define SDT_GEMM(BN, R) return launch_lora_gemm<BN, R>(x, w, bias, la, lb, scaling, y, t_out, M, K, N, main, st)

@@ -174,6 +174,15 @@ def main():
         guarded("bwd r32 1000x640x640", bwd_case, 1000, 640, 640, 32, 32)
         guarded("bwd r64 2048x1280x1280", bwd_case, 2048, 1280, 1280, 64, 64)
         guarded("bwd r16 4096x2560x320", bwd_case, 4096, 2560, 320, 16, 16)
+    if "ab" in which:
+        shapes = [(32768, 320, 320), (32768, 320, 2560), (32768, 1280, 320), (8192, 640, 640), (8192, 640, 5120),
+                  (8192, 2560, 640), (2048, 1280, 1280), (2048, 1280, 10240), (2048, 5120, 1280)]
+        for name, k11, k12 in (("single", 1, 0), ("pair160", 0, 1), ("auto", 0, 0)):
+            lib.sdt_debug_set(11, k11); lib.sdt_debug_set(12, k12)
+            log(f"== variant {name}")
+            for (M, K, N) in shapes:
+                guarded(f"{name} fwd {M}x{K}x{N}", fwd_case, M, K, N, 16, 16, True, True)
+        lib.sdt_debug_set(11, 0); lib.sdt_debug_set(12, 0)
     if "time" in which:
         for (M, K, N) in [(32768, 320, 320), (32768, 320, 2560), (32768, 1280, 320), (8192, 640, 640), (8192, 640, 5120),
                           (8192, 2560, 640), (2048, 1280, 1280), (2048, 1280, 10240), (2048, 5120, 1280)]:
