@@ -491,9 +491,10 @@ int lora_gemm_pair_bf16(const void* x, const void* w, const float* bias, const v
   const bool bn160 = (N % 160 == 0) || (N % 128 != 0 && N > 128);
 #define SDT_PAIR(BN, R) return launch_pair<BN, R>(x, w, bias, la, lb, scaling, y, t_out, M, K, N, st)
   // wide tiles (more FLOP per byte brought into the SM) when the rank accumulators still fit next to two 224-column
-  // main accumulators (2*224 + 2*R <= 512) and the ragged last tile wastes little
+  // main accumulators (2*224 + 2*R <= 512), the ragged last tile wastes little and there are enough column tiles to keep
+  // every pair busy (measured: N = 640 / 1280 are faster with 160-wide tiles)
   const int64_t n224 = (N + 223) / 224 * 224;
-  if (r <= 32 && n224 * 100 <= N * 106 && debug_get(12) == 0) {
+  if (r <= 32 && N >= 2048 && n224 * 100 <= N * 106 && debug_get(12) == 0) {
     switch (r) { case 0: SDT_PAIR(224, 0); case 16: SDT_PAIR(224, 16); default: SDT_PAIR(224, 32); }
   }
   if (bn160) {
