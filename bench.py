@@ -24,6 +24,18 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm (rank 0 only) is the CPU path on ALL host
+    # cores, so the thread-count variables must be fixed before torch (OpenMP / MKL) initialises
+    _n = os.cpu_count() or 1
+    try:
+        import psutil
+        _n = psutil.cpu_count(logical=False) or _n
+    except Exception:  # noqa: BLE001
+        pass
+    for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(_n)
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -331,13 +343,13 @@ def ours_main(args):
     # ---- roofline of the dominant kernel: fused LoRA forward GEMM, timed per launch inside a real step ----
     from scal_sdt_b200 import lora as lora_mod
     roof = None
+    lora_mod.PROFILE = [] if rank == 0 else None
+    for i in range(2):                      # every rank steps (the gradient all-reduce is collective); rank 0 records
+        tr.step(dev[i % len(dev)])
+    torch.cuda.synchronize()
+    rec = lora_mod.PROFILE
+    lora_mod.PROFILE = None
     if rank == 0:
-        lora_mod.PROFILE = []
-        for i in range(2):
-            tr.step(dev[i % len(dev)])
-        torch.cuda.synchronize()
-        rec = lora_mod.PROFILE
-        lora_mod.PROFILE = None
         f_fwd, f_bwd = site_flops(rec)
         t_fwd = sum(a.elapsed_time(b) for kind, *_, a, b in rec if kind == "fwd") * 1e-3
         t_bwd = sum(a.elapsed_time(b) for kind, *_, a, b in rec if kind == "bwd") * 1e-3
