@@ -257,6 +257,11 @@ def elementwise_roofline(device, peaks):
 
 
 def ours_main(args):
+    # Native libraries (NCCL's version banner, cuDNN warnings) write to fd 1; the contract is ONE JSON line on stdout,
+    # so everything else is routed to stderr and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     from scal_sdt_b200 import GradExchange, _lib, build
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -302,7 +307,7 @@ def ours_main(args):
         tr.step(dev[0])
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        print(json.dumps({"profiled": "one training step", "workload": WORKLOAD["name"]}), flush=True)
+        os.write(real_stdout, (json.dumps({"profiled": "one training step", "workload": WORKLOAD["name"]}) + "\n").encode())
         exchange.close()
         return 0
 
@@ -385,7 +390,8 @@ def ours_main(args):
             "gpu_launches": int(launches), "final_loss": final_loss, "e2e_last_loss": step_loss,
             "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     exchange.close()
     if world > 1:
         dist.destroy_process_group()

@@ -155,6 +155,15 @@ int sdt_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, cons
 int sdt_geglu(const void* proj, const void* dout, void* out_or_dproj, int64_t M, int64_t I, int backward, int dtype,
               void* stream);
 
+/* ---- f2: GroupNorm (+ SiLU) on channels-last bf16 activations [B, HW, C], frozen affine (gamma, beta f32[C]) ----
+ * forward : stats f32[B,G,2] (written: per-group sum, sum of squares); y = act((x - mean) * rstd * gamma + beta)
+ * backward: dx from (x, dout, stats); bstats f32[B,G,2] is scratch.  Needs C % 8 == 0 and C / G >= 8.
+ */
+int sdt_group_norm_nhwc(const void* x, const float* gamma, const float* beta, float* stats, void* y, int64_t B, int64_t HW,
+                        int C, int G, float eps, int silu, void* stream);
+int sdt_group_norm_nhwc_bwd(const void* x, const void* dout, const float* gamma, const float* beta, const float* stats,
+                            float* bstats, void* dx, int64_t B, int64_t HW, int C, int G, float eps, int silu, void* stream);
+
 /* ---- K6: data-parallel LoRA-gradient exchange (replaces Lightning DDP, train.py:98-109) -------
  * One NCCL communicator per process (libnccl is resolved at run time with dlopen, so the library
  * loads on machines without NCCL).  sdt_allreduce averages `count` elements in place.

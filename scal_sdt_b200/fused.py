@@ -39,3 +39,53 @@ def geglu(proj: torch.Tensor) -> torch.Tensor:
     """``h * gelu(gate)`` for ``proj = [h | gate]`` along the last dimension (CUDA tensors, bf16 or fp32)."""
     _lib.require_cuda(proj)
     return _GEGLU.apply(proj)
+
+
+class _GroupNormNHWC(torch.autograd.Function):
+    """GroupNorm with frozen affine parameters (+ optional SiLU) on a channels-last bf16 tensor."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, silu):
+        B, C, H, W = x.shape
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        stats = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().sdt_group_norm_nhwc(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), y.data_ptr(),
+                                                   B, H * W, C, groups, eps, int(silu), _lib.stream_ptr()), "sdt_group_norm_nhwc")
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.cfg = (groups, eps, silu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, gamma, beta, stats = ctx.saved_tensors
+        groups, eps, silu = ctx.cfg
+        B, C, H, W = x.shape
+        d = dout.contiguous(memory_format=torch.channels_last)
+        if d.dtype != x.dtype:
+            d = d.to(x.dtype)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        bstats = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().sdt_group_norm_nhwc_bwd(x.data_ptr(), d.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                       stats.data_ptr(), bstats.data_ptr(), dx.data_ptr(), B, H * W, C, groups,
+                                                       eps, int(silu), _lib.stream_ptr()), "sdt_group_norm_nhwc_bwd")
+        return dx, None, None, None, None, None
+
+
+def group_norm_nhwc_supported(norm: torch.nn.GroupNorm, x: torch.Tensor) -> bool:
+    c, g = norm.num_channels, norm.num_groups
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+            and not norm.weight.requires_grad and not norm.bias.requires_grad and c % 8 == 0 and c // g >= 8 and g <= 128
+            and c <= 4096)
+
+
+def group_norm_act(norm: torch.nn.GroupNorm, x: torch.Tensor, silu: bool) -> torch.Tensor:
+    """``silu(norm(x))`` / ``norm(x)``: fused channels-last kernels when they apply, torch otherwise (host model code)."""
+    if group_norm_nhwc_supported(norm, x):
+        cache = getattr(norm, "_sdt_affine_f32", None)
+        key = (norm.weight.data_ptr(), norm.weight._version, norm.bias._version)
+        if cache is None or cache[0] != key:
+            cache = (key, norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous())
+            norm._sdt_affine_f32 = cache
+        return _GroupNormNHWC.apply(x, cache[1], cache[2], norm.num_groups, float(norm.eps), bool(silu))
+    y = norm(x)
+    return torch.nn.functional.silu(y) if silu else y

@@ -19,6 +19,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .fused import group_norm_act
+
 
 @dataclass
 class UNetConfig:
@@ -77,9 +79,9 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
-        h = self.conv1(F.silu(self.norm1(x)))
+        h = self.conv1(group_norm_act(self.norm1, x, True))
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = self.conv2(group_norm_act(self.norm2, h, True))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
@@ -158,7 +160,7 @@ class Transformer2DModel(nn.Module):
     def forward(self, x, context):
         b, c, h, w = x.shape
         res = x
-        y = self.norm(x)
+        y = group_norm_act(self.norm, x, False)
         if self.linear_proj:
             y = self.proj_in(y.permute(0, 2, 3, 1).reshape(b, h * w, c))
         else:
@@ -311,5 +313,5 @@ class UNet2DConditionModel(nn.Module):
         x = self.mid_block(x, temb, ctx)
         for blk in self.up_blocks:
             x = blk(x, skips, temb, ctx)
-        x = self.conv_out(F.silu(self.conv_norm_out(x)))
+        x = self.conv_out(group_norm_act(self.conv_norm_out, x, True))
         return SimpleNamespace(sample=x)

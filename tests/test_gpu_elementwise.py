@@ -198,3 +198,34 @@ def test_geglu_forward_backward(sdt_lib, dtype, tol):
     assert out.shape == ref.shape and out.dtype == dtype
     assert (out.double().cpu() - ref).norm() <= tol * ref.norm()
     assert (po.grad.double().cpu() - pr.grad).norm() <= tol * pr.grad.norm()
+
+
+@pytest.mark.parametrize("C,G,H,W,silu", [(320, 32, 16, 16, True), (960, 32, 8, 12, True), (640, 32, 7, 5, False),
+                                          (2560, 32, 4, 4, True), (1280, 32, 16, 16, False)])
+def test_group_norm_nhwc_forward_backward(sdt_lib, C, G, H, W, silu):
+    from scal_sdt_b200.fused import group_norm_act, group_norm_nhwc_supported
+    torch.manual_seed(C + H)
+    norm = torch.nn.GroupNorm(G, C, eps=1e-5)
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.3)
+        norm.bias.normal_(0.0, 0.3)
+    x = (torch.randn(3, C, H, W) * 1.7 + 0.4).bfloat16()
+    dout = torch.randn(3, C, H, W).bfloat16()
+    # reference: fp64 on the same bf16-rounded inputs and parameters
+    ref_norm = torch.nn.GroupNorm(G, C, eps=1e-5).double()
+    with torch.no_grad():
+        ref_norm.weight.copy_(norm.weight.bfloat16().double())
+        ref_norm.bias.copy_(norm.bias.bfloat16().double())
+    xr = x.double().requires_grad_(True)
+    yr = ref_norm(xr)
+    if silu:
+        yr = torch.nn.functional.silu(yr)
+    yr.backward(dout.double())
+    gn = norm.to(DEV).to(torch.bfloat16).requires_grad_(False)
+    xo = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    assert group_norm_nhwc_supported(gn, xo)
+    yo = group_norm_act(gn, xo, silu)
+    assert yo.is_contiguous(memory_format=torch.channels_last) and yo.dtype == torch.bfloat16
+    yo.backward(dout.to(DEV))
+    assert (yo.double().cpu() - yr).norm() <= 1e-2 * yr.norm()
+    assert (xo.grad.double().cpu() - xr.grad).norm() <= 1e-2 * xr.grad.norm()
