@@ -297,10 +297,17 @@ def ours_main(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up ----
+    # ---- warm-up (eager), then capture the whole step as one CUDA graph ----
     for i in range(max(args.warmup, 3)):
         tr.step(dev[i % len(dev)])
     barrier()
+    use_graph = not args.no_graph and not args.profile_step
+    if use_graph:
+        tr.enable_cuda_graph(dev[0])
+        for i in range(2):
+            tr.graphed_step(dev[i % len(dev)])
+        barrier()
+    do_step = tr.graphed_step if use_graph else tr.step
 
     if args.profile_step:
         torch.cuda.profiler.start()
@@ -318,7 +325,7 @@ def ours_main(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            loss = tr.step(dev[i % len(dev)])
+            loss = do_step(dev[i % len(dev)])
         e1.record()
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -336,8 +343,11 @@ def ours_main(args):
     t0.record()
     for i in range(args.steps):
         hb = host[i % len(host)]
-        batch = {k: v.to(device, non_blocking=True) for k, v in hb.items()}
-        loss_host[i:i + 1].copy_(tr.step(batch).detach().reshape(1), non_blocking=True)
+        if use_graph:       # graphed_step copies the pinned host batch straight into the graph's static input buffers
+            batch = hb
+        else:
+            batch = {k: v.to(device, non_blocking=True) for k, v in hb.items()}
+        loss_host[i:i + 1].copy_(do_step(batch).detach().reshape(1), non_blocking=True)
     t1.record()
     barrier()
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
@@ -382,7 +392,7 @@ def ours_main(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "global_batch": world * B, "lora_params": n_lora,
                        "parallelism": f"dp{world}", "optimizer": "fused AdamW over the flat LoRA arena",
-                       "gradient_checkpointing": False,
+                       "gradient_checkpointing": False, "cuda_graph": bool(use_graph),
                        "l2": "no flush: a step streams > 10 GB of weights/activations, far beyond the 126 MB L2"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "latents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -405,6 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -55,33 +55,46 @@ gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dou
     const int64_t r_end = min(r_begin + (int64_t)s.rows_per_cta, s.HW);
     const uint4* xb = reinterpret_cast<const uint4*>(x) + ((size_t)b * s.HW) * s.vecs + v;
     const uint4* db = BWD ? reinterpret_cast<const uint4*>(dout) + ((size_t)b * s.HW) * s.vecs + v : nullptr;
-    for (int64_t r = r_begin + rp; r < r_end; r += s.rows_par) {
-      const uint4 xv = ld_stream(xb + r * s.vecs);
-      const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xv);
-      uint4 dv = make_uint4(0, 0, 0, 0);
-      if (BWD) dv = ld_stream(db + r * s.vecs);
-      const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv);
+    constexpr int U = 4;                      // independent 16-byte loads in flight per thread
+    for (int64_t r = r_begin + rp; r < r_end; r += (int64_t)U * s.rows_par) {
+      uint4 xvv[U], dvv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xe = bf16_bits_to_f32((j & 1) ? (xw[j >> 1] >> 16) : (xw[j >> 1] & 0xffffu));
-        const bool second = (c0 + j) / s.cpg != g0;
-        float p, pq;
-        if (!BWD) {
-          p = xe;
-          pq = xe * xe;
-        } else {
-          const float de = bf16_bits_to_f32((j & 1) ? (dw[j >> 1] >> 16) : (dw[j >> 1] & 0xffffu));
-          const float xhat = (xe - mean[second]) * rstd[second];
-          float dz = de;
-          if (SILU) {
-            const float z = xhat * gm[j] + bt[j];
-            const float sg = sigmoidf_(z);
-            dz = de * sg * (1.0f + z * (1.0f - sg));
-          }
-          p = dz * gm[j];
-          pq = p * xhat;
+      for (int u = 0; u < U; ++u) {
+        const int64_t ru = r + (int64_t)u * s.rows_par;
+        xvv[u] = make_uint4(0, 0, 0, 0);
+        dvv[u] = make_uint4(0, 0, 0, 0);
+        if (ru < r_end) {
+          xvv[u] = ld_stream(xb + ru * s.vecs);
+          if (BWD) dvv[u] = ld_stream(db + ru * s.vecs);
         }
-        if (second) { a1 += p; q1 += pq; } else { a0 += p; q0 += pq; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r + (int64_t)u * s.rows_par >= r_end) break;
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xvv[u]);
+        const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dvv[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xe = bf16_bits_to_f32((j & 1) ? (xw[j >> 1] >> 16) : (xw[j >> 1] & 0xffffu));
+          const bool second = (c0 + j) / s.cpg != g0;
+          float p, pq;
+          if (!BWD) {
+            p = xe;
+            pq = xe * xe;
+          } else {
+            const float de = bf16_bits_to_f32((j & 1) ? (dw[j >> 1] >> 16) : (dw[j >> 1] & 0xffffu));
+            const float xhat = (xe - mean[second]) * rstd[second];
+            float dz = de;
+            if (SILU) {
+              const float z = xhat * gm[j] + bt[j];
+              const float sg = sigmoidf_(z);
+              dz = de * sg * (1.0f + z * (1.0f - sg));
+            }
+            p = dz * gm[j];
+            pq = p * xhat;
+          }
+          if (second) { a1 += p; q1 += pq; } else { a0 += p; q0 += pq; }
+        }
       }
     }
     atomicAdd(&acc[2 * g0], a0);
@@ -124,32 +137,46 @@ gn_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dou
   const uint4* xb = reinterpret_cast<const uint4*>(x) + ((size_t)b * s.HW) * s.vecs + v;
   const uint4* db = BWD ? reinterpret_cast<const uint4*>(dout) + ((size_t)b * s.HW) * s.vecs + v : nullptr;
   uint4* ob = reinterpret_cast<uint4*>(out) + ((size_t)b * s.HW) * s.vecs + v;
-  for (int64_t r = r_begin + rp; r < r_end; r += s.rows_par) {
-    const uint4 xv = ld_stream(xb + r * s.vecs);
-    const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xv);
-    uint4 dv = make_uint4(0, 0, 0, 0);
-    if (BWD) dv = ld_stream(db + r * s.vecs);
-    const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv);
-    float o[8];
+  constexpr int U = 4;
+  for (int64_t r = r_begin + rp; r < r_end; r += (int64_t)U * s.rows_par) {
+    uint4 xvv[U], dvv[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xe = bf16_bits_to_f32((j & 1) ? (xw[j >> 1] >> 16) : (xw[j >> 1] & 0xffffu));
-      const bool second = (c0 + j) / s.cpg != g0;
-      const float xhat = (xe - mean[second]) * rstd[second];
-      const float z = xhat * gm[j] + bt[j];
-      if (!BWD) {
-        o[j] = SILU ? z * sigmoidf_(z) : z;
-      } else {
-        const float de = bf16_bits_to_f32((j & 1) ? (dw[j >> 1] >> 16) : (dw[j >> 1] & 0xffffu));
-        float dz = de;
-        if (SILU) {
-          const float sg = sigmoidf_(z);
-          dz = de * sg * (1.0f + z * (1.0f - sg));
-        }
-        o[j] = rstd[second] * (dz * gm[j] - p1[second] - xhat * p2[second]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + (int64_t)u * s.rows_par;
+      xvv[u] = make_uint4(0, 0, 0, 0);
+      dvv[u] = make_uint4(0, 0, 0, 0);
+      if (ru < r_end) {
+        xvv[u] = ld_stream(xb + ru * s.vecs);
+        if (BWD) dvv[u] = ld_stream(db + ru * s.vecs);
       }
     }
-    st_stream(ob + r * s.vecs, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + (int64_t)u * s.rows_par;
+      if (ru >= r_end) break;
+      const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xvv[u]);
+      const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dvv[u]);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xe = bf16_bits_to_f32((j & 1) ? (xw[j >> 1] >> 16) : (xw[j >> 1] & 0xffffu));
+        const bool second = (c0 + j) / s.cpg != g0;
+        const float xhat = (xe - mean[second]) * rstd[second];
+        const float z = xhat * gm[j] + bt[j];
+        if (!BWD) {
+          o[j] = SILU ? z * sigmoidf_(z) : z;
+        } else {
+          const float de = bf16_bits_to_f32((j & 1) ? (dw[j >> 1] >> 16) : (dw[j >> 1] & 0xffffu));
+          float dz = de;
+          if (SILU) {
+            const float sg = sigmoidf_(z);
+            dz = de * sg * (1.0f + z * (1.0f - sg));
+          }
+          o[j] = rstd[second] * (dz * gm[j] - p1[second] - xhat * p2[second]);
+        }
+      }
+      st_stream(ob + ru * s.vecs, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+    }
   }
 }
 
@@ -165,7 +192,7 @@ static int gn_shape(GnShape* s, int64_t B, int64_t HW, int C, int G, dim3* grid,
   // ~4 CTAs per SM over the batch; every CTA streams at least 8 rows per row slot
   int64_t want = (4LL * num_sms() + B - 1) / B;
   int64_t rows = (HW + want - 1) / want;
-  const int64_t min_rows = 8LL * s->rows_par;
+  const int64_t min_rows = 16LL * s->rows_par;
   if (rows < min_rows) rows = min_rows;
   s->rows_per_cta = (int)rows;
   *grid = dim3((unsigned)((HW + rows - 1) / rows), (unsigned)B);

@@ -33,27 +33,48 @@ class FlatAdamW:
             g["_range"] = (begin, end)
             self.param_groups.append(g)
 
+        # device copy of the per-group hyper-parameters (lr, beta1, beta2, eps, wd, bias_corr1, bias_corr2): lets a captured
+        # CUDA graph follow the step count / LR schedule without being re-captured
+        self._hyper_host = None
+        self._hyper_dev = None
+
+    def refresh_device_hyper(self, step: int) -> None:
+        """Write the hyper-parameters of optimizer step number `step` (1-based) to the device table (async copy)."""
+        n = len(self.param_groups)
+        if self._hyper_host is None:
+            self._hyper_host = torch.zeros(n, 8, dtype=torch.float32).pin_memory()
+            self._hyper_dev = torch.zeros(n, 8, dtype=torch.float32, device=self.arena.params.device)
+        for i, g in enumerate(self.param_groups):
+            b1, b2 = g["betas"]
+            self._hyper_host[i, :7] = torch.tensor([g["lr"], b1, b2, g["eps"], g["weight_decay"], 1.0 - b1 ** step, 1.0 - b2 ** step])
+        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.arena.zero_grad()
 
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0, ema_shadow: Optional[torch.Tensor] = None,
-             ema_one_minus_decay: float = 0.0) -> None:
+             ema_one_minus_decay: float = 0.0, use_device_hyper: bool = False,
+             ema_one_minus_decay_dev: Optional[torch.Tensor] = None) -> None:
+        """One AdamW step.  With ``use_device_hyper`` the kernels read the table written by ``refresh_device_hyper`` (the
+        caller advances ``step_count``) -- the form that can be captured in a CUDA graph."""
         lib = _lib.load()
-        self.step_count += 1
-        t = self.step_count
+        if not use_device_hyper:
+            self.step_count += 1
+        t = max(self.step_count, 1)
         a = self.arena
-        for g in self.param_groups:
+        for gi, g in enumerate(self.param_groups):
             begin, end = g["_range"]
             if end <= begin:
                 continue
             b1, b2 = g["betas"]
             hyper = (ctypes.c_float * 7)(g["lr"], b1, b2, g["eps"], g["weight_decay"], 1.0 - b1 ** t, 1.0 - b2 ** t)
             sh = 0 if ema_shadow is None else ema_shadow.data_ptr() + 4 * begin
+            hdev = self._hyper_dev.data_ptr() + 32 * gi if use_device_hyper else None
             _lib.check(lib.sdt_adamw_flat(a.params.data_ptr() + 4 * begin, a.grads.data_ptr() + 4 * begin,
                                           self.exp_avg.data_ptr() + 4 * begin, self.exp_avg_sq.data_ptr() + 4 * begin,
-                                          end - begin, hyper, None, grad_scale, sh, ema_one_minus_decay, None,
-                                          _lib.stream_ptr()), "sdt_adamw_flat")
+                                          end - begin, hyper, hdev, grad_scale, sh, ema_one_minus_decay,
+                                          _lib.ptr(ema_one_minus_decay_dev), _lib.stream_ptr()), "sdt_adamw_flat")
         # the masters changed in place: LoraArena.pack() (explicit, one launch) refreshes the bf16 operands
 
     def state_dict(self):

@@ -126,6 +126,70 @@ class LatentDiffusionTrainer:
         self.global_step += 1
         return loss
 
+    # ---- whole-step CUDA graph -------------------------------------------------------------------------------
+    def enable_cuda_graph(self, example_batch: dict, warmup: int = 3) -> None:
+        """Capture zero_grad -> forward -> loss -> backward -> all-reduce -> AdamW(+EMA) -> repack as ONE CUDA graph.
+
+        The step launches ~3,000 kernels; once the GPU work per step drops towards the host's launch rate the Python /
+        driver overhead shows.  Replays read the batch, the noise and the timesteps from static buffers (filled by a few
+        eager launches before each replay) and the optimizer's step-dependent scalars from a device table."""
+        dev = self.device
+        self._g_lat = example_batch["latents"].to(dev).clone()
+        self._g_cond = example_batch["conds"].to(dev).clone()
+        self._g_noise = torch.empty_like(self._g_lat)
+        self._g_t = torch.zeros(self._g_lat.shape[0], dtype=torch.int64, device=dev)
+        self._g_omd = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._g_omd_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        fused_ema = self.unet_ema is not None and self.unet_ema._shadow_flat is not None
+        if self.unet_ema is not None and not fused_ema:
+            raise NotImplementedError("CUDA-graph stepping needs the EMA shadow on the flat arena")
+
+        def body():
+            self.optimizer.zero_grad()
+            loss = self._denoise_loss(self._g_lat, self._g_cond, self._g_noise, self._g_t)
+            loss.backward()
+            self.exchange.all_reduce_mean_(self.arena.grads)
+            self.optimizer.step(use_device_hyper=True, ema_shadow=self.unet_ema._shadow_flat if fused_ema else None,
+                                ema_one_minus_decay_dev=self._g_omd if fused_ema else None)
+            if isinstance(self.arena, LoraArena):
+                self.arena.pack()
+            return loss.detach()
+
+        self._refresh_step_inputs()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_loss = body()
+        self.global_step += warmup + 1
+
+    def _refresh_step_inputs(self) -> None:
+        """Eager, tiny: new noise / timesteps (modules/model.py:294,297-298) and the step-dependent optimizer scalars."""
+        self._g_noise.normal_(generator=self.generator)
+        self._g_t.random_(0, self.scheduler.config.num_train_timesteps, generator=self.generator)
+        self.optimizer.step_count += 1
+        self.optimizer.refresh_device_hyper(self.optimizer.step_count)
+        if self.unet_ema is not None:
+            ema = self.unet_ema
+            if ema.num_updates is not None:
+                ema.num_updates += 1
+            self._g_omd_host[0] = ema.current_one_minus_decay()
+            self._g_omd.copy_(self._g_omd_host, non_blocking=True)
+
+    def graphed_step(self, batch: dict) -> torch.Tensor:
+        """Same contract as ``step`` (returns the device-resident loss), replaying the captured graph."""
+        self._g_lat.copy_(batch["latents"], non_blocking=True)
+        self._g_cond.copy_(batch["conds"], non_blocking=True)
+        self._refresh_step_inputs()
+        self._graph.replay()
+        self.global_step += 1
+        return self._g_loss
+
     # ---- modules/model.py:378-397 ----------------------------------------------------------------------
     def checkpoint_state_dict(self) -> dict[str, Any]:
         """Trainable-only state dict with the reference's keys (``unet.<path>.lora_A`` ..., plus ``unet_ema``)."""

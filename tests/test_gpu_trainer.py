@@ -57,3 +57,48 @@ def test_prior_preservation_step_and_checkpoint_keys(sdt_lib):
     assert all(k.startswith("unet.") and k.endswith(("lora_A", "lora_B")) for k in sd)
     assert len(sd) == 256 and "unet.mid_block.attentions.0.transformer_blocks.0.attn1.to_q.lora_A" in sd
     ours.criterion.raise_if_nan()
+
+
+def test_cuda_graph_step_matches_eager(sdt_lib):
+    """The captured step reproduces the eager loss and LoRA gradients on the same inputs (lr = 0 keeps the parameters
+    fixed, so the two can be compared directly), and a non-zero lr makes the loss go down over replays."""
+    import copy
+
+    import torch
+
+    from scal_sdt_b200 import NoiseScheduler
+    from scal_sdt_b200.targets import lora_unet_targets
+    from scal_sdt_b200.trainer import LatentDiffusionTrainer
+    from scal_sdt_b200.unet import UNet2DConditionModel, UNetConfig
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    base = UNet2DConditionModel(UNetConfig.tiny()).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+
+    def make(lr):
+        tr = LatentDiffusionTrainer(copy.deepcopy(base), NoiseScheduler(), lora_unet_targets(rank=8, alpha=8, lr=lr),
+                                    optimizer_params={"lr": lr, "beta1": 0.9, "beta2": 0.999, "weight_decay": 0.0, "eps": 1e-8},
+                                    ema={"enabled": True, "decay": 0.99}, seed=3)
+        g = torch.Generator(device=dev).manual_seed(1)
+        with torch.no_grad():
+            for _, m in tr.arena.sites:
+                m.lora_B.normal_(0, 0.05, generator=g)
+        tr.arena.pack()
+        return tr
+
+    g = torch.Generator().manual_seed(2)
+    batch = {"latents": torch.randn(2, 4, 16, 16, generator=g).to(dev), "conds": torch.randn(2, 7, 64, generator=g).to(dev)}
+    tr = make(0.0)
+    tr.enable_cuda_graph(batch)
+    loss_g = tr.graphed_step(batch).clone()
+    grads_g = tr.arena.grads.clone()
+    tr.optimizer.zero_grad()
+    loss_e = tr.training_step(batch, 0, tr._g_noise, tr._g_t)
+    loss_e.backward()
+    assert abs(loss_g.item() - loss_e.item()) <= 1e-3 * abs(loss_e.item())
+    assert (grads_g - tr.arena.grads).norm() <= 2e-2 * tr.arena.grads.norm()       # atomics: summation order differs
+    tr2 = make(2e-3)
+    tr2.enable_cuda_graph(batch)
+    first = tr2.graphed_step(batch).item()
+    for _ in range(20):
+        last = tr2.graphed_step(batch).item()
+    assert tr2.optimizer.step_count >= 21 and tr2.unet_ema.num_updates >= 21
