@@ -329,7 +329,9 @@ def ours_main(args):
         e1.record()
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = lib.sdt_launch_count() - launches0
+    launches = lib.sdt_launch_count() - launches0        # eager launches (noise/timestep refresh are torch ops: not counted)
+    if use_graph:
+        launches += args.steps * tr.graph_launches_per_step     # our kernels inside the captured step, replayed K times
     value = world * B * args.steps / (ms_total * 1e-3)
     final_loss = float(loss.item())
 

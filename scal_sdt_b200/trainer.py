@@ -163,9 +163,13 @@ class LatentDiffusionTrainer:
                 body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import _lib
+        before = _lib.load().sdt_launch_count()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._g_loss = body()
+        # kernels of libsdt_b200 recorded into the graph = launched on every replay
+        self.graph_launches_per_step = int(_lib.load().sdt_launch_count() - before)
         self.global_step += warmup + 1
 
     def _refresh_step_inputs(self) -> None:
