@@ -404,9 +404,16 @@ def ours_main(args):
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    exchange.close()
+    # teardown: the captured graph references the communicator, so it goes first
+    tr.release_cuda_graph()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        # every rank has its result out; communicator teardown after graph capture has been seen to block, and there is
+        # nothing left to flush but the process itself
+        sys.stderr.flush()
+        os._exit(0)
+    exchange.close()
     return 0
 
 

@@ -172,6 +172,13 @@ class LatentDiffusionTrainer:
         self.graph_launches_per_step = int(_lib.load().sdt_launch_count() - before)
         self.global_step += warmup + 1
 
+    def release_cuda_graph(self) -> None:
+        """Drop the captured graph (it pins the NCCL communicator and a private memory pool)."""
+        if getattr(self, "_graph", None) is not None:
+            torch.cuda.synchronize()
+            self._graph.reset()
+            self._graph = None
+
     def _refresh_step_inputs(self) -> None:
         """Eager, tiny: new noise / timesteps (modules/model.py:294,297-298) and the step-dependent optimizer scalars."""
         self._g_noise.normal_(generator=self.generator)
