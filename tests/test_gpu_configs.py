@@ -1,0 +1,164 @@
+"""GPU parity of the BASELINE.json configurations that are not the bench line, at reduced width (same code paths):
+cfg3 (rank 64 on attention + FF with EMA), cfg4 (aspect-ratio-bucketed mixed resolution + DreamBooth prior preservation),
+cfg5 (SD2.x-shaped UNet: linear proj_in/out, 'v' target, native full fine-tune + EMA)."""
+import copy
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.ref_trainer import RefTrainer
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _pair(cfg, targets, dtype, **kw):
+    from scal_sdt_b200 import NoiseScheduler
+    from scal_sdt_b200.trainer import LatentDiffusionTrainer
+    from scal_sdt_b200.unet import UNet2DConditionModel
+    torch.manual_seed(11)
+    unet_cpu = UNet2DConditionModel(cfg)
+    if dtype == torch.bfloat16:
+        with torch.no_grad():
+            for p in unet_cpu.parameters():
+                p.copy_(p.bfloat16().float())
+    unet_gpu = copy.deepcopy(unet_cpu).to(DEV).to(dtype)
+    if dtype == torch.bfloat16:
+        unet_gpu = unet_gpu.to(memory_format=torch.channels_last)
+    ptype = kw.pop("prediction_type", "epsilon")
+    ema_decay = kw.pop("ema_decay", None)
+    prior = kw.pop("prior", None)
+    opt = {"lr": 1e-3, "betas": (0.9, 0.999), "weight_decay": 1e-2, "eps": 1e-7}
+    ref = RefTrainer(unet_cpu, copy.deepcopy(targets), prediction_type=ptype, optimizer_params=opt, ema_decay=ema_decay,
+                     prior_preservation=prior is not None, prior_loss_weight=prior or 1.0)
+    ours = LatentDiffusionTrainer(unet_gpu, NoiseScheduler(prediction_type=ptype), copy.deepcopy(targets),
+                                  optimizer_params={"lr": 1e-3, "beta1": 0.9, "beta2": 0.999, "weight_decay": 1e-2, "eps": 1e-7},
+                                  ema={"enabled": ema_decay is not None, "decay": ema_decay or 0.0},
+                                  prior_preservation={"enabled": prior is not None, "prior_loss_weight": prior or 1.0}, seed=0)
+    return ref, ours
+
+
+def _sync_lora(ref, ours, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    refm = dict(ref.unet.named_modules())
+    with torch.no_grad():
+        for name, m in ours.arena.sites:
+            a = (torch.randn(m.lora_A.shape, generator=g) * 0.05).bfloat16().float()
+            b = (torch.randn(m.lora_B.shape, generator=g) * 0.05).bfloat16().float()
+            m.lora_A.copy_(a); m.lora_B.copy_(b)
+            refm[name].lora_A.copy_(a); refm[name].lora_B.copy_(b)
+    ours.arena.pack()
+    return refm
+
+
+def _grad_rel(ours, refm):
+    num = den = 0.0
+    for name, m in ours.arena.sites:
+        for pn in ("lora_A", "lora_B"):
+            go, gr = getattr(m, pn).grad.float().cpu(), getattr(refm[name], pn).grad
+            num += (go - gr).pow(2).sum().item()
+            den += gr.pow(2).sum().item()
+    return (num / den) ** 0.5
+
+
+def test_cfg3_rank64_attention_ff_with_ema(sdt_lib):
+    from scal_sdt_b200.targets import lora_unet_targets
+    from scal_sdt_b200.unet import UNetConfig
+    targets = lora_unet_targets(rank=64, alpha=64, projections=False)       # attention + FF: 160 sites
+    ref, ours = _pair(UNetConfig.tiny(), targets, torch.bfloat16, ema_decay=0.995)
+    assert len(ours.arena.sites) == 160 and all(m.r == 64 for _, m in ours.arena.sites)
+    refm = _sync_lora(ref, ours)
+    g = torch.Generator().manual_seed(1)
+    lat, cond = torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 7, 64, generator=g).bfloat16().float()
+    noise, t = torch.randn(2, 4, 16, 16, generator=g), torch.tensor([3, 977])
+    ours.optimizer.zero_grad()
+    lo = ours.training_step({"latents": lat.to(DEV), "conds": cond.to(DEV)}, 0, noise.to(DEV), t.to(DEV))
+    lo.backward()
+    lr_ = ref.training_step({"latents": lat, "conds": cond}, noise, t)
+    lr_.backward()
+    assert abs(lo.item() - lr_.item()) <= 2e-2 * abs(lr_.item())
+    assert _grad_rel(ours, refm) <= 5e-2
+    # optimizer + EMA step: bias-corrected first AdamW step moves every element by ~lr; compare against torch AdamW + RefEMA
+    for name, m in ours.arena.sites:           # feed the oracle's exact gradients so that only the update rule is compared
+        m.lora_A.grad.copy_(refm[name].lora_A.grad.to(DEV)); m.lora_B.grad.copy_(refm[name].lora_B.grad.to(DEV))
+    ours.optimizer_step()
+    ref.optimizer.step(); ref.ema.update()
+    for name, m in ours.arena.sites[:8]:
+        assert torch.allclose(m.lora_A.cpu(), refm[name].lora_A, rtol=1e-5, atol=1e-7)
+        assert torch.allclose(ours.unet_ema.shadow_params[name + ".lora_B"].cpu(), ref.ema.shadow_params[name + ".lora_B"],
+                              rtol=1e-5, atol=1e-7)
+    assert ours.unet_ema.num_updates == ref.ema.num_updates == 1
+
+
+def test_cfg4_bucketed_mixed_resolution_prior_preservation(sdt_lib):
+    from scal_sdt_b200.bucket import DEFAULT_BUCKET_CONFIG, AspectSamplerDB, collate_order
+    from scal_sdt_b200.targets import lora_unet_targets
+    from scal_sdt_b200.unet import UNetConfig
+    sizes = [(512, 512), (768, 512), (512, 768), (1024, 768), (768, 1024)]
+    rs = np.random.RandomState(0)
+    inst = {i: sizes[int(k)] for i, k in enumerate(rs.randint(0, len(sizes), size=64))}
+    cls = {i: sizes[int(k)] for i, k in enumerate(rs.randint(0, len(sizes), size=128))}
+    cfg = dict(DEFAULT_BUCKET_CONFIG, manual={"max_size": 786432})
+    random.seed(114514)
+    sampler = AspectSamplerDB(inst, cls, 512, cfg, 2, 114514, world_size=2, global_rank=1)
+    pairs = list(sampler)
+    batches = [pairs[i:i + 2] for i in range(0, len(pairs), 2)]
+    assert len({b[0][0].size for b in batches}) >= 2                       # several resolutions in one epoch
+    ref, ours = _pair(UNetConfig.tiny(), lora_unet_targets(rank=16, alpha=16), torch.bfloat16, prior=0.7)
+    refm = _sync_lora(ref, ours)
+    g = torch.Generator().manual_seed(2)
+    seen = set()
+    for batch in batches:
+        w, h = batch[0][0].size
+        if (w, h) in seen or len(seen) >= 3:
+            continue
+        seen.add((w, h))
+        order = collate_order(batch)                                       # instance items, then class items
+        assert all(ix.size == (w, h) for ix in order) and len(order) == 4
+        hh, ww = h // 64, w // 64                                          # toy latents: 1/8 of the real h/8 x w/8
+        lat = torch.randn(4, 4, hh, ww, generator=g)
+        cond = torch.randn(4, 7, 64, generator=g).bfloat16().float()
+        noise, t = torch.randn(4, 4, hh, ww, generator=g), torch.randint(0, 1000, (4,), generator=g)
+        ours.optimizer.zero_grad()
+        lo = ours.training_step({"latents": lat.to(DEV), "conds": cond.to(DEV)}, 0, noise.to(DEV), t.to(DEV))
+        lo.backward()
+        ref.optimizer.zero_grad(set_to_none=True)
+        lr_ = ref.training_step({"latents": lat, "conds": cond}, noise, t)
+        lr_.backward()
+        assert abs(lo.item() - lr_.item()) <= 2e-2 * abs(lr_.item()), (w, h)
+        assert _grad_rel(ours, refm) <= 5e-2, (w, h)
+    assert len(seen) >= 2
+
+
+def test_cfg5_sd2x_shape_full_finetune_v_prediction_ema(sdt_lib):
+    """Native fine-tune: gradients come from torch autograd; the path pieces exercised are K3 (v target), K4, the flat
+    AdamW and the EMA over the whole parameter arena (fp32, TF32 off: tight tolerances)."""
+    from scal_sdt_b200.targets import full_unet_targets
+    from scal_sdt_b200.unet import UNetConfig
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = UNetConfig(block_out_channels=(32, 64, 128, 128), cross_attention_dim=96, attention_head_dim=16, num_heads=None,
+                     use_linear_projection=True, norm_num_groups=8)
+    ref, ours = _pair(cfg, full_unet_targets(lr=1e-3, weight_decay=1e-2), torch.float32, prediction_type="v", ema_decay=0.99)
+    n_params = sum(p.numel() for p in ours.unet.parameters())
+    assert ours.arena.numel >= n_params and all(p.requires_grad for p in ours.unet.parameters())
+    g = torch.Generator().manual_seed(3)
+    lat, cond = torch.randn(2, 4, 12, 12, generator=g), torch.randn(2, 9, 96, generator=g)
+    noise, t = torch.randn(2, 4, 12, 12, generator=g), torch.tensor([10, 900])
+    for _ in range(2):
+        ours.optimizer.zero_grad()
+        lo = ours.training_step({"latents": lat.to(DEV), "conds": cond.to(DEV)}, 0, noise.to(DEV), t.to(DEV))
+        lo.backward()
+        ours.optimizer_step()
+        lr_ = ref.step({"latents": lat, "conds": cond}, noise, t)
+        assert abs(lo.item() - lr_.item()) <= 1e-4 * abs(lr_.item())
+    refp = dict(ref.unet.named_parameters())
+    worst = 0.0
+    for n, p in ours.unet.named_parameters():
+        worst = max(worst, ((p.detach().cpu() - refp[n]).norm() / (refp[n].norm() + 1e-12)).item())
+        s = ours.unet_ema.shadow_params[n].cpu()
+        assert (s - ref.ema.shadow_params[n]).norm() <= 1e-4 * (ref.ema.shadow_params[n].norm() + 1e-12), n
+    assert worst <= 1e-3, worst
+    assert set(ours.unet_ema.state_dict()["shadow_params"]) == set(refp)
