@@ -117,7 +117,7 @@ def test_cfg4_bucketed_mixed_resolution_prior_preservation(sdt_lib):
         seen.add((w, h))
         order = collate_order(batch)                                       # instance items, then class items
         assert all(ix.size == (w, h) for ix in order) and len(order) == 4
-        hh, ww = h // 64, w // 64                                          # toy latents: 1/8 of the real h/8 x w/8
+        hh, ww = h // 16, w // 16                                          # toy latents: half of the real h/8 x w/8
         lat = torch.randn(4, 4, hh, ww, generator=g)
         cond = torch.randn(4, 7, 64, generator=g).bfloat16().float()
         noise, t = torch.randn(4, 4, hh, ww, generator=g), torch.randint(0, 1000, (4,), generator=g)
