@@ -117,7 +117,7 @@ def test_cfg4_bucketed_mixed_resolution_prior_preservation(sdt_lib):
         seen.add((w, h))
         order = collate_order(batch)                                       # instance items, then class items
         assert all(ix.size == (w, h) for ix in order) and len(order) == 4
-        hh, ww = h // 16, w // 16                                          # toy latents: half of the real h/8 x w/8
+        hh, ww = h // 8, w // 8                                            # the real latent geometry of the bucket
         lat = torch.randn(4, 4, hh, ww, generator=g)
         cond = torch.randn(4, 7, 64, generator=g).bfloat16().float()
         noise, t = torch.randn(4, 4, hh, ww, generator=g), torch.randint(0, 1000, (4,), generator=g)
@@ -145,8 +145,8 @@ def test_cfg5_sd2x_shape_full_finetune_v_prediction_ema(sdt_lib):
     n_params = sum(p.numel() for p in ours.unet.parameters())
     assert ours.arena.numel >= n_params and all(p.requires_grad for p in ours.unet.parameters())
     g = torch.Generator().manual_seed(3)
-    lat, cond = torch.randn(2, 4, 12, 12, generator=g), torch.randn(2, 9, 96, generator=g)
-    noise, t = torch.randn(2, 4, 12, 12, generator=g), torch.tensor([10, 900])
+    lat, cond = torch.randn(2, 4, 16, 24, generator=g), torch.randn(2, 9, 96, generator=g)
+    noise, t = torch.randn(2, 4, 16, 24, generator=g), torch.tensor([10, 900])
     for _ in range(2):
         ours.optimizer.zero_grad()
         lo = ours.training_step({"latents": lat.to(DEV), "conds": cond.to(DEV)}, 0, noise.to(DEV), t.to(DEV))
