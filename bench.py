@@ -372,6 +372,20 @@ def ours_main(args):
         t_bwd = sum(a.elapsed_time(b) for kind, *_, a, b in rec if kind == "bwd") * 1e-3
         n_fwd = sum(1 for r in rec if r[0] == "fwd")
         ach = f_fwd / t_fwd / 1e12
+        # per-shape view of the same forward launches: which bound applies to which class of site
+        shapes = {}
+        for kind, M, K, N, R, a, b in (r for r in rec if r[0] == "fwd"):
+            e = shapes.setdefault((M, K, N, R), [0, 0.0])
+            e[0] += 1
+            e[1] += a.elapsed_time(b) * 1e-3
+        by_shape = []
+        for (M, K, N, R), (cnt, sec) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+            fl = 2.0 * M * K * N + 2.0 * M * R * (K + N)
+            by = 2.0 * (M * K + K * N + R * (K + N) + M * N + M * R)
+            tf, gbs = fl * cnt / sec / 1e12, by * cnt / sec / 1e9
+            by_shape.append({"M": M, "K": K, "N": N, "R": R, "launches": cnt, "avg_us": 1e6 * sec / cnt, "tflops": tf,
+                             "frac_tensor": tf / peaks["tf_sustained"], "algorithmic_gbs": gbs, "frac_hbm": gbs / peaks["hbm"],
+                             "bound": "tensor" if fl / by > peaks["tf_sustained"] * 1e3 / peaks["hbm"] else "hbm"})
         roof = {"kernel": "lora_gemm_kernel (K1: fused X W^T + bias + s (X A^T) B^T), all 192 forward launches of a step",
                 "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
@@ -379,7 +393,7 @@ def ours_main(args):
                 "flops_per_step": f_fwd / 2, "hot_path_gemm_seconds_per_step": (t_fwd + t_bwd) / 2,
                 "backward": {"kernels": "lora_gemm_kernel (dX,G) + 2x lora_wgrad_kernel (dA, dB)",
                              "achieved": f_bwd / t_bwd / 1e12, "frac": f_bwd / t_bwd / 1e12 / peaks["tf_sustained"]},
-                "elementwise": elementwise_roofline(device, peaks)}
+                "by_shape": by_shape, "elementwise": elementwise_roofline(device, peaks)}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----
     cpu = None

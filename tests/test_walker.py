@@ -77,3 +77,24 @@ def test_sd15_sites_have_survey_shapes():
     assert sum(shapes.values()) == 192
     r = 16
     assert sum(n * r * (k[0] + k[1]) for k, n in shapes.items()) == 6_782_976      # SURVEY 8(e) LoRA param count
+
+
+def test_kohya_export_key_layout():
+    """``ckpt_tool.py:185-222``: lora_A -> lora_down.weight, lora_B -> lora_up.weight, alpha int32 from the run config."""
+    from scal_sdt_b200.export import to_kohya_state_dict
+    gold = json.loads((GOLDEN / "walker.json").read_text())["lora"]
+    unet = UNet2DConditionModel(UNetConfig.tiny())
+    config_module(unet, gold["config"]["unet"]["targets"])
+    state = {f"unet.{n}": p.detach() for n, p in unet.named_parameters() if p.requires_grad}
+    state["condition_model.encoder.text_model.encoder.layers.0.self_attn.q_proj.lora_A"] = torch.zeros(16, 8)
+    state["condition_model.encoder.text_model.encoder.layers.0.self_attn.q_proj.lora_B"] = torch.zeros(8, 16)
+    state["unet_ema"] = {"decay": 0.9}
+    out = to_kohya_state_dict(state, optim_target=gold["config"])
+    k = "lora_unet_down_blocks_0_attentions_0_transformer_blocks_0_attn1_to_q"
+    assert out[k + ".lora_down.weight"].shape == (16, 32) and out[k + ".lora_up.weight"].shape == (32, 16)
+    assert out[k + ".lora_down.weight"].dtype == torch.float16
+    assert out[k + ".alpha"].dtype == torch.int32 and int(out[k + ".alpha"]) == 1
+    assert "lora_te_text_model_encoder_layers_0_self_attn_q_proj.lora_up.weight" in out
+    assert len(out) == 3 * 192 + 3
+    proj = "lora_unet_mid_block_attentions_0_proj_in.lora_down.weight"
+    assert out[proj].dim() == 2                     # 1x1-conv LoRA factors are emitted 2-D
