@@ -230,6 +230,8 @@ class _LoRABase(nn.Module):
             x2 = x2.to(torch.get_autocast_dtype("cuda"))
         if x2.dtype == torch.float16:
             raise SdtError("fp16 is not implemented: use bf16 (trainer.precision=bf16) or fp32")
+        if x2.shape[0] == 0:                 # empty batch: nothing to launch (F.linear returns an empty tensor too)
+            return x2.new_zeros(0, self.out_features) + 0.0 * (self.lora_A.sum() + self.lora_B.sum()).to(x2.dtype)
         return _LoRAProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self)
 
     def extra_repr(self) -> str:

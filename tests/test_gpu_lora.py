@@ -128,3 +128,54 @@ def test_arena_direct_gradients_and_pack(sdt_lib):
         arena.pack()
         losses.append(loss.item())
     assert losses[2] < losses[0]
+
+
+RAGGED = [(1, 64, 64), (7, 320, 320), (129, 72, 40), (255, 320, 640), (257, 640, 320), (616, 768, 1280), (1000, 8, 8),
+          (300, 1280, 24)]
+
+
+@pytest.mark.parametrize("M,K,N", RAGGED, ids=[f"{m}x{k}x{n}" for m, k, n in RAGGED])
+@pytest.mark.parametrize("rank", [4, 16])
+def test_ragged_shapes_bf16(sdt_lib, M, K, N, rank):
+    """Token counts / widths that do not fill the 128 x 160 x 64 tiles (TMA zero-fill on loads, clipping on stores)."""
+    ref, ours = make_pair("linear", K, N, rank, 2 * rank, True, 3, torch.bfloat16)
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g).bfloat16().float()
+    dy = torch.randn(M, N, generator=g).bfloat16().float()
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(dy.double())
+    xo = x.to(DEV).bfloat16().requires_grad_(True)
+    yo = ours(xo)
+    yo.backward(dy.to(DEV).bfloat16())
+    for name, a, b in (("y", yo, yr), ("dx", xo.grad, xr.grad), ("dA", ours.lora_A.grad, ref.lora_A.grad),
+                       ("dB", ours.lora_B.grad, ref.lora_B.grad)):
+        assert rel(a, b) <= 2e-2, (name, rel(a, b))
+
+
+def test_empty_batch(sdt_lib):
+    from scal_sdt_b200 import get_lora
+    m = get_lora(nn.Linear(64, 32).to(DEV), rank=4)
+    y = m(torch.zeros(0, 64, device=DEV, dtype=torch.bfloat16))
+    assert y.shape == (0, 32)
+    y.sum().backward()
+    assert m.lora_A.grad is not None and float(m.lora_A.grad.abs().sum()) == 0.0
+
+
+def test_largest_bucket_token_count_linearity(sdt_lib):
+    """cfg4's largest bucket at batch 8: M = 8 * 128 * 96 = 98,304 tokens.  Size-independent checks: the projection is
+    linear in x (f(x1 + x2) - f(0) = (f(x1) - f(0)) + (f(x2) - f(0))) and a random row sample matches the oracle."""
+    torch.manual_seed(0)
+    M, K, N, r = 98304, 320, 320, 16
+    ref, ours = make_pair("linear", K, N, r, 16, True, 9, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x1 = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
+    x2 = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
+    with torch.no_grad():
+        f0 = ours(torch.zeros(1, K, device=DEV, dtype=torch.bfloat16)).float()
+        y1, y2, y12 = ours(x1).float(), ours(x2).float(), ours((x1.float() + x2.float()).bfloat16()).float()
+    lin = (y12 - f0) - ((y1 - f0) + (y2 - f0))
+    assert lin.norm() <= 2e-2 * y12.norm()
+    rows = torch.randint(0, M, (257,), generator=torch.Generator().manual_seed(2))
+    yr = ref(x1[rows.to(DEV)].cpu().double())
+    assert rel(y1[rows.to(DEV)], yr) <= 2e-2
