@@ -386,9 +386,22 @@ def ours_main(args):
             by_shape.append({"M": M, "K": K, "N": N, "R": R, "launches": cnt, "avg_us": 1e6 * sec / cnt, "tflops": tf,
                              "frac_tensor": tf / peaks["tf_sustained"], "algorithmic_gbs": gbs, "frac_hbm": gbs / peaks["hbm"],
                              "bound": "tensor" if fl / by > peaks["tf_sustained"] * 1e3 / peaks["hbm"] else "hbm"})
-        roof = {"kernel": "lora_gemm_kernel (K1: fused X W^T + bias + s (X A^T) B^T), all 192 forward launches of a step",
+        # DRAM bytes per GEMM launch from the committed ncu pass over one training step (dram__bytes_read + write summed over
+        # the lora_gemm* launches / their count); bench.py cannot run ncu itself
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_v5_lora_kernels_per_step_ncu.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            gl = [v for k, v in tj.items() if "lora_gemm" in k]
+            if gl:
+                traffic = sum((v["dram_read_MB"] + v["dram_write_MB"]) * 1e6 for v in gl) / sum(v["launches"] for v in gl)
+                traffic_src = "profiles/r01_v5_lora_kernels_per_step_ncu.json (avg over the forward + dX GEMM launches of a step)"
+        alg_bytes = sum(2.0 * (M * K + K * N + R * (K + N) + M * N + M * R) for kind, M, K, N, R, *_ in rec if kind == "fwd") / max(n_fwd, 1)
+        roof = {"kernel": "lora_gemm_kernel / lora_gemm_pair_kernel (K1: fused X W^T + bias + s (X A^T) B^T), all 192 forward launches of a step",
                 "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "frac": ach / peaks["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peaks["source"] + ", sustained bf16",
                 "launches_timed": n_fwd, "avg_launch_us": 1e6 * t_fwd / max(n_fwd, 1),
                 "flops_per_step": f_fwd / 2, "hot_path_gemm_seconds_per_step": (t_fwd + t_bwd) / 2,
                 "backward": {"kernels": "lora_gemm_kernel (dX,G) + 2x lora_wgrad_kernel (dA, dB)",

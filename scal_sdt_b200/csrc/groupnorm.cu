@@ -36,6 +36,9 @@ gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dou
   const int c0 = v * 8;
   const int g0 = c0 / s.cpg, g1 = (c0 + 7) / s.cpg;
   float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
+  // elements j >= js of this thread's 8-channel vector belong to the next group (cpg >= 8: at most two groups per vector);
+  // computed once -- an integer division per element in the streaming loop would dominate the kernel
+  const int js = min(8, (g0 + 1) * s.cpg - c0);
   if (active) {
     float gm[8], bt[8], mean[2] = {0.f, 0.f}, rstd[2] = {0.f, 0.f};
     if (BWD) {
@@ -76,7 +79,7 @@ gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dou
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xe = bf16_bits_to_f32((j & 1) ? (xw[j >> 1] >> 16) : (xw[j >> 1] & 0xffffu));
-          const bool second = (c0 + j) / s.cpg != g0;
+          const bool second = j >= js;
           float p, pq;
           if (!BWD) {
             p = xe;
@@ -132,6 +135,17 @@ gn_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dou
       p2[k] = bstats[((size_t)b * s.G + g) * 2 + 1] * inv_n;
     }
   }
+  // per-element affine of the normalisation, hoisted out of the streaming loop: xhat = x * sc[j] + sh[j]
+  const int js = min(8, (g0 + 1) * s.cpg - c0);
+  float sc[8], sh[8], q1[8], q2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = j >= js ? 1 : 0;
+    sc[j] = rstd[k];
+    sh[j] = -mean[k] * rstd[k];
+    q1[j] = p1[k];
+    q2[j] = p2[k];
+  }
   const int64_t r_begin = (int64_t)blockIdx.x * s.rows_per_cta;
   const int64_t r_end = min(r_begin + (int64_t)s.rows_per_cta, s.HW);
   const uint4* xb = reinterpret_cast<const uint4*>(x) + ((size_t)b * s.HW) * s.vecs + v;
@@ -160,9 +174,8 @@ gn_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dou
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xe = bf16_bits_to_f32((j & 1) ? (xw[j >> 1] >> 16) : (xw[j >> 1] & 0xffffu));
-        const bool second = (c0 + j) / s.cpg != g0;
-        const float xhat = (xe - mean[second]) * rstd[second];
-        const float z = xhat * gm[j] + bt[j];
+        const float xhat = fmaf(xe, sc[j], sh[j]);
+        const float z = fmaf(xhat, gm[j], bt[j]);
         if (!BWD) {
           o[j] = SILU ? z * sigmoidf_(z) : z;
         } else {
@@ -172,7 +185,7 @@ gn_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dou
             const float sg = sigmoidf_(z);
             dz = de * sg * (1.0f + z * (1.0f - sg));
           }
-          o[j] = rstd[second] * (dz * gm[j] - p1[second] - xhat * p2[second]);
+          o[j] = sc[j] * (dz * gm[j] - q1[j] - xhat * q2[j]);
         }
       }
       st_stream(ob + ru * s.vecs, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
@@ -189,8 +202,8 @@ static int gn_shape(GnShape* s, int64_t B, int64_t HW, int C, int G, dim3* grid,
   s->rows_par = kGnThreads / s->vecs;
   if (s->rows_par > HW) s->rows_par = (int)HW;
   *threads = ((s->vecs * s->rows_par + 31) / 32) * 32;
-  // ~4 CTAs per SM over the batch; every CTA streams at least 8 rows per row slot
-  int64_t want = (4LL * num_sms() + B - 1) / B;
+  // ~2 CTAs per SM over the batch (per-thread set-up amortised over more rows); at least 16 rows per row slot
+  int64_t want = (2LL * num_sms() + B - 1) / B;
   int64_t rows = (HW + want - 1) / want;
   const int64_t min_rows = 16LL * s->rows_par;
   if (rows < min_rows) rows = min_rows;

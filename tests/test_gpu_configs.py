@@ -147,18 +147,27 @@ def test_cfg5_sd2x_shape_full_finetune_v_prediction_ema(sdt_lib):
     g = torch.Generator().manual_seed(3)
     lat, cond = torch.randn(2, 4, 16, 24, generator=g), torch.randn(2, 9, 96, generator=g)
     noise, t = torch.randn(2, 4, 16, 24, generator=g), torch.tensor([10, 900])
-    for _ in range(2):
+    refp = dict(ref.unet.named_parameters())
+    for step in range(2):
         ours.optimizer.zero_grad()
         lo = ours.training_step({"latents": lat.to(DEV), "conds": cond.to(DEV)}, 0, noise.to(DEV), t.to(DEV))
         lo.backward()
-        ours.optimizer_step()
-        lr_ = ref.step({"latents": lat, "conds": cond}, noise, t)
+        ref.optimizer.zero_grad(set_to_none=True)
+        lr_ = ref.training_step({"latents": lat, "conds": cond}, noise, t)
+        lr_.backward()
         assert abs(lo.item() - lr_.item()) <= 1e-4 * abs(lr_.item())
-    refp = dict(ref.unet.named_parameters())
-    worst = 0.0
-    for n, p in ours.unet.named_parameters():
-        worst = max(worst, ((p.detach().cpu() - refp[n]).norm() / (refp[n].norm() + 1e-12)).item())
-        s = ours.unet_ema.shadow_params[n].cpu()
-        assert (s - ref.ema.shadow_params[n]).norm() <= 1e-4 * (ref.ema.shadow_params[n].norm() + 1e-12), n
-    assert worst <= 1e-3, worst
+        num = sum((p.grad.cpu() - refp[n].grad).pow(2).sum().item() for n, p in ours.unet.named_parameters())
+        den = sum(refp[n].grad.pow(2).sum().item() for n, _ in ours.unet.named_parameters())
+        assert (num / den) ** 0.5 <= 1e-3
+        # Adam's first steps move every element by ~lr * sign(g): feed both optimizers the oracle's exact gradients so that
+        # the update rule (AdamW + EMA over the arena) is what is compared, not the sign of noise-level gradients
+        for n, p in ours.unet.named_parameters():
+            p.grad.copy_(refp[n].grad.to(DEV))
+        ours.optimizer_step()
+        ref.optimizer.step()
+        ref.ema.update()
+        for n, p in ours.unet.named_parameters():
+            assert torch.allclose(p.detach().cpu(), refp[n], rtol=2e-5, atol=2e-7), (step, n)
+            assert torch.allclose(ours.unet_ema.shadow_params[n].cpu(), ref.ema.shadow_params[n], rtol=2e-5, atol=2e-7), (step, n)
+    assert ours.unet_ema.num_updates == 2
     assert set(ours.unet_ema.state_dict()["shadow_params"]) == set(refp)
