@@ -357,27 +357,54 @@ def ours_main(args):
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
-    # ---- roofline of the dominant kernel: fused LoRA forward GEMM, timed per launch inside a real step ----
+    # ---- roofline of the dominant kernel: the fused LoRA GEMM launches of a real training step ----
+    # Pass 1 (eager, every rank: the all-reduce is collective): the ordered list of sites (kind, M, K, N, R) plus CUDA-event
+    # brackets.  Once the step is faster than the host can launch it, event brackets also contain the host's launch gap,
+    # so pass 2 takes the per-kernel durations of one replayed step from CUPTI (torch.profiler) and maps them onto the
+    # site list by launch order (forward sites first, then backward in reverse order; the order is deterministic).
     from scal_sdt_b200 import lora as lora_mod
     roof = None
     lora_mod.PROFILE = [] if rank == 0 else None
-    for i in range(2):                      # every rank steps (the gradient all-reduce is collective); rank 0 records
-        tr.step(dev[i % len(dev)])
+    tr.step(dev[0])
     torch.cuda.synchronize()
     rec = lora_mod.PROFILE
     lora_mod.PROFILE = None
+    kernel_times = None
+    if rank == 0 or world > 1:
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                do_step(dev[1 % len(dev)])
+                torch.cuda.synchronize()
+            ks = []
+            for e in prof.events():
+                if "lora_gemm" in e.name and str(getattr(e, "device_type", "")).endswith("CUDA"):
+                    ks.append((e.time_range.start, e.time_range.end - e.time_range.start))
+            ks.sort()
+            kernel_times = [d * 1e-6 for _, d in ks]      # seconds
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] CUPTI pass unavailable ({exc}); falling back to CUDA-event brackets", file=sys.stderr)
     if rank == 0:
+        fwd_sites = [r for r in rec if r[0] == "fwd"]
+        bwd_sites = [r for r in rec if r[0] == "bwd"]
+        n_fwd = len(fwd_sites)
+        timing = "cuda_events"
+        fwd_t = [a.elapsed_time(b) * 1e-3 for *_, a, b in fwd_sites]
+        bwd_gemm_t = None
+        t_bwd = sum(a.elapsed_time(b) for *_, a, b in bwd_sites) * 1e-3
+        if kernel_times is not None and len(kernel_times) == n_fwd + len(bwd_sites):
+            timing = "cupti_kernel_durations"
+            fwd_t = kernel_times[:n_fwd]
+            bwd_gemm_t = kernel_times[n_fwd:]
         f_fwd, f_bwd = site_flops(rec)
-        t_fwd = sum(a.elapsed_time(b) for kind, *_, a, b in rec if kind == "fwd") * 1e-3
-        t_bwd = sum(a.elapsed_time(b) for kind, *_, a, b in rec if kind == "bwd") * 1e-3
-        n_fwd = sum(1 for r in rec if r[0] == "fwd")
+        t_fwd = sum(fwd_t)
         ach = f_fwd / t_fwd / 1e12
         # per-shape view of the same forward launches: which bound applies to which class of site
         shapes = {}
-        for kind, M, K, N, R, a, b in (r for r in rec if r[0] == "fwd"):
+        for (kind, M, K, N, R, *_), sec in zip(fwd_sites, fwd_t):
             e = shapes.setdefault((M, K, N, R), [0, 0.0])
             e[0] += 1
-            e[1] += a.elapsed_time(b) * 1e-3
+            e[1] += sec
         by_shape = []
         for (M, K, N, R), (cnt, sec) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
             fl = 2.0 * M * K * N + 2.0 * M * R * (K + N)
@@ -397,16 +424,22 @@ def ours_main(args):
             if gl:
                 traffic = sum((v["dram_read_MB"] + v["dram_write_MB"]) * 1e6 for v in gl) / sum(v["launches"] for v in gl)
                 traffic_src = "profiles/r01_v5_lora_kernels_per_step_ncu.json (avg over the forward + dX GEMM launches of a step)"
-        alg_bytes = sum(2.0 * (M * K + K * N + R * (K + N) + M * N + M * R) for kind, M, K, N, R, *_ in rec if kind == "fwd") / max(n_fwd, 1)
+        alg_bytes = sum(2.0 * (M * K + K * N + R * (K + N) + M * N + M * R) for kind, M, K, N, R, *_ in fwd_sites) / max(n_fwd, 1)
+        dx_flops = sum(2.0 * M * K * N + 2.0 * M * R * (K + N) for kind, M, K, N, R, dx, *_ in bwd_sites if dx) + \
+            sum(2.0 * M * R * N for kind, M, K, N, R, dx, *_ in bwd_sites if not dx)
+        backward = {"kernels": "lora_gemm* (dX, G) + lora_wgrad_kernel (dA and dB in one launch)", "timing": "cuda_events",
+                    "achieved": f_bwd / t_bwd / 1e12, "frac": f_bwd / t_bwd / 1e12 / peaks["tf_sustained"]}
+        if bwd_gemm_t is not None:
+            backward["dx_gemm"] = {"timing": timing, "achieved": dx_flops / sum(bwd_gemm_t) / 1e12,
+                                   "frac": dx_flops / sum(bwd_gemm_t) / 1e12 / peaks["tf_sustained"],
+                                   "seconds_per_step": sum(bwd_gemm_t)}
         roof = {"kernel": "lora_gemm_kernel / lora_gemm_pair_kernel (K1: fused X W^T + bias + s (X A^T) B^T), all 192 forward launches of a step",
                 "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "frac": ach / peaks["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src, "timing": timing,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peaks["source"] + ", sustained bf16",
                 "launches_timed": n_fwd, "avg_launch_us": 1e6 * t_fwd / max(n_fwd, 1),
-                "flops_per_step": f_fwd / 2, "hot_path_gemm_seconds_per_step": (t_fwd + t_bwd) / 2,
-                "backward": {"kernels": "lora_gemm_kernel (dX,G) + 2x lora_wgrad_kernel (dA, dB)",
-                             "achieved": f_bwd / t_bwd / 1e12, "frac": f_bwd / t_bwd / 1e12 / peaks["tf_sustained"]},
-                "by_shape": by_shape, "elementwise": elementwise_roofline(device, peaks)}
+                "flops_per_step": f_fwd, "forward_gemm_seconds_per_step": t_fwd,
+                "backward": backward, "by_shape": by_shape, "elementwise": elementwise_roofline(device, peaks)}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----
     cpu = None
