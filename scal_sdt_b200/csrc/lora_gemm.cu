@@ -42,11 +42,12 @@ uint64_t debug_get(int key);
 template <int BN_, int R_>
 struct LoraGemmCfg {
   static constexpr int BM = 128, BN = BN_, BK = 64, R = R_;
-  static constexpr int kStages = (R_ >= 64) ? 3 : 4;
   static constexpr int X_BYTES = BM * BK * 2;              // 16 KiB
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int LA_BYTES = R * BK * 2;              // lora-down k-block [R,64]
   static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + LA_BYTES;
+  static constexpr int WS_STAGE_BYTES = X_BYTES + LA_BYTES;   // weight-stationary mode: the ring only carries X (+ lora-down)
+  static constexpr int kMaxStages = 8;                        // mbarrier slots (weight-stationary mode can use more stages)
   static constexpr int LB_BYTES = ((BN * R * 2 + 1023) / 1024) * 1024;   // lora-up tile [BN,R]
   static constexpr int KEXT = R + 16;                      // rank-R intermediate + the "ones" k-step (bias)
   static constexpr int T_SBO = (KEXT / 8) * 128;           // bytes between 8-row groups of the A operand
@@ -54,14 +55,16 @@ struct LoraGemmCfg {
   static constexpr int BIAS_BYTES = ((BN * 32 + 1023) / 1024) * 1024;    // [BN,16] bf16, un-swizzled cores
   static constexpr int STG_BYTES = 8 * 2 * 2048;           // 8 epilogue warps x 2 buffers x [32 rows x 64 B]
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES =
-      1024 /*align slack*/ + kStages * STAGE_BYTES + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
+  static constexpr int FIXED_BYTES = 1024 /*align slack*/ + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
+  static constexpr int RING_BYTES = ((232448 - FIXED_BYTES) / 1024) * 1024;   // everything else feeds the TMA ring
+  static constexpr int kStages = RING_BYTES / STAGE_BYTES > 6 ? 6 : RING_BYTES / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = FIXED_BYTES + RING_BYTES;
   static constexpr int TMEM_COLS = 512;
   static constexpr int ACC1_COL = BN, T_COL = 2 * BN;      // rank accumulators at T_COL and T_COL + R
   static_assert(2 * BN + 2 * R <= 512, "TMEM budget");
   static_assert(BN % 32 == 0 && BN <= 256, "BN");
   static_assert(R == 0 || R == 16 || R == 32 || R == 64, "rank must be padded to 16/32/64");
-  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(SMEM_BYTES <= 232448 && kStages >= 3, "shared memory budget");
 };
 
 constexpr int kGemmThreads = 14 * 32;
@@ -73,6 +76,8 @@ struct LoraGemmParams {
   int M, N, K;
   int n_tiles, n_groups, group_size, n_items;
   int main;               // 0: only the rank-R projection is computed (t_out), no base GEMM
+  int ws;                 // weight-stationary: every CTA keeps the W k-blocks of ITS n-tile resident (K <= 320), see launch
+  int ws_stages;
   long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
 };
 
@@ -84,33 +89,40 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   using C = LoraGemmCfg<BN, R>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* lb_smem = smem + C::kStages * C::STAGE_BYTES;
+  uint8_t* lb_smem = smem + C::RING_BYTES;
   uint8_t* stg_smem = lb_smem + C::LB_BYTES;
   uint8_t* t_smem = stg_smem + C::STG_BYTES;
   uint8_t* bias_smem = t_smem + C::T_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + C::BIAS_BYTES);
-  uint64_t* full = bars;                       // [kStages]
-  uint64_t* empty = bars + C::kStages;         // [kStages]
-  uint64_t* acc_full = bars + 2 * C::kStages;  // [2]
+  uint64_t* full = bars;                       // [kMaxStages]
+  uint64_t* empty = bars + C::kMaxStages;      // [kMaxStages]
+  uint64_t* acc_full = bars + 2 * C::kMaxStages;  // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint64_t* t_full = acc_empty + 2;            // rank accumulator complete (MMA -> side warps)
   uint64_t* t_ready = t_full + 1;              // A operand (+ bias operand) of the tail is in smem (side warps -> MMA)
   uint64_t* lb_full = t_ready + 1;             // lora-up tile landed (TMA -> MMA)
   uint64_t* lb_empty = lb_full + 1;            // tail MMAs of a tile completed (MMA -> producer, side warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lb_empty + 1);
+  uint64_t* w_full = lb_empty + 1;             // weight-stationary: resident W k-blocks landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (p.K + C::BK - 1) / C::BK;
   const bool has_main = p.main != 0;
   const bool has_bias = has_main && p.bias != nullptr;
   const bool has_tail = has_main && (R > 0 || has_bias);   // UMMAs issued after the K loop of a tile
+  // weight-stationary layout: [nk resident W k-blocks | ring of (X, lora-down) stages]; otherwise ring of (X, W, lora-down)
+  const bool ws = p.ws != 0;
+  const int n_stages = ws ? p.ws_stages : C::kStages;
+  const int stage_bytes = ws ? C::WS_STAGE_BYTES : C::STAGE_BYTES;
+  uint8_t* ring = ws ? smem + nk * C::W_BYTES : smem;
 
   if (threadIdx.x == 0) SDT_TRACE(0);
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_x);
     if (has_main) { prefetch_tmap(&tm_w); prefetch_tmap(&tm_y); }
     if (R > 0) { prefetch_tmap(&tm_la); if (has_main) prefetch_tmap(&tm_lb); }
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < C::kMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(w_full, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     mbar_init(t_full, 1);
     mbar_init(t_ready, 4);
@@ -152,18 +164,27 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
           const int n0 = nt * C::BN;
-          const uint32_t tx = C::X_BYTES + (has_main ? C::W_BYTES : 0) + (first ? C::LA_BYTES : 0);
+          if (ws && tile_ctr == 0) {
+            // this CTA's n-tile never changes (grid is a multiple of n_tiles): W and the lora-up tile are loaded once
+            mbar_arrive_expect_tx(w_full, (uint32_t)nk * C::W_BYTES);
+            for (int kb = 0; kb < nk; ++kb) tma_load_2d(smem + kb * C::W_BYTES, &tm_w, kb * C::BK, n0, w_full);
+            if (R > 0) {
+              mbar_arrive_expect_tx(lb_full, BN * R * 2);
+              tma_load_2d(lb_smem, &tm_lb, 0, n0, lb_full);
+            }
+          }
+          const uint32_t tx = C::X_BYTES + (has_main && !ws ? C::W_BYTES : 0) + (first ? C::LA_BYTES : 0);
           for (int kb = 0; kb < nk; ++kb, ++it) {
-            const int s = it % C::kStages;
-            mbar_wait(&empty[s], ((it / C::kStages) & 1) ^ 1);
-            uint8_t* st = smem + s * C::STAGE_BYTES;
+            const int s = it % n_stages;
+            mbar_wait(&empty[s], ((it / n_stages) & 1) ^ 1);
+            uint8_t* st = ring + s * stage_bytes;
             mbar_arrive_expect_tx(&full[s], tx);
             if (it == 0) SDT_TRACE(2);
             tma_load_2d(st, &tm_x, kb * C::BK, m0, &full[s]);
-            if (has_main) tma_load_2d(st + C::X_BYTES, &tm_w, kb * C::BK, n0, &full[s]);
-            if (first) tma_load_2d(st + C::X_BYTES + C::W_BYTES, &tm_la, kb * C::BK, 0, &full[s]);
+            if (has_main && !ws) tma_load_2d(st + C::X_BYTES, &tm_w, kb * C::BK, n0, &full[s]);
+            if (first) tma_load_2d(st + C::X_BYTES + (ws ? 0 : C::W_BYTES), &tm_la, kb * C::BK, 0, &full[s]);
           }
-          if (R > 0 && has_main) {
+          if (R > 0 && has_main && !ws) {
             mbar_wait(lb_empty, (tile_ctr & 1) ^ 1);
             mbar_arrive_expect_tx(lb_full, BN * R * 2);
             tma_load_2d(lb_smem, &tm_lb, 0, n0, lb_full);
@@ -191,13 +212,13 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
     auto tail_ready = [&]() -> bool {
       // all 32 lanes probe the same barriers, so the result is warp-uniform
-      if (R > 0 && !mbar_test(lb_full, pend_tile & 1)) return false;
+      if (R > 0 && !mbar_test(lb_full, ws ? 0u : (pend_tile & 1))) return false;   // ws: loaded once -> phase 0 stays complete
       if (pend_needs_ready && !mbar_test(t_ready, pend_ready & 1)) return false;
       return true;
     };
     auto issue_tail = [&]() {
       // tail of tile pend_tile: acc += Ts B^T (R/16 k-steps) + ones x bias (1 k-step); then hand the accumulator over
-      if (R > 0) mbar_wait(lb_full, pend_tile & 1);
+      if (R > 0) mbar_wait(lb_full, ws ? 0u : (pend_tile & 1));
       if (pend_needs_ready) mbar_wait(t_ready, pend_ready & 1);
       tc_fence_after();
       if (elect_one()) {
@@ -233,15 +254,16 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           tc_fence_after();
         }
         if (lane == 0 && tile_ctr < 6) SDT_TRACE(8 + 4 * tile_ctr);
+        if (ws && tile_ctr == 0) mbar_wait(w_full, 0);
         for (int kb = 0; kb < nk; ++kb, ++it) {
-          const int s = it % C::kStages;
-          mbar_wait(&full[s], (it / C::kStages) & 1);
+          const int s = it % n_stages;
+          mbar_wait(&full[s], (it / n_stages) & 1);
           if (lane == 0 && tile_ctr < 6 && kb == 0) SDT_TRACE(9 + 4 * tile_ctr);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
-            const uint32_t wa = xa + C::X_BYTES;
-            const uint32_t la = wa + C::W_BYTES;
+            const uint32_t xa = smem_u32(ring + s * stage_bytes);
+            const uint32_t wa = ws ? smem_u32(smem + kb * C::W_BYTES) : xa + C::X_BYTES;
+            const uint32_t la = ws ? xa + C::X_BYTES : wa + C::W_BYTES;
 #pragma unroll
             for (int k = 0; k < C::BK / 16; ++k) {
               const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
@@ -294,7 +316,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
-          if (has_bias) {
+          if (has_bias && !(ws && tile_ctr > 0)) {       // ws: the n-tile (hence the bias operand) never changes
             // the previous tile's tail must have finished reading the bias operand
             if (tile_ctr > 0) mbar_wait(lb_empty, (tile_ctr - 1) & 1);
             const int n0 = nt * C::BN;
@@ -565,7 +587,25 @@ static int launch_lora_gemm(const void* x, const void* w, const float* bias, con
   const int sms = num_sms();
   choose_groups(m_tiles, p.n_tiles, BN, R, sms, &p.group_size, &p.n_groups);
   p.n_items = m_tiles * p.n_groups;
-  const int grid = p.n_items < sms ? p.n_items : sms;
+  int grid = p.n_items < sms ? p.n_items : sms;
+  // Weight-stationary schedule for short K loops (K <= 320: the whole [BN, K] slab of W fits beside the ring): CTA c keeps
+  // the W k-blocks, lora-up tile and bias of n-tile (c mod n_tiles) resident and streams only X.  The kernel is bound by
+  // the bytes an SM ingests per k-block; without W that is 16 KiB instead of 36 KiB.  Needs every CTA to see >= 2 row tiles.
+  const int nk = (int)((K + C::BK - 1) / C::BK);
+  const int ws_stages_fit = (C::RING_BYTES - nk * C::W_BYTES) / C::WS_STAGE_BYTES;
+  p.ws = 0;
+  p.ws_stages = 0;
+  if (main && nk * C::W_BYTES < C::RING_BYTES && ws_stages_fit >= 3 && p.n_tiles <= sms && debug_get(13) == 0) {
+    const int g = (sms / p.n_tiles) * p.n_tiles;
+    if ((long)m_tiles * p.n_tiles >= 2L * g) {
+      p.ws = 1;
+      p.ws_stages = ws_stages_fit > C::kMaxStages ? C::kMaxStages : ws_stages_fit;
+      p.group_size = 1;
+      p.n_groups = p.n_tiles;
+      p.n_items = m_tiles * p.n_tiles;
+      grid = g;
+    }
+  }
   lora_gemm_kernel<BN, R><<<grid, kGemmThreads, C::SMEM_BYTES, st>>>(tm_x, tm_w, tm_la, tm_lb, tm_y, p);
   SDT_LAUNCH_OK("lora_gemm");
   return SDT_OK;

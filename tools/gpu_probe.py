@@ -168,6 +168,9 @@ def main():
         guarded("fwd r64 2048x1280x1280", fwd_case, 2048, 1280, 1280, 64, 64, True)
         guarded("fwd r16 BN128 512x256x384", fwd_case, 512, 256, 384, 16, 16, True)
         guarded("fwd r16 4096x320x2560", fwd_case, 4096, 320, 2560, 16, 16, True)
+        guarded("fwd ws r16 32768x320x320", fwd_case, 32768, 320, 320, 16, 16, True)
+        guarded("fwd ws r32 20000x256x640 nobias", fwd_case, 20000, 256, 640, 32, 32, False)
+        guarded("fwd ws r0 40000x384x320", fwd_case, 40000, 384, 320, 0, 0, True)
     if "bwd" in which:
         guarded("bwd r16 256x320x320", bwd_case, 256, 320, 320, 16, 16)
         guarded("bwd r4 616x768x320 nodx", bwd_case, 616, 768, 320, 4, 16, False)
@@ -177,12 +180,12 @@ def main():
     if "ab" in which:
         shapes = [(32768, 320, 320), (32768, 320, 2560), (32768, 1280, 320), (8192, 640, 640), (8192, 640, 5120),
                   (8192, 2560, 640), (2048, 1280, 1280), (2048, 1280, 10240), (2048, 5120, 1280)]
-        for name, k11, k12 in (("single", 1, 0), ("pair160", 0, 1), ("auto", 0, 0)):
-            lib.sdt_debug_set(11, k11); lib.sdt_debug_set(12, k12)
+        for name, k11, k12, k13 in (("single-no-ws", 1, 0, 1), ("single", 1, 0, 0), ("pair160", 0, 1, 0), ("auto", 0, 0, 0)):
+            lib.sdt_debug_set(11, k11); lib.sdt_debug_set(12, k12); lib.sdt_debug_set(13, k13)
             log(f"== variant {name}")
             for (M, K, N) in shapes:
                 guarded(f"{name} fwd {M}x{K}x{N}", fwd_case, M, K, N, 16, 16, True, True)
-        lib.sdt_debug_set(11, 0); lib.sdt_debug_set(12, 0)
+        lib.sdt_debug_set(11, 0); lib.sdt_debug_set(12, 0); lib.sdt_debug_set(13, 0)
     if "time" in which:
         for (M, K, N) in [(32768, 320, 320), (32768, 320, 2560), (32768, 1280, 320), (8192, 640, 640), (8192, 640, 5120),
                           (8192, 2560, 640), (2048, 1280, 1280), (2048, 1280, 10240), (2048, 5120, 1280)]:
