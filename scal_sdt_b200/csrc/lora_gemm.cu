@@ -287,7 +287,8 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if (has_tail) {
             pending = true;
             pend_tile = tile_ctr;
-            pend_needs_ready = first || has_bias;
+            // the bias operand is rewritten per tile, except in weight-stationary mode where it is written once
+            pend_needs_ready = first || (has_bias && !(ws && tile_ctr > 0));
             pend_ready = ready_ctr;
             if (pend_needs_ready) ++ready_ctr;
             if (tail_ready()) issue_tail();      // non-first tiles: operands are usually already there
@@ -355,7 +356,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             }
             ++first_ctr;
           }
-          if (first || has_bias) {
+          if (first || (has_bias && !(ws && tile_ctr > 0))) {
             fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
             tc_fence_before();
             __syncwarp();

@@ -47,5 +47,9 @@ def run(M, K, N, R, bias=True):
         print(f"{v - t0:8d}  {NAMES.get(slot, slot)}")
 
 
-for shape in [(32768, 320, 320, 16), (2048, 1280, 1280, 16), (8192, 640, 5120, 16)]:
-    run(*shape)
+lib.sdt_debug_set(11, 1)          # single-CTA kernel (the traced one)
+for ws_off in (1, 0):
+    lib.sdt_debug_set(13, ws_off)
+    print("==== weight-stationary", "off" if ws_off else "on")
+    for shape in [(32768, 320, 320, 16), (32768, 320, 2560, 16)]:
+        run(*shape)
