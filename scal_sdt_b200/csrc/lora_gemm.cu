@@ -60,7 +60,11 @@ struct LoraGemmCfg {
   static constexpr int kStages = RING_BYTES / STAGE_BYTES > 6 ? 6 : RING_BYTES / STAGE_BYTES;
   static constexpr int SMEM_BYTES = FIXED_BYTES + RING_BYTES;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int ACC1_COL = BN, T_COL = 2 * BN;      // rank accumulators at T_COL and T_COL + R
+  // TMEM: two accumulator buffers of BN + R columns: [main (BN) | rank (R)].  On the first tile of an item ONE UMMA of
+  // N = BN + R computes both (the lora-down k-block sits right behind the W k-block in the stage, so [W ; A] is one B
+  // operand): the X tile is fetched from shared memory once instead of twice -- the tensor core is bound by its operand
+  // fetch (~64 B/clk), and a separate N = R UMMA costs almost half a main one for 1/10 of the FLOPs.
+  static constexpr int ACC1_COL = BN + R, T_COL = BN;
   static_assert(2 * BN + 2 * R <= 512, "TMEM budget");
   static_assert(BN % 32 == 0 && BN <= 256, "BN");
   static_assert(R == 0 || R == 16 || R == 32 || R == 64, "rank must be padded to 16/32/64");
@@ -196,6 +200,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // ===================================== MMA issuer =======================================
     constexpr int RR = R > 0 ? R : 16;
     constexpr uint32_t idesc_main = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t idesc_both = make_idesc_bf16(128, BN + R, 0, 0);      // [W ; lora-down] as one B operand
     constexpr uint32_t idesc_t = make_idesc_bf16(128, RR, 0, 0);
     constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
     // lora-up tile [BN,R], K-major, rows of R*2 bytes written by TMA with the matching swizzle
@@ -244,7 +249,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const bool first = (nt == nt0) && R > 0;
         const uint32_t buf = tile_ctr & 1;
         const uint32_t d_main = tmem_base + buf * C::ACC1_COL;
-        const uint32_t d_tacc = tmem_base + C::T_COL + (first_ctr & 1) * RR;
+        const uint32_t d_tacc = d_main + C::T_COL;           // rank columns of the same buffer
         if (has_main) {
           mbar_wait(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -267,8 +272,12 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
             for (int k = 0; k < C::BK / 16; ++k) {
               const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
-              if (has_main) umma_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), idesc_main, (kb | k) != 0);
-              if (first) umma_f16_ss(d_tacc, a_desc, smem_desc(d_sw128, la + k * 32), idesc_t, (kb | k) != 0);
+              if (has_main && first && !ws)
+                umma_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), idesc_both, (kb | k) != 0);
+              else {
+                if (has_main) umma_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), idesc_main, (kb | k) != 0);
+                if (first) umma_f16_ss(d_tacc, a_desc, smem_desc(d_sw128, la + k * 32), idesc_t, (kb | k) != 0);
+              }
             }
             umma_commit(&empty[s]);
           }
@@ -335,7 +344,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
             for (int c = 0; c < RR / 16; ++c) {
               uint32_t v[16];
-              tmem_ld_x16(lane_addr + C::T_COL + (first_ctr & 1) * RR + c * 16, v);
+              tmem_ld_x16(lane_addr + (tile_ctr & 1) * C::ACC1_COL + C::T_COL + c * 16, v);
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -589,6 +598,8 @@ static int launch_lora_gemm(const void* x, const void* w, const float* bias, con
   choose_groups(m_tiles, p.n_tiles, BN, R, sms, &p.group_size, &p.n_groups);
   p.n_items = m_tiles * p.n_groups;
   int grid = p.n_items < sms ? p.n_items : sms;
+  // (Experimental, opt-in with sdt_debug_set(13, 2): measured no gain -- the K loop is bound by the tensor core's operand
+  // fetch, not by the bytes brought into shared memory, and every tile then pays the rank projection.)
   // Weight-stationary schedule for short K loops (K <= 320: the whole [BN, K] slab of W fits beside the ring): CTA c keeps
   // the W k-blocks, lora-up tile and bias of n-tile (c mod n_tiles) resident and streams only X.  The kernel is bound by
   // the bytes an SM ingests per k-block; without W that is 16 KiB instead of 36 KiB.  Needs every CTA to see >= 2 row tiles.
@@ -596,7 +607,7 @@ static int launch_lora_gemm(const void* x, const void* w, const float* bias, con
   const int ws_stages_fit = (C::RING_BYTES - nk * C::W_BYTES) / C::WS_STAGE_BYTES;
   p.ws = 0;
   p.ws_stages = 0;
-  if (main && nk * C::W_BYTES < C::RING_BYTES && ws_stages_fit >= 3 && p.n_tiles <= sms && debug_get(13) == 0) {
+  if (main && nk * C::W_BYTES < C::RING_BYTES && ws_stages_fit >= 3 && p.n_tiles <= sms && debug_get(13) == 2) {
     const int g = (sms / p.n_tiles) * p.n_tiles;
     if ((long)m_tiles * p.n_tiles >= 2L * g) {
       p.ws = 1;

@@ -85,11 +85,11 @@ struct PairCfg {
   static constexpr int W_BYTES = HN * BK * 2;                       // own half of the W tile
   static constexpr int LA_BYTES = ((HR * BK * 2 + 1023) / 1024) * 1024;   // own half of the lora-down k-block
   static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + LA_BYTES;
-  static constexpr int LB_BYTES = ((HN * R * 2 + 1023) / 1024) * 1024;    // own half of the lora-up tile [BN/2, R]
+  static constexpr int LB_BYTES = (((HN + HR) * R * 2 + 1023) / 1024) * 1024;   // own half of the lora-up tile [BN/2, R] + HR zero rows
   static constexpr int KEXT = R + 16;
   static constexpr int T_SBO = (KEXT / 8) * 128;
   static constexpr int T_BYTES = (BM / 8) * T_SBO;
-  static constexpr int BIAS_BYTES = ((HN * 32 + 1023) / 1024) * 1024;     // own half of the bias operand [BN/2, 16]
+  static constexpr int BIAS_BYTES = (((HN + HR) * 32 + 1023) / 1024) * 1024;   // own half of the bias operand [BN/2, 16] + HR zero rows
   static constexpr int STG_BYTES = 8 * 2 * 2048;
   static constexpr int BAR_BYTES = 256;
   static constexpr int FIXED_BYTES = 1024 + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
@@ -97,7 +97,12 @@ struct PairCfg {
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
   static constexpr int SMEM_BYTES = FIXED_BYTES + kStages * STAGE_BYTES;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int ACC1_COL = BN, T_COL = 2 * BN;
+  // TMEM: two accumulator buffers of BN + R columns.  On the first tile of an item ONE UMMA of N = BN + R computes the base
+  // GEMM and the rank projection together ([W half ; lora-down half] is one B operand per CTA), so X is fetched once.  With
+  // cta_group::2 the N index runs over CTA 0's rows, then CTA 1's, so the columns of such a tile are
+  //   [Y 0..HN) | T 0..HR) | Y HN..BN) | T HR..R)]      (acc_col(y) = y < HN ? y : y + HR ; acc_col(t) = t < HR ? HN + t : BN + t)
+  // and the tail UMMAs use the same N with zero rows appended to the lora-up / bias operands.  Other tiles are plain [Y].
+  static constexpr int ACC1_COL = BN + R;
   static_assert(2 * BN + 2 * R <= 512, "TMEM budget");
   static_assert(BN % 32 == 0 && HN % 8 == 0 && BN <= 256, "BN");
   static_assert(R == 0 || R == 16 || R == 32 || R == 64, "rank must be padded to 16/32/64");
@@ -165,8 +170,13 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
     *reinterpret_cast<uint4*>(trow + (R / 8) * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // bf16 1.0, 1.0
     *reinterpret_cast<uint4*>(trow + (R / 8 + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
-    for (int n = row; n < C::HN; n += 128)
+    for (int n = row; n < C::HN + C::HR; n += 128) {
       *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + 128 + (n & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      if (n >= C::HN) *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // zero rows behind the lora-up tile (rows of R*2 bytes; the TMA box only ever writes the first HN rows)
+    for (int i = row; i < C::HR * R * 2 / 16; i += 128)
+      *reinterpret_cast<uint4*>(lb_smem + C::HN * R * 2 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -212,14 +222,14 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     if (leader) {
       constexpr int RR = R > 0 ? R : 16;
       constexpr uint32_t idesc_main = make_idesc_bf16(256, BN, 0, 0);
-      constexpr uint32_t idesc_t = make_idesc_bf16(256, RR, 0, 0);
+      constexpr uint32_t idesc_both = make_idesc_bf16(256, BN + R, 0, 0);    // first tile of an item: [W ; lora-down]
       constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
       constexpr uint32_t lb_layout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
       constexpr uint64_t d_lb = make_smem_desc_base(16, 8 * RR * 2, lb_layout);
       constexpr uint64_t d_t = make_smem_desc_base(128, C::T_SBO, kLayoutNone);
       constexpr uint64_t d_bias = make_smem_desc_base(128, 256, kLayoutNone);
       uint32_t it = 0, tile_ctr = 0, first_ctr = 0, ready_ctr = 0;
-      bool pending = false, pend_needs_ready = false;
+      bool pending = false, pend_needs_ready = false, pend_first = false;
       uint32_t pend_tile = 0, pend_ready = 0;
 
       auto tail_ready = [&]() -> bool {
@@ -234,10 +244,11 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         if (elect_one()) {
           const uint32_t d = tmem_base + (pend_tile & 1) * C::ACC1_COL;
           const uint32_t ta = smem_u32(t_smem), ba = smem_u32(lb_smem);
+          const uint32_t idesc_tail = pend_first ? idesc_both : idesc_main;   // same column layout as the tile's K loop
 #pragma unroll
           for (int k = 0; k < R / 16; ++k)
-            umma2_f16_ss(d, smem_desc(d_t, ta + k * 256), smem_desc(d_lb, ba + k * 32), idesc_main, 1u);
-          if (has_bias) umma2_f16_ss(d, smem_desc(d_t, ta + (R / 16) * 256), smem_desc(d_bias, smem_u32(bias_smem)), idesc_main, 1u);
+            umma2_f16_ss(d, smem_desc(d_t, ta + k * 256), smem_desc(d_lb, ba + k * 32), idesc_tail, 1u);
+          if (has_bias) umma2_f16_ss(d, smem_desc(d_t, ta + (R / 16) * 256), smem_desc(d_bias, smem_u32(bias_smem)), idesc_tail, 1u);
           umma2_commit_both(lb_empty);
           umma2_commit_both(&acc_full[pend_tile & 1]);
         }
@@ -253,7 +264,6 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           const bool first = (nt == nt0) && R > 0;
           const uint32_t buf = tile_ctr & 1;
           const uint32_t d_main = tmem_base + buf * C::ACC1_COL;
-          const uint32_t d_tacc = tmem_base + C::T_COL + (first_ctr & 1) * RR;
           mbar_wait(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1);
           tc_fence_after();
           for (int kb = 0; kb < nk; ++kb, ++it) {
@@ -267,8 +277,7 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
               for (int k = 0; k < C::BK / 16; ++k) {
                 const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
-                umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), idesc_main, (kb | k) != 0);
-                if (first) umma2_f16_ss(d_tacc, a_desc, smem_desc(d_sw128, la + k * 32), idesc_t, (kb | k) != 0);
+                umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main, (kb | k) != 0);
               }
               umma2_commit_both(&empty[s]);
             }
@@ -283,6 +292,7 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           if (has_tail) {
             pending = true;
             pend_tile = tile_ctr;
+            pend_first = first;
             pend_needs_ready = first || has_bias;
             pend_ready = ready_ctr;
             if (pend_needs_ready) ++ready_ctr;
@@ -326,13 +336,15 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             tc_fence_after();
             uint32_t packed[RR / 2];
 #pragma unroll
-            for (int c = 0; c < RR / 16; ++c) {
-              uint32_t v[16];
-              tmem_ld_x16(lane_addr + C::T_COL + (first_ctr & 1) * RR + c * 16, v);
+            for (int c = 0; c < RR / 8; ++c) {
+              // rank column t lives at HN + t (t < HR: CTA 0's lora-down rows) or BN + t (CTA 1's)
+              const int t0 = c * 8;
+              uint32_t v[8];
+              tmem_ld_x8(lane_addr + (tile_ctr & 1) * C::ACC1_COL + (t0 < C::HR ? C::HN + t0 : C::BN + t0), v);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                packed[c * 8 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling);
+              for (int j = 0; j < 4; ++j)
+                packed[c * 4 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling);
             }
             uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
 #pragma unroll
@@ -373,12 +385,21 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const uint32_t buf = tile_ctr & 1;
         const int n0 = nt * C::BN;
         const bool rows_live = m0 + q * 32 < p.M;
+        const int gap = (nt == nt0 && R > 0) ? C::HR : 0;      // first tile of an item: Y columns >= HN sit HR further right
         mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
         tc_fence_after();
         int c = (tile_ctr + half) & 1;
         uint32_t v[32];
+        // 32 output columns = two 16-column TMEM loads (HN is a multiple of 16, so a half never straddles the gap)
+        auto load_chunk = [&](int cc) {
+          uint32_t(&lo)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
+          uint32_t(&hi)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[16]);
+          const int y0 = cc * 32, y1 = cc * 32 + 16;
+          tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y0 + (y0 >= C::HN ? gap : 0), lo);
+          tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y1 + (y1 >= C::HN ? gap : 0), hi);
+        };
         bool have = c < C::BN / 32 && n0 + c * 32 < p.N;
-        if (have) tmem_ld_x32(lane_addr + buf * C::ACC1_COL + c * 32, v);
+        if (have) load_chunk(c);
         while (have) {
           tmem_ld_wait();
           uint32_t pk[16];
@@ -387,7 +408,7 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           const int col0 = n0 + c * 32;
           c += 2;
           have = c < C::BN / 32 && n0 + c * 32 < p.N;
-          if (have) tmem_ld_x32(lane_addr + buf * C::ACC1_COL + c * 32, v);
+          if (have) load_chunk(c);
           if (rows_live) {
             uint8_t* sb = stg + (stores & 1) * 2048;
             if (stores >= 2) {
