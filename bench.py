@@ -207,8 +207,9 @@ def build_trainer(device, exchange):
 
 
 def site_flops(records):
-    fwd = sum(2.0 * M * K * N + 2.0 * M * R * (K + N) for kind, M, K, N, R, *_ in records if kind == "fwd")
-    bwd = sum((2.0 * M * K * N if dx else 0.0) + 4.0 * M * R * (K + N) for kind, M, K, N, R, dx, *_ in records if kind == "bwd")
+    # one record per lora_gemm* launch; G = same-shape projections computed by that launch (grouped q/k/v, k/v)
+    fwd = sum(G * (2.0 * M * K * N + 2.0 * M * R * (K + N)) for kind, M, K, N, R, G, *_ in records if kind == "fwd")
+    bwd = sum(G * ((2.0 * M * K * N if dx else 0.0) + 4.0 * M * R * (K + N)) for kind, M, K, N, R, G, dx, *_ in records if kind == "bwd")
     return fwd, bwd
 
 
@@ -401,16 +402,16 @@ def ours_main(args):
         ach = f_fwd / t_fwd / 1e12
         # per-shape view of the same forward launches: which bound applies to which class of site
         shapes = {}
-        for (kind, M, K, N, R, *_), sec in zip(fwd_sites, fwd_t):
-            e = shapes.setdefault((M, K, N, R), [0, 0.0])
+        for (kind, M, K, N, R, G, *_), sec in zip(fwd_sites, fwd_t):
+            e = shapes.setdefault((M, K, N, R, G), [0, 0.0])
             e[0] += 1
             e[1] += sec
         by_shape = []
-        for (M, K, N, R), (cnt, sec) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
-            fl = 2.0 * M * K * N + 2.0 * M * R * (K + N)
-            by = 2.0 * (M * K + K * N + R * (K + N) + M * N + M * R)
+        for (M, K, N, R, G), (cnt, sec) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+            fl = G * (2.0 * M * K * N + 2.0 * M * R * (K + N))
+            by = 2.0 * (M * K + G * (K * N + R * (K + N) + M * N + M * R))      # a grouped launch reads its shared X once
             tf, gbs = fl * cnt / sec / 1e12, by * cnt / sec / 1e9
-            by_shape.append({"M": M, "K": K, "N": N, "R": R, "launches": cnt, "avg_us": 1e6 * sec / cnt, "tflops": tf,
+            by_shape.append({"M": M, "K": K, "N": N, "R": R, "projections_per_launch": G, "launches": cnt, "avg_us": 1e6 * sec / cnt, "tflops": tf,
                              "frac_tensor": tf / peaks["tf_sustained"], "algorithmic_gbs": gbs, "frac_hbm": gbs / peaks["hbm"],
                              "bound": "tensor" if fl / by > peaks["tf_sustained"] * 1e3 / peaks["hbm"] else "hbm"})
         # DRAM bytes per GEMM launch from the committed ncu pass over one training step (dram__bytes_read + write summed over
@@ -424,16 +425,16 @@ def ours_main(args):
             if gl:
                 traffic = sum((v["dram_read_MB"] + v["dram_write_MB"]) * 1e6 for v in gl) / sum(v["launches"] for v in gl)
                 traffic_src = "profiles/r01_v5_lora_kernels_per_step_ncu.json (avg over the forward + dX GEMM launches of a step)"
-        alg_bytes = sum(2.0 * (M * K + K * N + R * (K + N) + M * N + M * R) for kind, M, K, N, R, *_ in fwd_sites) / max(n_fwd, 1)
-        dx_flops = sum(2.0 * M * K * N + 2.0 * M * R * (K + N) for kind, M, K, N, R, dx, *_ in bwd_sites if dx) + \
-            sum(2.0 * M * R * N for kind, M, K, N, R, dx, *_ in bwd_sites if not dx)
+        alg_bytes = sum(2.0 * (M * K + G * (K * N + R * (K + N) + M * N + M * R)) for kind, M, K, N, R, G, *_ in fwd_sites) / max(n_fwd, 1)
+        dx_flops = sum(G * (2.0 * M * K * N + 2.0 * M * R * (K + N)) for kind, M, K, N, R, G, dx, *_ in bwd_sites if dx) + \
+            sum(G * 2.0 * M * R * N for kind, M, K, N, R, G, dx, *_ in bwd_sites if not dx)
         backward = {"kernels": "lora_gemm* (dX, G) + lora_wgrad_kernel (dA and dB in one launch)", "timing": "cuda_events",
                     "achieved": f_bwd / t_bwd / 1e12, "frac": f_bwd / t_bwd / 1e12 / peaks["tf_sustained"]}
         if bwd_gemm_t is not None:
             backward["dx_gemm"] = {"timing": timing, "achieved": dx_flops / sum(bwd_gemm_t) / 1e12,
                                    "frac": dx_flops / sum(bwd_gemm_t) / 1e12 / peaks["tf_sustained"],
                                    "seconds_per_step": sum(bwd_gemm_t)}
-        roof = {"kernel": "lora_gemm_kernel / lora_gemm_pair_kernel (K1: fused X W^T + bias + s (X A^T) B^T), all 192 forward launches of a step",
+        roof = {"kernel": "lora_gemm_kernel / lora_gemm_pair_kernel (K1: fused X W^T + bias + s (X A^T) B^T), every forward launch of a step (192 projections; q/k/v and cross-attention k/v go out as grouped launches)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src, "timing": timing,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peaks["source"] + ", sustained bf16",

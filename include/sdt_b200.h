@@ -57,6 +57,21 @@ int sdt_lora_linear_fwd(const void* x, const void* w, const float* bias, const v
                         float scaling, void* y, void* t_save,
                         int64_t M, int64_t K, int64_t N, int r, int dtype, void* stream);
 
+/* ---- K1 (grouped): several projections of ONE shape in one launch ---------------------------
+ * The reference calls to_q / to_k / to_v of a self-attention on the same normalised hidden states, and to_k / to_v
+ * of a cross-attention on the same text context (diffusers CrossAttention.forward under modules/lora.py:12-14): three
+ * (two) launches of 6.7 GFLOP each.  This entry runs up to SDT_MAX_GROUP such projections -- identical (M, K, N, r,
+ * scaling), own W / A / B / bias / y / t_save, x may be shared -- as the work items of ONE persistent kernel, so launch,
+ * prologue and pipeline-drain costs are paid once and the wave quantisation is that of the combined tile count.
+ * `problems` is a HOST array; bf16 only; every problem has a bias or none has.
+ */
+#define SDT_MAX_GROUP 4
+typedef struct {
+  const void* x; const void* w; const float* bias; const void* A; const void* B; void* y; void* t_save;
+} sdt_lora_problem;
+int sdt_lora_linear_fwd_group(const sdt_lora_problem* problems /* host */, int n_problems, float scaling,
+                              int64_t M, int64_t K, int64_t N, int r, int dtype, void* stream);
+
 /* ---- K2: fused LoRA projection, backward ---------------------------------------------------
  * Autograd of the above with W, bias frozen (modules/model.py:137):
  *     G  = scaling * (dY B)             [M,r]   (on-chip; also written to g_ws)

@@ -24,6 +24,14 @@ class PackSite(ctypes.Structure):
                 ("Bt_p", c_void_p), ("K", c_int32), ("N", c_int32), ("r_true", c_int32), ("r", c_int32)]
 
 
+class LoraProblem(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("A", c_void_p), ("B", c_void_p), ("y", c_void_p),
+                ("t_save", c_void_p)]
+
+
+MAX_GROUP = 4
+
+
 class Chunk(ctypes.Structure):
     _fields_ = [("tensor", c_int32), ("pad", c_int32), ("offset", c_int64)]
 
@@ -36,6 +44,7 @@ SIGNATURES = {
     "sdt_launch_count": (ctypes.c_longlong, []),
     "sdt_lora_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "sdt_lora_linear_fwd_group": (c_int, [c_void_p, c_int, c_float, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sdt_lora_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                     c_void_p]),

@@ -2,6 +2,7 @@
 //   SDT_BF16 -> tcgen05 / TMEM / TMA kernels (lora_gemm.cu, lora_wgrad.cu)
 //   SDT_F32  -> FFMA kernels (simt_gemm.cu): parity path of the reference's fp32 configuration
 #include "sdt_common.cuh"
+#include "lora_gemm.cuh"
 
 namespace sdt {
 int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
@@ -38,6 +39,22 @@ extern "C" int sdt_lora_linear_fwd(const void* x, const void* w, const float* bi
                         (float*)t_save, M, K, N, r, st);
   set_error("sdt_lora_linear_fwd: unsupported dtype %d (there is no fallback path)", dtype);
   return SDT_ERR_UNSUPPORTED;
+}
+
+static_assert(sizeof(sdt_lora_problem) == sizeof(LoraProblem), "sdt_lora_problem mirrors sdt::LoraProblem");
+
+extern "C" int sdt_lora_linear_fwd_group(const sdt_lora_problem* problems, int n_problems, float scaling, int64_t M, int64_t K,
+                                         int64_t N, int r, int dtype, void* stream) {
+  SDT_REQUIRE(problems != nullptr && n_problems >= 1 && n_problems <= SDT_MAX_GROUP, SDT_ERR_ARG,
+              "sdt_lora_linear_fwd_group: 1..%d problems per launch (got %d)", SDT_MAX_GROUP, n_problems);
+  SDT_REQUIRE(dtype == SDT_BF16, SDT_ERR_UNSUPPORTED,
+              "sdt_lora_linear_fwd_group: bf16 only (fp32 sites go through sdt_lora_linear_fwd one by one; there is no fallback)");
+  SDT_REQUIRE(r == 16 || r == 32 || r == 64, SDT_ERR_UNSUPPORTED, "sdt_lora_linear_fwd_group: padded rank must be 16, 32 or 64 (got %d)", r);
+  for (int q = 0; q < n_problems; ++q)
+    SDT_REQUIRE(problems[q].x && problems[q].w && problems[q].A && problems[q].B && problems[q].y && problems[q].t_save, SDT_ERR_ARG,
+                "sdt_lora_linear_fwd_group: null pointer in problem %d", q);
+  return lora_gemm_group_bf16(reinterpret_cast<const LoraProblem*>(problems), n_problems, scaling, M, K, N, r, true,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt, const void* At, const void* Bt,

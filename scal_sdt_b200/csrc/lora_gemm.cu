@@ -23,6 +23,7 @@
 // down projection is computed once per group, not once per output tile.
 #include "sdt_common.cuh"
 #include "sm100_ptx.cuh"
+#include "lora_gemm.cuh"
 
 #include <mutex>
 #include <unordered_map>
@@ -74,10 +75,10 @@ struct LoraGemmCfg {
 constexpr int kGemmThreads = 14 * 32;
 
 struct LoraGemmParams {
-  const float* bias;      // [N] or null
-  __nv_bfloat16* t_out;   // [M,R] or null
   float scaling;
   int M, N, K;
+  int n_probs;            // problems of identical shape in this launch (<= G); items enumerate (m-tile, problem, n-group)
+  int has_bias;           // every problem has a bias (all or none)
   int n_tiles, n_groups, group_size, n_items;
   int main;               // 0: only the rank-R projection is computed (t_out), no base GEMM
   int ws;                 // weight-stationary: every CTA keeps the W k-blocks of ITS n-tile resident (K <= 320), see launch
@@ -85,11 +86,29 @@ struct LoraGemmParams {
   long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
 };
 
-template <int BN, int R>
+// item -> (problem, first row, n-group).  Consecutive items walk the problems and n-groups of ONE row tile, so CTAs that run
+// side by side read the same rows of a shared X from L2.
+struct ItemCoord { int prob, m0, g; };
+template <int G>
+__device__ __forceinline__ ItemCoord decode_item(int item, const LoraGemmParams& p, int BM) {
+  ItemCoord c;
+  if (G == 1) {
+    c.prob = 0;
+    c.m0 = (item / p.n_groups) * BM;
+    c.g = item % p.n_groups;
+  } else {
+    const int per_m = p.n_probs * p.n_groups;
+    const int mt = item / per_m, rem = item - mt * per_m;
+    c.prob = rem / p.n_groups;
+    c.m0 = mt * BM;
+    c.g = rem - c.prob * p.n_groups;
+  }
+  return c;
+}
+
+template <int BN, int R, int G>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                 const __grid_constant__ CUtensorMap tm_la, const __grid_constant__ CUtensorMap tm_lb,
-                 const __grid_constant__ CUtensorMap tm_y, const LoraGemmParams p) {
+lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p) {
   using C = LoraGemmCfg<BN, R>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -112,7 +131,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (p.K + C::BK - 1) / C::BK;
   const bool has_main = p.main != 0;
-  const bool has_bias = has_main && p.bias != nullptr;
+  const bool has_bias = has_main && p.has_bias != 0;
   const bool has_tail = has_main && (R > 0 || has_bias);   // UMMAs issued after the K loop of a tile
   // weight-stationary layout: [nk resident W k-blocks | ring of (X, lora-down) stages]; otherwise ring of (X, W, lora-down)
   const bool ws = p.ws != 0;
@@ -122,9 +141,11 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
   if (threadIdx.x == 0) SDT_TRACE(0);
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm_x);
-    if (has_main) { prefetch_tmap(&tm_w); prefetch_tmap(&tm_y); }
-    if (R > 0) { prefetch_tmap(&tm_la); if (has_main) prefetch_tmap(&tm_lb); }
+    for (int q = 0; q < (G == 1 ? 1 : p.n_probs); ++q) {
+      prefetch_tmap(&gm.x[q]);
+      if (has_main) { prefetch_tmap(&gm.w[q]); prefetch_tmap(&gm.y[q]); }
+      if (R > 0) { prefetch_tmap(&gm.la[q]); if (has_main) prefetch_tmap(&gm.lb[q]); }
+    }
     for (int s = 0; s < C::kMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(w_full, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
@@ -161,8 +182,12 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       uint32_t it = 0;       // k-block counter across the whole CTA lifetime
       uint32_t tile_ctr = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int m0 = (item / p.n_groups) * C::BM;
-        const int g = item % p.n_groups;
+        const ItemCoord ic = decode_item<G>(item, p, C::BM);
+        const int m0 = ic.m0, g = ic.g;
+        const CUtensorMap* tm_x = &gm.x[ic.prob];
+        const CUtensorMap* tm_w = &gm.w[ic.prob];
+        const CUtensorMap* tm_la = &gm.la[ic.prob];
+        const CUtensorMap* tm_lb = &gm.lb[ic.prob];
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -171,10 +196,10 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if (ws && tile_ctr == 0) {
             // this CTA's n-tile never changes (grid is a multiple of n_tiles): W and the lora-up tile are loaded once
             mbar_arrive_expect_tx(w_full, (uint32_t)nk * C::W_BYTES);
-            for (int kb = 0; kb < nk; ++kb) tma_load_2d(smem + kb * C::W_BYTES, &tm_w, kb * C::BK, n0, w_full);
+            for (int kb = 0; kb < nk; ++kb) tma_load_2d(smem + kb * C::W_BYTES, tm_w, kb * C::BK, n0, w_full);
             if (R > 0) {
               mbar_arrive_expect_tx(lb_full, BN * R * 2);
-              tma_load_2d(lb_smem, &tm_lb, 0, n0, lb_full);
+              tma_load_2d(lb_smem, tm_lb, 0, n0, lb_full);
             }
           }
           const uint32_t tx = C::X_BYTES + (has_main && !ws ? C::W_BYTES : 0) + (first ? C::LA_BYTES : 0);
@@ -184,14 +209,14 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             uint8_t* st = ring + s * stage_bytes;
             mbar_arrive_expect_tx(&full[s], tx);
             if (it == 0) SDT_TRACE(2);
-            tma_load_2d(st, &tm_x, kb * C::BK, m0, &full[s]);
-            if (has_main && !ws) tma_load_2d(st + C::X_BYTES, &tm_w, kb * C::BK, n0, &full[s]);
-            if (first) tma_load_2d(st + C::X_BYTES + (ws ? 0 : C::W_BYTES), &tm_la, kb * C::BK, 0, &full[s]);
+            tma_load_2d(st, tm_x, kb * C::BK, m0, &full[s]);
+            if (has_main && !ws) tma_load_2d(st + C::X_BYTES, tm_w, kb * C::BK, n0, &full[s]);
+            if (first) tma_load_2d(st + C::X_BYTES + (ws ? 0 : C::W_BYTES), tm_la, kb * C::BK, 0, &full[s]);
           }
           if (R > 0 && has_main && !ws) {
             mbar_wait(lb_empty, (tile_ctr & 1) ^ 1);
             mbar_arrive_expect_tx(lb_full, BN * R * 2);
-            tma_load_2d(lb_smem, &tm_lb, 0, n0, lb_full);
+            tma_load_2d(lb_smem, tm_lb, 0, n0, lb_full);
           }
         }
       }
@@ -242,7 +267,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     };
 
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int g = item % p.n_groups;
+      const int g = decode_item<G>(item, p, C::BM).g;
       const int nt0 = g * p.group_size;
       const int nt1 = min(nt0 + p.group_size, p.n_tiles);
       for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -320,8 +345,10 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     uint32_t tile_ctr = 0, first_ctr = 0;
     if (has_tail || (!has_main && R > 0)) {
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int m0 = (item / p.n_groups) * C::BM;
-        const int g = item % p.n_groups;
+        const ItemCoord ic = decode_item<G>(item, p, C::BM);
+        const int m0 = ic.m0, g = ic.g;
+        const float* bias = gm.bias[ic.prob];
+        __nv_bfloat16* t_out = gm.t_out[ic.prob];
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -331,7 +358,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             if (tile_ctr > 0) mbar_wait(lb_empty, (tile_ctr - 1) & 1);
             const int n0 = nt * C::BN;
             for (int n = tid; n < BN; n += 128) {
-              const float b = (n0 + n < p.N) ? __ldg(p.bias + n0 + n) : 0.f;
+              const float b = (n0 + n < p.N) ? __ldg(bias + n0 + n) : 0.f;
               const float hi = round_bf16(b);
               *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) =
                   make_uint4(pack_bf16x2(hi, b - hi), 0u, 0u, 0u);
@@ -357,8 +384,8 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 *reinterpret_cast<uint4*>(trow + kc * 128) =
                     make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
             }
-            if (p.t_out != nullptr && g == 0 && m0 + row < p.M) {
-              uint4* dst = reinterpret_cast<uint4*>(p.t_out + (size_t)(m0 + row) * RR);
+            if (t_out != nullptr && g == 0 && m0 + row < p.M) {
+              uint4* dst = reinterpret_cast<uint4*>(t_out + (size_t)(m0 + row) * RR);
 #pragma unroll
               for (int kc = 0; kc < RR / 8; ++kc)
                 dst[kc] = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
@@ -385,8 +412,9 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     uint32_t tile_ctr = 0, stores = 0;
     if (has_main) {
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int m0 = (item / p.n_groups) * C::BM;
-        const int g = item % p.n_groups;
+        const ItemCoord ic = decode_item<G>(item, p, C::BM);
+        const int m0 = ic.m0, g = ic.g;
+        const CUtensorMap* tm_y = &gm.y[ic.prob];
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -426,7 +454,7 @@ lora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               __syncwarp();
               if (lane == 0) {
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                                 reinterpret_cast<uint64_t>(&tm_y)),
+                                 reinterpret_cast<uint64_t>(tm_y)),
                              "r"(col0), "r"(m0 + q * 32), "r"(smem_u32(sb))
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -550,64 +578,71 @@ static void choose_groups(int m_tiles, int n_tiles, int BN, int R, int sms, int*
   *n_groups = (n_tiles + best_gs - 1) / best_gs;
 }
 
-template <int BN, int R>
-static int launch_lora_gemm(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling,
-                            void* y, void* t_out, int64_t M, int64_t K, int64_t N, bool main, cudaStream_t st) {
+template <int BN, int R, int G>
+static int launch_lora_gemm(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, bool main,
+                            cudaStream_t st) {
   using C = LoraGemmCfg<BN, R>;
   static bool attr_set = false;
   if (!attr_set) {
-    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_kernel<BN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_kernel<BN, R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  CUtensorMap tm_x, tm_w, tm_la, tm_lb, tm_y;
-  int rc = make_tmap_2d_bf16(&tm_x, x, M, K, K * 2, C::BM, C::BK, TMAP_SW_128);
-  if (rc != SDT_OK) return rc;
-  if (main) {
-    rc = make_tmap_2d_bf16(&tm_w, w, N, K, K * 2, BN, C::BK, TMAP_SW_128);
-    if (rc != SDT_OK) return rc;
-    rc = make_tmap_2d_bf16(&tm_y, y, M, N, N * 2, 32, 32, TMAP_SW_64);
-    if (rc != SDT_OK) return rc;
-  } else {
-    tm_w = tm_x;
-    tm_y = tm_x;
-  }
-  if (R > 0) {
-    rc = make_tmap_2d_bf16(&tm_la, la, R, K, K * 2, R, C::BK, TMAP_SW_128);
+  GemmGroup<G> gm;
+  for (int q = 0; q < G; ++q) {
+    const LoraProblem& pr = probs[q < n_probs ? q : 0];     // unused slots repeat problem 0 (never dereferenced)
+    int rc = make_tmap_2d_bf16(&gm.x[q], pr.x, M, K, K * 2, C::BM, C::BK, TMAP_SW_128);
     if (rc != SDT_OK) return rc;
     if (main) {
-      rc = make_tmap_2d_bf16(&tm_lb, lb, N, R, (uint64_t)R * 2, BN, R,
-                             R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
+      rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, BN, C::BK, TMAP_SW_128);
+      if (rc != SDT_OK) return rc;
+      rc = make_tmap_2d_bf16(&gm.y[q], pr.y, M, N, N * 2, 32, 32, TMAP_SW_64);
       if (rc != SDT_OK) return rc;
     } else {
-      tm_lb = tm_la;
+      gm.w[q] = gm.x[q];
+      gm.y[q] = gm.x[q];
     }
-  } else {
-    tm_la = tm_x;
-    tm_lb = tm_x;
+    if (R > 0) {
+      rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, R, C::BK, TMAP_SW_128);
+      if (rc != SDT_OK) return rc;
+      if (main) {
+        rc = make_tmap_2d_bf16(&gm.lb[q], pr.lb, N, R, (uint64_t)R * 2, BN, R,
+                               R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
+        if (rc != SDT_OK) return rc;
+      } else {
+        gm.lb[q] = gm.la[q];
+      }
+    } else {
+      gm.la[q] = gm.x[q];
+      gm.lb[q] = gm.x[q];
+    }
+    gm.bias[q] = pr.bias;
+    gm.t_out[q] = reinterpret_cast<__nv_bfloat16*>(pr.t_out);
   }
   LoraGemmParams p;
-  p.bias = bias;
-  p.t_out = reinterpret_cast<__nv_bfloat16*>(t_out);
   p.scaling = scaling;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.n_probs = n_probs;
+  p.has_bias = probs[0].bias != nullptr ? 1 : 0;
   p.main = main ? 1 : 0;
   p.trace = reinterpret_cast<long long*>(debug_get(10));
   const int m_tiles = (int)((M + C::BM - 1) / C::BM);
   p.n_tiles = main ? (int)((N + BN - 1) / BN) : 1;
   const int sms = num_sms();
-  choose_groups(m_tiles, p.n_tiles, BN, R, sms, &p.group_size, &p.n_groups);
-  p.n_items = m_tiles * p.n_groups;
+  // the problems of a launch multiply the number of row tiles a scheduling round can draw from
+  choose_groups(m_tiles * n_probs, p.n_tiles, BN, R, sms, &p.group_size, &p.n_groups);
+  p.n_items = m_tiles * n_probs * p.n_groups;
   int grid = p.n_items < sms ? p.n_items : sms;
-  // (Experimental, opt-in with sdt_debug_set(13, 2): measured no gain -- the K loop is bound by the tensor core's operand
-  // fetch, not by the bytes brought into shared memory, and every tile then pays the rank projection.)
+  // (Experimental, opt-in with sdt_debug_set(13, 2): measured no gain.  tools/umma_bench.cu shows why: with A read from
+  // shared memory a UMMA costs N/2 + 38 cycles, so a schedule that pays a separate N = R rank UMMA on every tile is bound by
+  // the tensor core's operand fetch even when the ring only carries X.)
   // Weight-stationary schedule for short K loops (K <= 320: the whole [BN, K] slab of W fits beside the ring): CTA c keeps
-  // the W k-blocks, lora-up tile and bias of n-tile (c mod n_tiles) resident and streams only X.  The kernel is bound by
-  // the bytes an SM ingests per k-block; without W that is 16 KiB instead of 36 KiB.  Needs every CTA to see >= 2 row tiles.
+  // the W k-blocks, lora-up tile and bias of n-tile (c mod n_tiles) resident and streams only X.  Needs every CTA to see >= 2
+  // row tiles.
   const int nk = (int)((K + C::BK - 1) / C::BK);
   const int ws_stages_fit = (C::RING_BYTES - nk * C::W_BYTES) / C::WS_STAGE_BYTES;
   p.ws = 0;
   p.ws_stages = 0;
-  if (main && nk * C::W_BYTES < C::RING_BYTES && ws_stages_fit >= 3 && p.n_tiles <= sms && debug_get(13) == 2) {
+  if (G == 1 && main && nk * C::W_BYTES < C::RING_BYTES && ws_stages_fit >= 3 && p.n_tiles <= sms && debug_get(13) == 2) {
     const int g = (sms / p.n_tiles) * p.n_tiles;
     if ((long)m_tiles * p.n_tiles >= 2L * g) {
       p.ws = 1;
@@ -618,36 +653,61 @@ static int launch_lora_gemm(const void* x, const void* w, const float* bias, con
       grid = g;
     }
   }
-  lora_gemm_kernel<BN, R><<<grid, kGemmThreads, C::SMEM_BYTES, st>>>(tm_x, tm_w, tm_la, tm_lb, tm_y, p);
+  lora_gemm_kernel<BN, R, G><<<grid, kGemmThreads, C::SMEM_BYTES, st>>>(gm, p);
   SDT_LAUNCH_OK("lora_gemm");
   return SDT_OK;
 }
 
-int lora_gemm_pair_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
-                        void* t_out, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st);
+static int check_group(const LoraProblem* probs, int n_probs, int r, bool main) {
+  SDT_REQUIRE(probs != nullptr && n_probs >= 1 && n_probs <= kMaxGroup, SDT_ERR_ARG,
+              "lora_gemm: a launch takes 1..%d problems (got %d)", kMaxGroup, n_probs);
+  for (int q = 0; q < n_probs; ++q) {
+    const LoraProblem& pr = probs[q];
+    SDT_REQUIRE(pr.x != nullptr && (!main || (pr.w != nullptr && pr.y != nullptr)), SDT_ERR_ARG, "lora_gemm: null operand in problem %d", q);
+    SDT_REQUIRE((r == 0) == (pr.la == nullptr) && (r == 0 || !main || pr.lb != nullptr), SDT_ERR_ARG,
+                "lora_gemm: lora operands must be given exactly when r > 0 (problem %d)", q);
+    SDT_REQUIRE((pr.bias != nullptr) == (probs[0].bias != nullptr), SDT_ERR_ARG,
+                "lora_gemm: the problems of one launch must all have a bias or all have none");
+    SDT_REQUIRE(aligned16(pr.x) && aligned16(pr.w) && aligned16(pr.la) && aligned16(pr.lb) && aligned16(pr.y) && aligned16(pr.t_out),
+                SDT_ERR_ARG, "lora_gemm: pointers must be 16-byte aligned (problem %d)", q);
+  }
+  return SDT_OK;
+}
 
-// bf16 entry used by sdt_lora_linear_fwd / sdt_lora_linear_bwd (lora_api.cu)
-int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
-                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, cudaStream_t st) {
+// bf16 entry used by sdt_lora_linear_fwd(_group) / sdt_lora_linear_bwd (lora_api.cu): n_probs problems of one shape
+int lora_gemm_group_bf16(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, int r, bool main,
+                         cudaStream_t st) {
   SDT_REQUIRE(M > 0 && K > 0 && N > 0, SDT_ERR_ARG, "lora_gemm: bad sizes M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
   SDT_REQUIRE(M < (1ll << 31) && K < (1ll << 31) && N < (1ll << 31), SDT_ERR_UNSUPPORTED, "lora_gemm: dimension exceeds int32");
   SDT_REQUIRE(K % 8 == 0 && N % 8 == 0, SDT_ERR_UNSUPPORTED, "lora_gemm: K and N must be multiples of 8 (K=%lld N=%lld)", (long long)K, (long long)N);
   SDT_REQUIRE(r == 0 || r == 16 || r == 32 || r == 64, SDT_ERR_UNSUPPORTED,
               "lora_gemm: padded rank must be 0, 16, 32 or 64 (got %d)", r);
   SDT_REQUIRE(main || r > 0, SDT_ERR_ARG, "lora_gemm: nothing to compute");
+  int rc = check_group(probs, n_probs, r, main);
+  if (rc != SDT_OK) return rc;
+  SDT_REQUIRE(n_probs == 1 || r > 0, SDT_ERR_UNSUPPORTED, "lora_gemm: grouped launches are built for r > 0 only");
   // CTA-pair (cta_group::2) kernel when there is a base GEMM, at least one full pair of row tiles and a K loop long
   // enough (>= 8 k-blocks) to amortise the cross-CTA hand-shakes (measured: K = 320 is faster on the single-CTA kernel);
   // sdt_debug_set(11, 1) forces the single-CTA kernel (A/B measurements)
   if (main && M >= 256 && K >= 512 && debug_get(11) == 0)
-    return lora_gemm_pair_bf16(x, w, bias, la, lb, scaling, y, t_out, M, K, N, r, st);
+    return lora_gemm_pair_group_bf16(probs, n_probs, scaling, M, K, N, r, st);
   const bool bn160 = !main || (N % 160 == 0) || (N % 128 != 0 && N > 128);
-#define SDT_GEMM(BN, R) return launch_lora_gemm<BN, R>(x, w, bias, la, lb, scaling, y, t_out, M, K, N, main, st)
-  if (bn160) {
-    switch (r) { case 0: SDT_GEMM(160, 0); case 16: SDT_GEMM(160, 16); case 32: SDT_GEMM(160, 32); default: SDT_GEMM(160, 64); }
-  } else {
-    switch (r) { case 0: SDT_GEMM(128, 0); case 16: SDT_GEMM(128, 16); case 32: SDT_GEMM(128, 32); default: SDT_GEMM(128, 64); }
+#define SDT_GEMM(BN, R, G) return launch_lora_gemm<BN, R, G>(probs, n_probs, scaling, M, K, N, main, st)
+#define SDT_GEMM_R(BN, G)                                                                     \
+  switch (r) { case 16: SDT_GEMM(BN, 16, G); case 32: SDT_GEMM(BN, 32, G); default: SDT_GEMM(BN, 64, G); }
+  if (n_probs == 1) {
+    if (r == 0) { if (bn160) SDT_GEMM(160, 0, 1); else SDT_GEMM(128, 0, 1); }
+    if (bn160) { SDT_GEMM_R(160, 1) } else { SDT_GEMM_R(128, 1) }
   }
+  if (bn160) { SDT_GEMM_R(160, kMaxGroup) } else { SDT_GEMM_R(128, kMaxGroup) }
+#undef SDT_GEMM_R
 #undef SDT_GEMM
+}
+
+int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
+                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, cudaStream_t st) {
+  const LoraProblem pr{x, w, bias, la, lb, y, t_out};
+  return lora_gemm_group_bf16(&pr, 1, scaling, M, K, N, r, main, st);
 }
 
 }  // namespace sdt

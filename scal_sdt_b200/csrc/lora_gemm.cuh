@@ -1,0 +1,40 @@
+// Types shared by the fused LoRA GEMM kernels (lora_gemm.cu: single CTA; lora_gemm2.cu: CTA pair) and their callers.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdt {
+
+// One projection Y = X W^T + bias + (s X la^T) lb^T of a launch.  Every problem of a launch has the same (M, K, N, R,
+// scaling); pointers may repeat (q / k / v read the same X).
+struct LoraProblem {
+  const void* x;       // [M,K] bf16
+  const void* w;       // [N,K] bf16 (null when only the rank-R projection is wanted)
+  const float* bias;   // [N] f32 or null
+  const void* la;      // lora-down [R,K] bf16
+  const void* lb;      // lora-up   [N,R] bf16
+  void* y;             // [M,N] bf16
+  void* t_out;         // [M,R] bf16 or null
+};
+
+// Problems per launch: q/k/v of a self-attention (3), k/v of cross-attentions that read the same text context (2-4).
+constexpr int kMaxGroup = 4;
+
+// Kernel-parameter block: the tensor maps of up to G problems (G = 1: 656 bytes; G = 4: 2.6 KB, indexed dynamically in
+// the parameter space -- no copy to local memory, `prefetch.tensormap` / TMA take the generic address of the entry).
+template <int G>
+struct GemmGroup {
+  CUtensorMap x[G], w[G], la[G], lb[G], y[G];
+  const float* bias[G];
+  __nv_bfloat16* t_out[G];
+};
+
+// entry points (lora_gemm.cu / lora_gemm2.cu)
+int lora_gemm_group_bf16(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, int r, bool main,
+                         cudaStream_t st);
+int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, int r,
+                              cudaStream_t st);
+
+}  // namespace sdt

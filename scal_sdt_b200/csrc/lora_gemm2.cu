@@ -13,6 +13,7 @@
 //   * every B-type operand (W, lora-down, lora-up, bias) is split by rows between the two CTAs.
 #include "sdt_common.cuh"
 #include "sm100_ptx.cuh"
+#include "lora_gemm.cuh"
 
 namespace sdt {
 
@@ -113,18 +114,35 @@ struct PairCfg {
 constexpr int kPairThreads = 14 * 32;
 
 struct PairParams {
-  const float* bias;
-  __nv_bfloat16* t_out;
   float scaling;
   int M, N, K;
-  int n_tiles, n_groups, group_size, n_items;   // items are (256-row tile, n-group)
+  int n_probs;            // problems of identical shape in this launch (<= G)
+  int has_bias;
+  int n_tiles, n_groups, group_size, n_items;   // items are (256-row tile, problem, n-group)
 };
 
-template <int BN, int R>
+// item -> (problem, 256-row tile index, n-group); consecutive items share the row tile (see lora_gemm.cu)
+struct PairItem { int prob, mt, g; };
+template <int G>
+__device__ __forceinline__ PairItem decode_pair_item(int item, const PairParams& p) {
+  PairItem c;
+  if (G == 1) {
+    c.prob = 0;
+    c.mt = item / p.n_groups;
+    c.g = item % p.n_groups;
+  } else {
+    const int per_m = p.n_probs * p.n_groups;
+    c.mt = item / per_m;
+    const int rem = item - c.mt * per_m;
+    c.prob = rem / p.n_groups;
+    c.g = rem - c.prob * p.n_groups;
+  }
+  return c;
+}
+
+template <int BN, int R, int G>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
-lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                      const __grid_constant__ CUtensorMap tm_la, const __grid_constant__ CUtensorMap tm_lb,
-                      const __grid_constant__ CUtensorMap tm_y, const PairParams p) {
+lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams p) {
   using C = PairCfg<BN, R>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -148,14 +166,16 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   const bool leader = rank == 0;
   const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int nk = (p.K + C::BK - 1) / C::BK;
-  const bool has_bias = p.bias != nullptr;
+  const bool has_bias = p.has_bias != 0;
   const bool has_tail = R > 0 || has_bias;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm_x);
-    prefetch_tmap(&tm_w);
-    prefetch_tmap(&tm_y);
-    if (R > 0) { prefetch_tmap(&tm_la); prefetch_tmap(&tm_lb); }
+    for (int q = 0; q < (G == 1 ? 1 : p.n_probs); ++q) {
+      prefetch_tmap(&gm.x[q]);
+      prefetch_tmap(&gm.w[q]);
+      prefetch_tmap(&gm.y[q]);
+      if (R > 0) { prefetch_tmap(&gm.la[q]); prefetch_tmap(&gm.lb[q]); }
+    }
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 16); }
     mbar_init(t_full, 1);
@@ -191,8 +211,13 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       const uint32_t lb_full_leader = map_to_rank(lb_full, 0);
       uint32_t it = 0, tile_ctr = 0;
       for (int item = pair_id; item < p.n_items; item += n_pairs) {
-        const int m0 = (item / p.n_groups) * 2 * C::BM + (int)rank * C::BM;
-        const int g = item % p.n_groups;
+        const PairItem ic = decode_pair_item<G>(item, p);
+        const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
+        const int g = ic.g;
+        const CUtensorMap* tm_x = &gm.x[ic.prob];
+        const CUtensorMap* tm_w = &gm.w[ic.prob];
+        const CUtensorMap* tm_la = &gm.la[ic.prob];
+        const CUtensorMap* tm_lb = &gm.lb[ic.prob];
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -205,14 +230,14 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             uint8_t* st = smem + s * C::STAGE_BYTES;
             const uint32_t full_leader = map_to_rank(&full[s], 0);
             if (leader) mbar_arrive_expect_tx(&full[s], tx);
-            tma_load_2d_pair(st, &tm_x, kb * C::BK, m0, full_leader);
-            tma_load_2d_pair(st + C::X_BYTES, &tm_w, kb * C::BK, n0, full_leader);
-            if (first) tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES, &tm_la, kb * C::BK, (int)rank * C::HR, full_leader);
+            tma_load_2d_pair(st, tm_x, kb * C::BK, m0, full_leader);
+            tma_load_2d_pair(st + C::X_BYTES, tm_w, kb * C::BK, n0, full_leader);
+            if (first) tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES, tm_la, kb * C::BK, (int)rank * C::HR, full_leader);
           }
           if (R > 0) {
             mbar_wait(lb_empty, (tile_ctr & 1) ^ 1);
             if (leader) mbar_arrive_expect_tx(lb_full, 2u * C::HN * R * 2);
-            tma_load_2d_pair(lb_smem, &tm_lb, 0, n0, lb_full_leader);
+            tma_load_2d_pair(lb_smem, tm_lb, 0, n0, lb_full_leader);
           }
         }
       }
@@ -257,7 +282,7 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       };
 
       for (int item = pair_id; item < p.n_items; item += n_pairs) {
-        const int g = item % p.n_groups;
+        const int g = decode_pair_item<G>(item, p).g;
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -316,8 +341,11 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     uint32_t tile_ctr = 0, first_ctr = 0;
     if (has_tail) {
       for (int item = pair_id; item < p.n_items; item += n_pairs) {
-        const int m0 = (item / p.n_groups) * 2 * C::BM + (int)rank * C::BM;
-        const int g = item % p.n_groups;
+        const PairItem ic = decode_pair_item<G>(item, p);
+        const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
+        const int g = ic.g;
+        const float* bias = gm.bias[ic.prob];
+        __nv_bfloat16* t_out = gm.t_out[ic.prob];
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -326,7 +354,7 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             if (tile_ctr > 0) mbar_wait(lb_empty, (tile_ctr - 1) & 1);
             const int n0 = nt * C::BN + (int)rank * C::HN;
             for (int n = tid; n < C::HN; n += 128) {
-              const float b = (n0 + n < p.N) ? __ldg(p.bias + n0 + n) : 0.f;
+              const float b = (n0 + n < p.N) ? __ldg(bias + n0 + n) : 0.f;
               const float hi = round_bf16(b);
               *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) = make_uint4(pack_bf16x2(hi, b - hi), 0u, 0u, 0u);
             }
@@ -350,8 +378,8 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
             for (int kc = 0; kc < RR / 8; ++kc)
               *reinterpret_cast<uint4*>(trow + kc * 128) = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
-            if (p.t_out != nullptr && g == 0 && m0 + row < p.M) {
-              uint4* dst = reinterpret_cast<uint4*>(p.t_out + (size_t)(m0 + row) * RR);
+            if (t_out != nullptr && g == 0 && m0 + row < p.M) {
+              uint4* dst = reinterpret_cast<uint4*>(t_out + (size_t)(m0 + row) * RR);
 #pragma unroll
               for (int kc = 0; kc < RR / 8; ++kc)
                 dst[kc] = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
@@ -377,8 +405,10 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     uint32_t acc_empty_leader[2] = {map_to_rank(&acc_empty[0], 0), map_to_rank(&acc_empty[1], 0)};
     uint32_t tile_ctr = 0, stores = 0;
     for (int item = pair_id; item < p.n_items; item += n_pairs) {
-      const int m0 = (item / p.n_groups) * 2 * C::BM + (int)rank * C::BM;
-      const int g = item % p.n_groups;
+      const PairItem ic = decode_pair_item<G>(item, p);
+      const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
+      const int g = ic.g;
+      const CUtensorMap* tm_y = &gm.y[ic.prob];
       const int nt0 = g * p.group_size;
       const int nt1 = min(nt0 + p.group_size, p.n_tiles);
       for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -424,7 +454,7 @@ lora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             __syncwarp();
             if (lane == 0) {
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                               reinterpret_cast<uint64_t>(&tm_y)),
+                               reinterpret_cast<uint64_t>(tm_y)),
                            "r"(col0), "r"(m0 + q * 32), "r"(smem_u32(sb))
                            : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -465,64 +495,70 @@ static void choose_groups_pair(int m_tiles, int n_tiles, int BN, int R, int pair
   *n_groups = (n_tiles + best_gs - 1) / best_gs;
 }
 
-template <int BN, int R>
-static int launch_pair(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling,
-                       void* y, void* t_out, int64_t M, int64_t K, int64_t N, cudaStream_t st) {
+template <int BN, int R, int G>
+static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, cudaStream_t st) {
   using C = PairCfg<BN, R>;
   static bool attr_set = false;
   if (!attr_set) {
-    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  CUtensorMap tm_x, tm_w, tm_la, tm_lb, tm_y;
-  int rc = make_tmap_2d_bf16(&tm_x, x, M, K, K * 2, C::BM, C::BK, TMAP_SW_128);
-  if (rc != SDT_OK) return rc;
-  rc = make_tmap_2d_bf16(&tm_w, w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);
-  if (rc != SDT_OK) return rc;
-  rc = make_tmap_2d_bf16(&tm_y, y, M, N, N * 2, 32, 32, TMAP_SW_64);
-  if (rc != SDT_OK) return rc;
-  if (R > 0) {
-    rc = make_tmap_2d_bf16(&tm_la, la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
+  GemmGroup<G> gm;
+  for (int q = 0; q < G; ++q) {
+    const LoraProblem& pr = probs[q < n_probs ? q : 0];
+    int rc = make_tmap_2d_bf16(&gm.x[q], pr.x, M, K, K * 2, C::BM, C::BK, TMAP_SW_128);
     if (rc != SDT_OK) return rc;
-    rc = make_tmap_2d_bf16(&tm_lb, lb, N, R, (uint64_t)R * 2, C::HN, R, R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
+    rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);
     if (rc != SDT_OK) return rc;
-  } else {
-    tm_la = tm_x;
-    tm_lb = tm_x;
+    rc = make_tmap_2d_bf16(&gm.y[q], pr.y, M, N, N * 2, 32, 32, TMAP_SW_64);
+    if (rc != SDT_OK) return rc;
+    if (R > 0) {
+      rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
+      if (rc != SDT_OK) return rc;
+      rc = make_tmap_2d_bf16(&gm.lb[q], pr.lb, N, R, (uint64_t)R * 2, C::HN, R, R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
+      if (rc != SDT_OK) return rc;
+    } else {
+      gm.la[q] = gm.x[q];
+      gm.lb[q] = gm.x[q];
+    }
+    gm.bias[q] = pr.bias;
+    gm.t_out[q] = reinterpret_cast<__nv_bfloat16*>(pr.t_out);
   }
   PairParams p;
-  p.bias = bias;
-  p.t_out = reinterpret_cast<__nv_bfloat16*>(t_out);
   p.scaling = scaling;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.n_probs = n_probs;
+  p.has_bias = probs[0].bias != nullptr ? 1 : 0;
   const int m_tiles = (int)((M + 2 * C::BM - 1) / (2 * C::BM));
   p.n_tiles = (int)((N + BN - 1) / BN);
   const int pairs_max = num_sms() / 2;
-  choose_groups_pair(m_tiles, p.n_tiles, BN, R, pairs_max, &p.group_size, &p.n_groups);
-  p.n_items = m_tiles * p.n_groups;
+  choose_groups_pair(m_tiles * n_probs, p.n_tiles, BN, R, pairs_max, &p.group_size, &p.n_groups);
+  p.n_items = m_tiles * n_probs * p.n_groups;
   const int pairs = p.n_items < pairs_max ? p.n_items : pairs_max;
-  lora_gemm_pair_kernel<BN, R><<<2 * pairs, kPairThreads, C::SMEM_BYTES, st>>>(tm_x, tm_w, tm_la, tm_lb, tm_y, p);
+  lora_gemm_pair_kernel<BN, R, G><<<2 * pairs, kPairThreads, C::SMEM_BYTES, st>>>(gm, p);
   SDT_LAUNCH_OK("lora_gemm_pair");
   return SDT_OK;
 }
 
-// CTA-pair entry; same contract as lora_gemm_bf16 with main == true
-int lora_gemm_pair_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
-                        void* t_out, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st) {
+// CTA-pair entry; same contract as lora_gemm_group_bf16 with main == true (arguments already validated there)
+int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, int r,
+                              cudaStream_t st) {
   const bool bn160 = (N % 160 == 0) || (N % 128 != 0 && N > 128);
-#define SDT_PAIR(BN, R) return launch_pair<BN, R>(x, w, bias, la, lb, scaling, y, t_out, M, K, N, st)
+#define SDT_PAIR(BN, R, G) return launch_pair<BN, R, G>(probs, n_probs, scaling, M, K, N, st)
+#define SDT_PAIR_R(BN, G)                                                                     \
+  switch (r) { case 16: SDT_PAIR(BN, 16, G); case 32: SDT_PAIR(BN, 32, G); default: SDT_PAIR(BN, 64, G); }
   // wide tiles (more FLOP per byte brought into the SM) when the rank accumulators still fit next to two 224-column
   // main accumulators (2*224 + 2*R <= 512), the ragged last tile wastes little and there are enough column tiles to keep
   // every pair busy (measured: N = 640 / 1280 are faster with 160-wide tiles)
   const int64_t n224 = (N + 223) / 224 * 224;
-  if (r <= 32 && N >= 2048 && n224 * 100 <= N * 106 && debug_get(12) == 0) {
-    switch (r) { case 0: SDT_PAIR(224, 0); case 16: SDT_PAIR(224, 16); default: SDT_PAIR(224, 32); }
+  const bool wide = r <= 32 && N >= 2048 && n224 * 100 <= N * 106 && debug_get(12) == 0;
+  if (n_probs == 1) {
+    if (wide) { switch (r) { case 0: SDT_PAIR(224, 0, 1); case 16: SDT_PAIR(224, 16, 1); default: SDT_PAIR(224, 32, 1); } }
+    if (r == 0) { if (bn160) SDT_PAIR(160, 0, 1); else SDT_PAIR(128, 0, 1); }
+    if (bn160) { SDT_PAIR_R(160, 1) } else { SDT_PAIR_R(128, 1) }
   }
-  if (bn160) {
-    switch (r) { case 0: SDT_PAIR(160, 0); case 16: SDT_PAIR(160, 16); case 32: SDT_PAIR(160, 32); default: SDT_PAIR(160, 64); }
-  } else {
-    switch (r) { case 0: SDT_PAIR(128, 0); case 16: SDT_PAIR(128, 16); case 32: SDT_PAIR(128, 32); default: SDT_PAIR(128, 64); }
-  }
+  if (bn160) { SDT_PAIR_R(160, kMaxGroup) } else { SDT_PAIR_R(128, kMaxGroup) }
+#undef SDT_PAIR_R
 #undef SDT_PAIR
 }
 

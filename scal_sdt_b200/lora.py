@@ -24,8 +24,9 @@ from ._lib import PackSite, SdtError
 
 MAX_TC_RANK = 64
 
-# bench.py sets this to a list to time every projection launch with CUDA events on the launching stream:
-# records are (kind, M, K, N, R, [need_dx,] start_event, end_event)
+# bench.py sets this to a list to time every projection launch with CUDA events on the launching stream.  One record per
+# lora_gemm* kernel launch: ("fwd", M, K, N, R, G, start_event, end_event) / ("bwd", M, K, N, R, G, need_dx, start, end),
+# G = number of same-shape projections the launch computes (1 unless grouped)
 PROFILE = None
 
 
@@ -109,7 +110,7 @@ class _LoRAProjection(torch.autograd.Function):
                                                lora_A.data_ptr(), lora_B.data_ptr(), mod.scaling, y.data_ptr(),
                                                t_save.data_ptr(), M, K, N, r, code, st), "sdt_lora_linear_fwd")
         if ev0 is not None:
-            PROFILE.append(("fwd", M, K, N, ops.R, ev0, _ev()))
+            PROFILE.append(("fwd", M, K, N, ops.R, 1, ev0, _ev()))
         ctx.mod = mod
         ctx.code = code
         ctx.need_dx = x2.requires_grad
@@ -119,43 +120,129 @@ class _LoRAProjection(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        lib = _lib.load()
-        mod = ctx.mod
         x2, t_save, lora_A, lora_B = ctx.saved_tensors
-        M, K = x2.shape
-        N = mod.out_features
-        st = _lib.stream_ptr()
-        dy = dy.contiguous()
-        if dy.dtype != x2.dtype:
-            dy = dy.to(x2.dtype)
-        dx = torch.empty_like(x2) if ctx.need_dx else None
-        # gradient destinations: the flat arena when one is attached (no per-site copies), else fresh zeros
-        direct = mod._grad_A is not None
-        if direct:
-            dA, dB = mod._grad_A, mod._grad_B
-        else:
-            dA = torch.zeros(mod.r, K, dtype=torch.float32, device=x2.device)
-            dB = torch.zeros(N, mod.r, dtype=torch.float32, device=x2.device)
-        if ctx.code == _lib.SDT_BF16:
-            ops = mod._packed_operands()
-            wt = mod._weight_t_bf16() if ctx.need_dx else None
-            g_ws = torch.empty(M, ops.R, dtype=torch.bfloat16, device=x2.device)
-            ev0 = _ev() if PROFILE is not None else None
-            _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), _lib.ptr(wt), ops.At_p.data_ptr(),
-                                               ops.Bt_p.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
-                                               g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, ops.R, mod.r,
-                                               ctx.code, st), "sdt_lora_linear_bwd")
-            if ev0 is not None:
-                PROFILE.append(("bwd", M, K, N, ops.R, ctx.need_dx, ev0, _ev()))
-        else:
-            g_ws = torch.empty(M, mod.r, dtype=torch.float32, device=x2.device)
-            _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), mod.weight.data_ptr(), lora_A.data_ptr(),
-                                               lora_B.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
-                                               g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, mod.r, mod.r,
-                                               ctx.code, st), "sdt_lora_linear_bwd")
-        if direct:
-            return dx, None, None, None
+        dx, dA, dB = _site_backward(ctx.mod, ctx.code, x2, t_save, lora_A, lora_B, dy, ctx.need_dx)
         return dx, dA, dB, None
+
+
+def _site_backward(mod, code, x2, t_save, lora_A, lora_B, dy, need_dx):
+    """dX (optional), dA, dB of one site through ``sdt_lora_linear_bwd``.  Returns (dx, dA, dB); dA / dB are None when the
+    kernels accumulated straight into the flat gradient arena."""
+    lib = _lib.load()
+    M, K = x2.shape
+    N = mod.out_features
+    st = _lib.stream_ptr()
+    dy = dy.contiguous()
+    if dy.dtype != x2.dtype:
+        dy = dy.to(x2.dtype)
+    dx = torch.empty_like(x2) if need_dx else None
+    # gradient destinations: the flat arena when one is attached (no per-site copies), else fresh zeros
+    direct = mod._grad_A is not None
+    if direct:
+        dA, dB = mod._grad_A, mod._grad_B
+    else:
+        dA = torch.zeros(mod.r, K, dtype=torch.float32, device=x2.device)
+        dB = torch.zeros(N, mod.r, dtype=torch.float32, device=x2.device)
+    if code == _lib.SDT_BF16:
+        ops = mod._packed_operands()
+        wt = mod._weight_t_bf16() if need_dx else None
+        g_ws = torch.empty(M, ops.R, dtype=torch.bfloat16, device=x2.device)
+        ev0 = _ev() if PROFILE is not None else None
+        _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), _lib.ptr(wt), ops.At_p.data_ptr(),
+                                           ops.Bt_p.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
+                                           g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, ops.R, mod.r,
+                                           code, st), "sdt_lora_linear_bwd")
+        if ev0 is not None:
+            PROFILE.append(("bwd", M, K, N, ops.R, 1, need_dx, ev0, _ev()))
+    else:
+        g_ws = torch.empty(M, mod.r, dtype=torch.float32, device=x2.device)
+        _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), mod.weight.data_ptr(), lora_A.data_ptr(),
+                                           lora_B.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
+                                           g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, mod.r, mod.r,
+                                           code, st), "sdt_lora_linear_bwd")
+    if direct:
+        return dx, None, None
+    return dx, dA, dB
+
+
+class _LoRAProjectionGroup(torch.autograd.Function):
+    """G same-shape projections of ONE input (to_q / to_k / to_v on the normalised hidden states; to_k / to_v of one or two
+    cross-attentions on the text context) as the work items of one ``sdt_lora_linear_fwd_group`` launch."""
+
+    @staticmethod
+    def forward(ctx, x2, mods, *lora_params):
+        lib = _lib.load()
+        M, K = x2.shape
+        N = mods[0].out_features
+        G = len(mods)
+        st = _lib.stream_ptr()
+        ops = [m._packed_operands() for m in mods]
+        R = ops[0].R
+        ys = [torch.empty(M, N, dtype=x2.dtype, device=x2.device) for _ in mods]
+        ts = [torch.empty(M, R, dtype=torch.bfloat16, device=x2.device) for _ in mods]
+        probs = (_lib.LoraProblem * G)(*[
+            _lib.LoraProblem(x2.data_ptr(), m._weight_bf16().data_ptr(), _lib.ptr(m._bias_f32()), o.A_p.data_ptr(),
+                             o.B_p.data_ptr(), y.data_ptr(), t.data_ptr())
+            for m, o, y, t in zip(mods, ops, ys, ts)])
+        ev0 = _ev() if PROFILE is not None else None
+        _lib.check(lib.sdt_lora_linear_fwd_group(ctypes.addressof(probs), G, mods[0].scaling, M, K, N, R, _lib.SDT_BF16, st),
+                   "sdt_lora_linear_fwd_group")
+        if ev0 is not None:
+            PROFILE.append(("fwd", M, K, N, R, G, ev0, _ev()))
+        ctx.mods = mods
+        ctx.need_dx = x2.requires_grad
+        ctx.save_for_backward(x2, *ts, *lora_params)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        mods = ctx.mods
+        G = len(mods)
+        saved = ctx.saved_tensors
+        x2, ts, lora_params = saved[0], saved[1:1 + G], saved[1 + G:]
+        dx = None
+        grads = []
+        for g, (m, dy) in enumerate(zip(mods, dys)):
+            if dy is None:                    # this output was not used downstream
+                grads += [None, None]
+                continue
+            dx_g, dA, dB = _site_backward(m, _lib.SDT_BF16, x2, ts[g], lora_params[2 * g], lora_params[2 * g + 1], dy, ctx.need_dx)
+            grads += [dA, dB]
+            if dx_g is not None:
+                dx = dx_g if dx is None else dx.add_(dx_g)
+        return (dx, None, *grads)
+
+
+def groupable(mods, x2: torch.Tensor) -> bool:
+    """True when ``mods`` can share one grouped launch on ``x2`` [M,K]: LoRA sites of one shape, rank, scaling and bias-ness,
+    bf16 tensor-core path.  Anything else goes through the per-site launches (same kernels, one problem each)."""
+    if not (2 <= len(mods) <= _lib.MAX_GROUP) or not all(isinstance(m, LoRALinear) for m in mods):
+        return False
+    m0 = mods[0]
+    if not x2.is_cuda or x2.shape[0] == 0:
+        return False
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x2.dtype
+    if dt != torch.bfloat16:
+        return False
+    return all(m.in_features == m0.in_features and m.out_features == m0.out_features and m.r == m0.r
+               and m.scaling == m0.scaling and (m.bias is None) == (m0.bias is None) and m.lora_dropout_p == 0.0
+               for m in mods)
+
+
+def project_group(mods, x: torch.Tensor):
+    """``[m(x) for m in mods]`` -- one launch when the sites are ``groupable``."""
+    mods = list(mods)
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if not groupable(mods, x2):
+        return [m(x) for m in mods]
+    _lib.require_cuda(x2, *(m.weight for m in mods))
+    _lib.device_check()
+    if x2.dtype != torch.bfloat16:
+        x2 = x2.to(torch.bfloat16)
+    params = [p for m in mods for p in (m.lora_A, m.lora_B)]
+    ys = _LoRAProjectionGroup.apply(x2.contiguous(), mods, *params)
+    return [y.view(*lead, m.out_features) for y, m in zip(ys, mods)]
 
 
 class _LoRABase(nn.Module):

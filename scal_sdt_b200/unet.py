@@ -20,6 +20,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .fused import group_norm_act
+from .lora import project_group
 
 
 @dataclass
@@ -95,13 +96,27 @@ class CrossAttention(nn.Module):
         self.to_k = nn.Linear(context_dim or dim, dim, bias=False)
         self.to_v = nn.Linear(context_dim or dim, dim, bias=False)
         self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+        self._kv_pre = None          # (k, v) of the text context when UNet.forward projected it ahead of the blocks
 
     def forward(self, x, context=None):
-        ctx = x if context is None else context
         b, n, c = x.shape
-        q = self.to_q(x).view(b, n, self.heads, c // self.heads).transpose(1, 2)
-        k = self.to_k(ctx).view(b, ctx.shape[1], self.heads, c // self.heads).transpose(1, 2)
-        v = self.to_v(ctx).view(b, ctx.shape[1], self.heads, c // self.heads).transpose(1, 2)
+        # same-shape projections of one input go out as ONE grouped launch when they are LoRA sites (fused
+        # q/k/v); plain nn.Linear modules (CPU oracle arm, un-targeted sites) are simply called one by one
+        if context is None:
+            q, k, v = project_group([self.to_q, self.to_k, self.to_v], x)
+            n_kv = n
+        else:
+            q = self.to_q(x)
+            kv = self._kv_pre
+            if kv is not None:                      # projected up front together with other blocks' (UNet.forward)
+                self._kv_pre = None
+                k, v = kv
+            else:
+                k, v = project_group([self.to_k, self.to_v], context)
+            n_kv = context.shape[1]
+        q = q.view(b, n, self.heads, c // self.heads).transpose(1, 2)
+        k = k.view(b, n_kv, self.heads, c // self.heads).transpose(1, 2)
+        v = v.view(b, n_kv, self.heads, c // self.heads).transpose(1, 2)
         o = F.scaled_dot_product_attention(q, k, v)
         o = o.transpose(1, 2).reshape(b, n, c)
         return self.to_out[1](self.to_out[0](o))
@@ -299,11 +314,34 @@ class UNet2DConditionModel(nn.Module):
     def dtype(self):
         return self.conv_in.weight.dtype
 
+    def _project_context(self, ctx) -> None:
+        """The text context is the input of EVERY cross-attention's to_k / to_v, so those projections do not have to wait
+        for their block: sites of equal width are projected up front, ``MAX_GROUP`` per launch (two blocks' k and v), and
+        each attention picks its pair up when it runs.  Only LoRA sites on CUDA take part (``project_group`` decides)."""
+        from . import _lib
+        from .lora import LoRALinear
+        if not ctx.is_cuda:
+            return
+        by_width: dict[int, list] = {}
+        for m in self.modules():
+            if isinstance(m, BasicTransformerBlock):
+                a = m.attn2
+                if isinstance(a.to_k, LoRALinear) and isinstance(a.to_v, LoRALinear):
+                    by_width.setdefault(a.to_k.out_features, []).append(a)
+        per = _lib.MAX_GROUP // 2
+        for attns in by_width.values():
+            for i in range(0, len(attns), per):
+                chunk = attns[i:i + per]
+                outs = project_group([p for a in chunk for p in (a.to_k, a.to_v)], ctx)
+                for j, a in enumerate(chunk):
+                    a._kv_pre = (outs[2 * j], outs[2 * j + 1])
+
     def forward(self, sample, timesteps, encoder_hidden_states):
         """Returns an object with ``.sample`` like diffusers (``modules/model.py:304``)."""
         dt = self.dtype
         temb = self.time_embedding(timestep_embedding(timesteps, self.config.block_out_channels[0]).to(dt))
         ctx = encoder_hidden_states.to(dt)
+        self._project_context(ctx)
         fmt = torch.channels_last if self.channels_last else torch.contiguous_format
         x = self.conv_in(sample.to(dt).contiguous(memory_format=fmt))
         skips = [x]

@@ -179,3 +179,55 @@ def test_largest_bucket_token_count_linearity(sdt_lib):
     rows = torch.randint(0, M, (257,), generator=torch.Generator().manual_seed(2))
     yr = ref(x1[rows.to(DEV)].cpu().double())
     assert rel(y1[rows.to(DEV)], yr) <= 2e-2
+
+
+GROUP_CASES = [
+    # x shape, cin, cout, rank, alpha, bias, number of projections
+    ((2, 256, 320), 320, 320, 16, 1, False, 3),     # attn1 q/k/v, level 0 width -> single-CTA kernel (K < 512)
+    ((2, 300, 640), 640, 640, 16, 8, False, 3),     # q/k/v, ragged M -> CTA-pair kernel (K >= 512)
+    ((2, 77, 768), 768, 320, 4, 1, False, 4),       # k/v of two cross-attentions on one text context (M = 154 < 256)
+    ((8, 77, 768), 768, 1280, 64, 64, True, 2),     # k/v, rank 64, with bias, M = 616 -> pair kernel
+    ((1, 130, 1024), 1024, 640, 32, 16, False, 3),  # SD2.x context width, BN = 128 tiles
+]
+
+
+@pytest.mark.parametrize("case", GROUP_CASES, ids=[f"{c[1]}x{c[2]}-r{c[3]}-g{c[6]}" for c in GROUP_CASES])
+def test_grouped_projection_matches_oracle_and_single_launches(sdt_lib, case):
+    """``project_group`` (one launch for G same-shape sites on a shared input) against the oracle, and bit-for-bit against
+    the per-site launches it replaces; gradients flow to the shared input and to every site's lora_A / lora_B."""
+    from scal_sdt_b200.lora import groupable, project_group
+    xshape, cin, cout, rank, alpha, bias, G = case
+    pairs = [make_pair("linear", cin, cout, rank, alpha, bias, 100 + g, torch.bfloat16) for g in range(G)]
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(*xshape, generator=gen).bfloat16().float()
+    dys = [torch.randn(*xshape[:-1], cout, generator=gen).bfloat16().float() for _ in range(G)]
+    # oracle
+    xr = x.double().requires_grad_(True)
+    yrs = [ref(xr) for ref, _ in pairs]
+    torch.autograd.backward(yrs, [d.double() for d in dys])
+    # grouped launch
+    mods = [ours for _, ours in pairs]
+    xo = x.to(DEV).bfloat16().requires_grad_(True)
+    assert groupable(mods, xo.reshape(-1, cin))
+    yos = project_group(mods, xo)
+    torch.autograd.backward(yos, [d.to(DEV).bfloat16() for d in dys])
+    for g in range(G):
+        assert rel(yos[g], yrs[g]) <= 2e-2, ("y", g, rel(yos[g], yrs[g]))
+        assert rel(mods[g].lora_A.grad, pairs[g][0].lora_A.grad) <= 2e-2, ("dA", g)
+        assert rel(mods[g].lora_B.grad, pairs[g][0].lora_B.grad) <= 2e-2, ("dB", g)
+    assert rel(xo.grad, xr.grad) <= 2e-2, ("dx", rel(xo.grad, xr.grad))
+    # the same sites one launch each: identical tiles, identical arithmetic order
+    xs = x.to(DEV).bfloat16()
+    for g in range(G):
+        assert torch.equal(mods[g](xs), yos[g]), f"grouped launch differs from the single launch (site {g})"
+
+
+def test_group_falls_back_to_per_site_launches_on_mixed_shapes(sdt_lib):
+    from scal_sdt_b200 import get_lora
+    from scal_sdt_b200.lora import groupable, project_group
+    a = get_lora(nn.Linear(320, 320, bias=False).to(DEV).bfloat16(), 16, 1)
+    b = get_lora(nn.Linear(320, 640, bias=False).to(DEV).bfloat16(), 16, 1)
+    x = torch.randn(4, 64, 320, device=DEV, dtype=torch.bfloat16)
+    assert not groupable([a, b], x.reshape(-1, 320))
+    ya, yb = project_group([a, b], x)
+    assert torch.equal(ya, a(x)) and torch.equal(yb, b(x))
