@@ -179,6 +179,18 @@ int sdt_group_norm_nhwc(const void* x, const float* gamma, const float* beta, fl
 int sdt_group_norm_nhwc_bwd(const void* x, const void* dout, const float* gamma, const float* beta, const float* stats,
                             float* bstats, void* dx, int64_t B, int64_t HW, int C, int G, float eps, int silu, void* stream);
 
+/* ---- f2: LayerNorm over C of token-major bf16 activations [M, C], frozen affine (gamma, beta f32[C]), fused residual add ----
+ * diffusers BasicTransformerBlock (the UNet loaded at modules/model.py:82-91): x = x + attn(...); h = norm(x).
+ * forward : res != NULL: xs_out = bf16(x + res) (the new residual stream) and y = LN(xs_out); res == NULL: y = LN(x).
+ *           stats f32[M,2] = (mean, rstd) per row.
+ * backward: dx = LN'(dy) (+ dres, the gradient arriving on the residual stream); xs = the tensor that was normalised.
+ * One warp per row, row resident in registers, 128-bit accesses; C % 8 == 0, C <= 2048.
+ */
+int sdt_layer_norm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* xs_out, void* y,
+                       float* stats, int64_t M, int C, float eps, void* stream);
+int sdt_layer_norm_bwd(const void* xs, const void* dy, const void* dres, const float* gamma, const float* stats, void* dx,
+                       int64_t M, int C, void* stream);
+
 /* ---- K6: data-parallel LoRA-gradient exchange (replaces Lightning DDP, train.py:98-109) -------
  * One NCCL communicator per process (libnccl is resolved at run time with dlopen, so the library
  * loads on machines without NCCL).  sdt_allreduce averages `count` elements in place.

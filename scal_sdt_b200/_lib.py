@@ -64,6 +64,9 @@ SIGNATURES = {
                                     c_int, c_void_p]),
     "sdt_group_norm_nhwc_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                         c_int, c_int, c_float, c_int, c_void_p]),
+    "sdt_layer_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
+                                   c_void_p]),
+    "sdt_layer_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "sdt_comm_unique_id": (c_int, [c_void_p]),
     "sdt_comm_init": (c_int, [c_void_p, c_int, c_int]),
     "sdt_comm_world": (c_int, []),

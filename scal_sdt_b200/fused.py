@@ -89,3 +89,80 @@ def group_norm_act(norm: torch.nn.GroupNorm, x: torch.Tensor, silu: bool) -> tor
         return _GroupNormNHWC.apply(x, cache[1], cache[2], norm.num_groups, float(norm.eps), bool(silu))
     y = norm(x)
     return torch.nn.functional.silu(y) if silu else y
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """``xs = x + res; y = layer_norm(xs)`` (res optional) with frozen affine parameters, one launch per direction."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps):
+        C = x.shape[-1]
+        x2 = x.reshape(-1, C).contiguous()
+        M = x2.shape[0]
+        y = torch.empty_like(x2)
+        stats = torch.empty(M, 2, dtype=torch.float32, device=x.device)
+        if res is not None:
+            r2 = res.reshape(-1, C).contiguous()
+            xs = torch.empty_like(x2)
+        else:
+            r2, xs = None, None
+        _lib.check(_lib.load().sdt_layer_norm_fwd(x2.data_ptr(), _lib.ptr(r2), gamma.data_ptr(), beta.data_ptr(), _lib.ptr(xs),
+                                                  y.data_ptr(), stats.data_ptr(), M, C, eps, _lib.stream_ptr()), "sdt_layer_norm_fwd")
+        ctx.save_for_backward(xs if res is not None else x2, gamma, stats)
+        ctx.has_res = res is not None
+        ctx.shape = x.shape
+        if res is not None:
+            return xs.view(x.shape), y.view(x.shape)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        xs, gamma, stats = ctx.saved_tensors
+        M, C = xs.shape
+        if ctx.has_res:
+            dxs, dy = grads
+        else:
+            dxs, dy = None, grads[0]
+        if dy is None:                               # only the residual stream was used downstream
+            return dxs, (dxs if ctx.has_res else None), None, None, None
+        dy2 = dy.reshape(M, C).contiguous()
+        if dy2.dtype != xs.dtype:
+            dy2 = dy2.to(xs.dtype)
+        d2 = None
+        if dxs is not None:
+            d2 = dxs.reshape(M, C).contiguous()
+            if d2.dtype != xs.dtype:
+                d2 = d2.to(xs.dtype)
+        dx = torch.empty_like(xs)
+        _lib.check(_lib.load().sdt_layer_norm_bwd(xs.data_ptr(), dy2.data_ptr(), _lib.ptr(d2), gamma.data_ptr(), stats.data_ptr(),
+                                                  dx.data_ptr(), M, C, _lib.stream_ptr()), "sdt_layer_norm_bwd")
+        dx = dx.view(ctx.shape)
+        return dx, (dx if ctx.has_res else None), None, None, None
+
+
+def layer_norm_supported(norm: torch.nn.LayerNorm, x: torch.Tensor) -> bool:
+    c = x.shape[-1]
+    return (x.is_cuda and x.dtype == torch.bfloat16 and len(norm.normalized_shape) == 1 and norm.normalized_shape[0] == c
+            and norm.weight is not None and norm.bias is not None and not norm.weight.requires_grad
+            and not norm.bias.requires_grad and c % 8 == 0 and c <= 2048 and x.numel() > 0)
+
+
+def _ln_affine(norm):
+    cache = getattr(norm, "_sdt_affine_f32", None)
+    key = (norm.weight.data_ptr(), norm.weight._version, norm.bias._version)
+    if cache is None or cache[0] != key:
+        cache = (key, norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous())
+        norm._sdt_affine_f32 = cache
+    return cache[1], cache[2]
+
+
+def add_layer_norm(norm: torch.nn.LayerNorm, x: torch.Tensor, res: torch.Tensor | None = None):
+    """``res is None``: ``norm(x)``.  Otherwise ``(x + res, norm(x + res))`` -- the residual add and the LayerNorm that follows
+    it in the transformer block as one pass (torch otherwise: host-model code for trainable norms / CPU / fp32)."""
+    if layer_norm_supported(norm, x) and (res is None or (res.shape == x.shape and res.dtype == x.dtype and res.is_cuda)):
+        g, b = _ln_affine(norm)
+        return _AddLayerNorm.apply(x, res, g, b, float(norm.eps))
+    if res is None:
+        return norm(x)
+    xs = x + res
+    return xs, norm(xs)

@@ -19,7 +19,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .fused import group_norm_act
+from .fused import add_layer_norm, group_norm_act
 from .lora import project_group
 
 
@@ -158,9 +158,10 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x, context):
-        x = x + self.attn1(self.norm1(x))
-        x = x + self.attn2(self.norm2(x), context)
-        return x + self.ff(self.norm3(x))
+        # residual add + the LayerNorm that follows it are one pass
+        x, h = add_layer_norm(self.norm2, x, self.attn1(add_layer_norm(self.norm1, x)))
+        x, h = add_layer_norm(self.norm3, x, self.attn2(h, context))
+        return x + self.ff(h)
 
 
 class Transformer2DModel(nn.Module):

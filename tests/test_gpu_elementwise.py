@@ -201,7 +201,8 @@ def test_geglu_forward_backward(sdt_lib, dtype, tol):
 
 
 @pytest.mark.parametrize("C,G,H,W,silu", [(320, 32, 16, 16, True), (960, 32, 8, 12, True), (640, 32, 7, 5, False),
-                                          (2560, 32, 4, 4, True), (1280, 32, 16, 16, False)])
+                                          (2560, 32, 4, 4, True), (1280, 32, 16, 16, False), (320, 32, 64, 64, True),
+                                          (1920, 32, 32, 32, True), (64, 8, 3, 3, False)])
 def test_group_norm_nhwc_forward_backward(sdt_lib, C, G, H, W, silu):
     from scal_sdt_b200.fused import group_norm_act, group_norm_nhwc_supported
     torch.manual_seed(C + H)
