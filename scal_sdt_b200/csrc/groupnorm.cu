@@ -25,16 +25,31 @@ struct GnShape {
   int rows_per_cta;
 };
 
-// sigmoid(z) = 0.5 tanh(z/2) + 0.5 with the hardware tanh: ONE special-function op per element instead of ex2 + a full-precision
-// division (these kernels were bound by the special-function / issue rate, not by memory); |error| < 2^-11, below bf16 resolution
-__device__ __forceinline__ float sigmoidf_(float z) {
+// SiLU through the hardware tanh: with h = z/2 and t = tanh(h),  sigmoid(z) = (1 + t)/2,
+//     silu(z)  = z sigmoid(z)                 = h + h t                          (FFMA)
+//     silu'(z) = sigmoid (1 + z (1 - sigmoid)) = (1 + t)(1 + h - h t) / 2
+// ONE special-function op per element instead of ex2 + a full-precision division (ncu: these kernels were bound by the
+// special-function / issue rate, not by memory); |error| < 2^-11, below bf16 resolution.  The SiLU variants therefore keep
+// HALVED affine rows in the table (h comes straight out of one FFMA) and fold the factor 2 back where A multiplies dz.
+__device__ __forceinline__ float tanh_approx(float h) {
   float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
-  return fmaf(0.5f, t, 0.5f);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return t;
 }
-__device__ __forceinline__ float bf16_elem(const uint4& u, int j) {
-  const uint32_t w = (&u.x)[j >> 1];
-  return (j & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
+// 2 * silu'(2h)
+__device__ __forceinline__ float silu_grad_x2(float h) {
+  const float t = tanh_approx(h);
+  return (1.0f + t) * (fmaf(-h, t, h) + 1.0f);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
 // per-channel table rows (each a float[C] in dynamic shared memory)
@@ -43,12 +58,14 @@ enum { T_A = 0, T_BC = 1, T_SC = 2, T_SH = 3, T_D = 2, T_E = 3 };
 // Per-(sample, channel) table in shared memory.  The loads of TU channels per thread are all issued before the first use:
 // one global-memory latency per CTA instead of C / blockDim of them (C = 2560 with 160 threads was 16 dependent rounds).
 //   kStatsBwd: rows A, Bc, Sc, Sh (backward statistics pass)        kApplyBwd: rows A, Bc, D, E        neither: A, Bc
-template <bool kStatsBwd, bool kApplyBwd>
+//   kHalf (SiLU variants): A and Bc are stored halved
+template <bool kStatsBwd, bool kApplyBwd, bool kHalf>
 __device__ __forceinline__ void build_table(float* tab, const float* __restrict__ gamma, const float* __restrict__ beta,
                                             const float* __restrict__ fstats, const float* __restrict__ bstats, int b,
                                             const GnShape& s, float eps) {
   constexpr int TU = 8;
   const float inv_n = 1.0f / ((float)s.HW * (float)s.cpg);
+  const float ab = kHalf ? 0.5f : 1.0f;
   for (int cb = threadIdx.x; cb < s.C; cb += TU * blockDim.x) {
     float gm[TU], bt[TU], f0[TU], f1[TU], b0[TU], b1[TU];
 #pragma unroll
@@ -70,8 +87,8 @@ __device__ __forceinline__ void build_table(float* tab, const float* __restrict_
         const float mean = f0[t] * inv_n;
         const float var = fmaxf(f1[t] * inv_n - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
-        tab[T_A * s.C + c] = rstd * gm[t];
-        tab[T_BC * s.C + c] = bt[t] - mean * rstd * gm[t];
+        tab[T_A * s.C + c] = ab * rstd * gm[t];
+        tab[T_BC * s.C + c] = ab * (bt[t] - mean * rstd * gm[t]);
         if (kStatsBwd) {
           tab[T_SC * s.C + c] = rstd;
           tab[T_SH * s.C + c] = -mean * rstd;
@@ -88,7 +105,7 @@ __device__ __forceinline__ void build_table(float* tab, const float* __restrict_
   }
 }
 
-// ---- statistics: stats[b][g] = (sum x, sum x^2)   or, for the backward, (sum dzg, sum dzg * xhat) ---------------
+// ---- statistics: stats[b][g] = (sum x, sum x^2)   or, for the backward, (sum dz A, sum dz A xhat) = rstd (sum dzg, sum dzg xhat)
 template <bool BWD, bool SILU>
 __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dout, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ fstats, float* __restrict__ out_stats,
@@ -97,65 +114,72 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* 
   __shared__ float acc[2 * 128];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) acc[i] = 0.f;
-  if (BWD) build_table<true, false>(tab, gamma, beta, fstats, nullptr, b, s, eps);
+  if (BWD) build_table<true, false, SILU>(tab, gamma, beta, fstats, nullptr, b, s, eps);
   __syncthreads();
   const int v = threadIdx.x % s.vecs, rp = threadIdx.x / s.vecs;
   const int c0 = v * 8;
-  const int g0 = c0 / s.cpg, g1 = (c0 + 7) / s.cpg;
-  float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
-  // elements j >= js of this thread's 8-channel vector belong to the next group (cpg >= 8: at most two groups per vector)
-  const int js = min(8, (g0 + 1) * s.cpg - c0);
   if (rp < s.rows_par) {
     float tA[8], tB[8], tS[8], tH[8];
     if (BWD) {
+      load8(tab + T_A * s.C + c0, tA);
+      load8(tab + T_BC * s.C + c0, tB);
+      load8(tab + T_SC * s.C + c0, tS);
+      load8(tab + T_SH * s.C + c0, tH);
+    }
+    // one accumulator pair per element position: the streaming loop is pure FMAs, the split into groups happens once at the end
+    float S[8], Q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { S[j] = 0.f; Q[j] = 0.f; }
+    const int r_begin = blockIdx.x * s.rows_per_cta;
+    const int n_rows = min(s.rows_per_cta, (int)(s.HW - r_begin));
+    // this thread's rows are rp, rp + rows_par, ...: consecutive ones are rstep vectors apart in the slab
+    const size_t base = ((size_t)b * s.HW + r_begin + rp) * s.vecs + v;
+    const uint4* xb = reinterpret_cast<const uint4*>(x) + base;
+    const uint4* db = BWD ? reinterpret_cast<const uint4*>(dout) + base : nullptr;
+    const int rstep = s.rows_par * s.vecs;
+    const int nk = rp < n_rows ? (n_rows - rp + s.rows_par - 1) / s.rows_par : 0;
+    auto accumulate = [&](const uint4& xu, const uint4& du) {
+      float xe[8], de[8];
+      unpack8(xu, xe);
+      if (BWD) unpack8(du, de);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        tA[j] = tab[T_A * s.C + c0 + j]; tB[j] = tab[T_BC * s.C + c0 + j];
-        tS[j] = tab[T_SC * s.C + c0 + j]; tH[j] = tab[T_SH * s.C + c0 + j];
+        if (!BWD) {
+          S[j] += xe[j];
+          Q[j] = fmaf(xe[j], xe[j], Q[j]);
+        } else {
+          float dz = de[j];
+          if (SILU) dz *= silu_grad_x2(fmaf(xe[j], tA[j], tB[j]));      // 2 dz, against the halved A
+          const float p = dz * tA[j];
+          S[j] += p;
+          Q[j] = fmaf(p, fmaf(xe[j], tS[j], tH[j]), Q[j]);
+        }
       }
-    }
-    const int64_t r_begin = (int64_t)blockIdx.x * s.rows_per_cta;
-    const int64_t r_end = min(r_begin + (int64_t)s.rows_per_cta, s.HW);
-    const uint4* xb = reinterpret_cast<const uint4*>(x) + ((size_t)b * s.HW) * s.vecs + v;
-    const uint4* db = BWD ? reinterpret_cast<const uint4*>(dout) + ((size_t)b * s.HW) * s.vecs + v : nullptr;
+    };
     constexpr int U = 4;                      // independent 16-byte loads in flight per thread (x2 in the backward)
-    for (int64_t r = r_begin + rp; r < r_end; r += (int64_t)U * s.rows_par) {
+    int k = 0;
+    for (; k + U <= nk; k += U) {
       uint4 xvv[U], dvv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t ru = r + (int64_t)u * s.rows_par;
-        xvv[u] = make_uint4(0, 0, 0, 0);
-        dvv[u] = make_uint4(0, 0, 0, 0);
-        if (ru < r_end) {
-          xvv[u] = ld_stream(xb + ru * s.vecs);
-          if (BWD) dvv[u] = ld_stream(db + ru * s.vecs);
-        }
+        xvv[u] = ld_stream(xb + (k + u) * rstep);
+        if (BWD) dvv[u] = ld_stream(db + (k + u) * rstep);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (r + (int64_t)u * s.rows_par >= r_end) break;
+      for (int u = 0; u < U; ++u) accumulate(xvv[u], BWD ? dvv[u] : xvv[u]);
+    }
+    for (; k < nk; ++k) {
+      const uint4 xu = ld_stream(xb + k * rstep);
+      const uint4 du = BWD ? ld_stream(db + k * rstep) : xu;
+      accumulate(xu, du);
+    }
+    // elements j >= js of this thread's 8-channel vector belong to the next group (cpg >= 8: at most two groups per vector)
+    const int g0 = c0 / s.cpg, g1 = (c0 + 7) / s.cpg;
+    const int js = min(8, (g0 + 1) * s.cpg - c0);
+    float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xe = bf16_elem(xvv[u], j);
-          float p, pq;
-          if (!BWD) {
-            p = xe;
-            pq = xe * xe;
-          } else {
-            const float de = bf16_elem(dvv[u], j);
-            float dz = de;
-            if (SILU) {
-              const float z = fmaf(xe, tA[j], tB[j]);
-              const float sg = sigmoidf_(z);
-              dz = de * sg * (1.0f + z * (1.0f - sg));
-            }
-            // dzg = dz * gamma = dz * A / rstd; accumulate dz*A and dz*A*xhat, the 1/rstd goes into the apply pass' table
-            p = dz * tA[j];
-            pq = p * fmaf(xe, tS[j], tH[j]);
-          }
-          if (j >= js) { a1 += p; q1 += pq; } else { a0 += p; q0 += pq; }
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      if (j < js) { a0 += S[j]; q0 += Q[j]; } else { a1 += S[j]; q1 += Q[j]; }
     }
     atomicAdd(&acc[2 * g0], a0);
     atomicAdd(&acc[2 * g0 + 1], q0);
@@ -171,75 +195,69 @@ template <bool BWD, bool SILU>
 __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dout, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ fstats, const float* __restrict__ bstats,
                                 uint16_t* __restrict__ out, GnShape s, float eps) {
-  extern __shared__ float tab[];                 // forward [2][C] (A, Bc); backward [4][C] (A, Bc, D, E)
+  extern __shared__ float tab[];                 // forward [2][C] (A, Bc); backward [4][C] (A, Bc, D, E); A, Bc halved for SiLU
   const int b = blockIdx.y;
-  build_table<false, BWD>(tab, gamma, beta, fstats, bstats, b, s, eps);
+  build_table<false, BWD, SILU>(tab, gamma, beta, fstats, bstats, b, s, eps);
   __syncthreads();
-  const int64_t r_begin = (int64_t)blockIdx.x * s.rows_per_cta;
-  const int64_t r_end = min(r_begin + (int64_t)s.rows_per_cta, s.HW);
-  const int64_t n_vec = (r_end - r_begin) * s.vecs;          // this CTA's contiguous slab of 16-byte vectors
+  const int r_begin = blockIdx.x * s.rows_per_cta;
+  const int n_rows = min(s.rows_per_cta, (int)(s.HW - r_begin));
+  const int n_vec = n_rows * s.vecs;                         // this CTA's contiguous slab of 16-byte vectors
   const size_t base = ((size_t)b * s.HW + r_begin) * s.vecs;
   const uint4* xb = reinterpret_cast<const uint4*>(x) + base;
   const uint4* db = BWD ? reinterpret_cast<const uint4*>(dout) + base : nullptr;
   uint4* ob = reinterpret_cast<uint4*>(out) + base;
+  auto process = [&](int i, int vv, const uint4& xu, const uint4& du) {
+    const int c0 = vv * 8;
+    float A[8], Bc[8], xe[8], o[8];
+    load8(tab + T_A * s.C + c0, A);
+    load8(tab + T_BC * s.C + c0, Bc);
+    unpack8(xu, xe);
+    if (!BWD) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float h = fmaf(xe[j], A[j], Bc[j]);              // SiLU: z / 2, otherwise z
+        o[j] = SILU ? fmaf(h, tanh_approx(h), h) : h;
+      }
+    } else {
+      float D[8], E[8], de[8];
+      load8(tab + T_D * s.C + c0, D);
+      load8(tab + T_E * s.C + c0, E);
+      unpack8(du, de);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dz = de[j];
+        if (SILU) dz *= silu_grad_x2(fmaf(xe[j], A[j], Bc[j]));
+        o[j] = fmaf(A[j], dz, -fmaf(E[j], xe[j], D[j]));
+      }
+    }
+    st_stream(ob + i, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+  };
   constexpr int U = 4;
   const int step = blockDim.x;
   // channel vector of slab element i is i % vecs: advanced incrementally (no division in the loop)
   const int dv = step % s.vecs;
   int v = threadIdx.x % s.vecs;
-  for (int64_t i = threadIdx.x; i < n_vec; i += (int64_t)U * step) {
+  int i = threadIdx.x;
+  for (; i + (U - 1) * step < n_vec; i += U * step) {
     uint4 xvv[U], dvv[U];
     int vv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t iu = i + (int64_t)u * step;
       vv[u] = v;
       v += dv;
       if (v >= s.vecs) v -= s.vecs;
-      xvv[u] = make_uint4(0, 0, 0, 0);
-      dvv[u] = make_uint4(0, 0, 0, 0);
-      if (iu < n_vec) {
-        xvv[u] = ld_stream(xb + iu);
-        if (BWD) dvv[u] = ld_stream(db + iu);
-      }
+      xvv[u] = ld_stream(xb + i + u * step);
+      if (BWD) dvv[u] = ld_stream(db + i + u * step);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t iu = i + (int64_t)u * step;
-      if (iu >= n_vec) break;
-      const int c0 = vv[u] * 8;
-      const float4* ta = reinterpret_cast<const float4*>(tab + T_A * s.C + c0);
-      const float4* tb = reinterpret_cast<const float4*>(tab + T_BC * s.C + c0);
-      const float4 a0 = ta[0], a1 = ta[1], b0 = tb[0], b1 = tb[1];
-      const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float Bc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
-      if (!BWD) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(bf16_elem(xvv[u], j), A[j], Bc[j]);
-          o[j] = SILU ? z * sigmoidf_(z) : z;
-        }
-      } else {
-        const float4* td = reinterpret_cast<const float4*>(tab + T_D * s.C + c0);
-        const float4* te = reinterpret_cast<const float4*>(tab + T_E * s.C + c0);
-        const float4 d0 = td[0], d1 = td[1], e0 = te[0], e1 = te[1];
-        const float D[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const float E[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xe = bf16_elem(xvv[u], j);
-          float dz = bf16_elem(dvv[u], j);
-          if (SILU) {
-            const float z = fmaf(xe, A[j], Bc[j]);
-            const float sg = sigmoidf_(z);
-            dz = dz * sg * (1.0f + z * (1.0f - sg));
-          }
-          o[j] = fmaf(A[j], dz, -fmaf(E[j], xe, D[j]));
-        }
-      }
-      st_stream(ob + iu, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
-    }
+    for (int u = 0; u < U; ++u) process(i + u * step, vv[u], xvv[u], BWD ? dvv[u] : xvv[u]);
+  }
+  for (; i < n_vec; i += step) {
+    const uint4 xu = ld_stream(xb + i);
+    const uint4 du = BWD ? ld_stream(db + i) : xu;
+    process(i, v, xu, du);
+    v += dv;
+    if (v >= s.vecs) v -= s.vecs;
   }
 }
 

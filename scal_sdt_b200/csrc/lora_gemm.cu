@@ -54,8 +54,8 @@ struct LoraGemmCfg {
   static constexpr int T_SBO = (KEXT / 8) * 128;           // bytes between 8-row groups of the A operand
   static constexpr int T_BYTES = (BM / 8) * T_SBO;
   static constexpr int BIAS_BYTES = ((BN * 32 + 1023) / 1024) * 1024;    // [BN,16] bf16, un-swizzled cores
-  static constexpr int STG_BYTES = 8 * 2 * 2048;           // 8 epilogue warps x 2 buffers x [32 rows x 64 B]
   static constexpr int BAR_BYTES = 256;
+  static constexpr int STG_BYTES = 8 * 4096;               // 8 epilogue warps x [32 rows x 128 B] transpose buffers
   static constexpr int FIXED_BYTES = 1024 /*align slack*/ + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
   static constexpr int RING_BYTES = ((232448 - FIXED_BYTES) / 1024) * 1024;   // everything else feeds the TMA ring
   static constexpr int kStages = RING_BYTES / STAGE_BYTES > 6 ? 6 : RING_BYTES / STAGE_BYTES;
@@ -143,7 +143,7 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
   if (warp == 0 && lane == 0) {
     for (int q = 0; q < (G == 1 ? 1 : p.n_probs); ++q) {
       prefetch_tmap(&gm.x[q]);
-      if (has_main) { prefetch_tmap(&gm.w[q]); prefetch_tmap(&gm.y[q]); }
+      if (has_main) prefetch_tmap(&gm.w[q]);
       if (R > 0) { prefetch_tmap(&gm.la[q]); if (has_main) prefetch_tmap(&gm.lb[q]); }
     }
     for (int s = 0; s < C::kMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -276,6 +276,11 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
         const uint32_t d_main = tmem_base + buf * C::ACC1_COL;
         const uint32_t d_tacc = d_main + C::T_COL;           // rank columns of the same buffer
         if (has_main) {
+          // The accumulator buffer may still be with the epilogue.  A pending tail must not wait for that as well: its
+          // epilogue would start only after this one has finished and the two could never overlap (timeline in profiles/:
+          // store-bound shapes ran at epilogue + tail latency per tile instead of the epilogue alone).
+          while (pending && !mbar_test(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1))
+            if (tail_ready()) issue_tail();
           mbar_wait(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1);
           tc_fence_after();
         } else if (first_ctr >= 1) {
@@ -404,63 +409,44 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
     }
   } else {
     // ===================================== epilogue warps ====================================
+    // TMEM -> registers -> bf16 -> per-warp transpose buffer -> global, in blocks of [32 rows x 64 columns] (see
+    // write_staged_block in sm100_ptx.cuh): full 128-byte lines per row and request.
     const int e = warp - 6;                       // 0..7
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int half = e >> 2;                      // which of the two warps of this quarter
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* stg = stg_smem + e * 4096;
-    uint32_t tile_ctr = 0, stores = 0;
+    const uint32_t stg = smem_u32(stg_smem + e * 4096);
+    uint32_t tile_ctr = 0;
     if (has_main) {
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const ItemCoord ic = decode_item<G>(item, p, C::BM);
         const int m0 = ic.m0, g = ic.g;
-        const CUtensorMap* tm_y = &gm.y[ic.prob];
+        uint8_t* yp = gm.y[ic.prob];
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const uint32_t buf = tile_ctr & 1;
           const int n0 = nt * C::BN;
-          const bool rows_live = m0 + q * 32 < p.M;
           mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE(48 + 2 * tile_ctr);
           tc_fence_after();
-          // chunks c with (c + tile_ctr + half) even belong to this warp: the odd chunk count of BN=160 alternates
-          int c = (tile_ctr + half) & 1;
+          // 32-column sub-chunks of this tile that hold live columns; 64-column blocks alternate between the two warps of a
+          // quarter, and the warp that starts alternates with the tile (BN = 160 is 2.5 blocks)
+          const int n_sub = min(C::BN / 32, (p.N - n0 + 31) / 32);
           uint32_t v[32];
-          bool have = c < C::BN / 32 && n0 + c * 32 < p.N;
-          if (have) tmem_ld_x32(lane_addr + buf * C::ACC1_COL + c * 32, v);
-          while (have) {
-            tmem_ld_wait();
-            uint32_t pk[16];
+          for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2) {
+            const int subs = min(2, n_sub - 2 * cb);
+            for (int h = 0; h < subs; ++h) {
+              tmem_ld_x32(lane_addr + buf * C::ACC1_COL + (2 * cb + h) * 32, v);
+              tmem_ld_wait();
+              uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-            const int col0 = n0 + c * 32;
-            c += 2;
-            have = c < C::BN / 32 && n0 + c * 32 < p.N;
-            if (have) tmem_ld_x32(lane_addr + buf * C::ACC1_COL + c * 32, v);   // overlaps the store below
-            if (rows_live) {
-              uint8_t* sb = stg + (stores & 1) * 2048;
-              if (stores >= 2) {            // the TMA store that last read this buffer must have drained it
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                __syncwarp();
-              }
-              // 64B-swizzled [32 rows x 64 B]: 16 B chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
-              uint8_t* srow = sb + lane * 64;
-              const int sw = (lane >> 1) & 3;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                                 reinterpret_cast<uint64_t>(tm_y)),
-                             "r"(col0), "r"(m0 + q * 32), "r"(smem_u32(sb))
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              }
-              ++stores;
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              stage_row_chunk(stg, lane, h, pk);
             }
+            __syncwarp();
+            write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * subs);
+            __syncwarp();
           }
           // every tcgen05.ld of this buffer has completed (wait::ld above): release it to the MMA warp
           tc_fence_before();
@@ -469,9 +455,6 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE(49 + 2 * tile_ctr);
         }
       }
-      // the staging buffers must stay alive until the bulk stores have read them; the writes themselves are
-      // complete (and visible) at kernel end
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       if (warp == 6 && lane == 0) SDT_TRACE(62);
     }
   }
@@ -595,12 +578,10 @@ static int launch_lora_gemm(const LoraProblem* probs, int n_probs, float scaling
     if (main) {
       rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, BN, C::BK, TMAP_SW_128);
       if (rc != SDT_OK) return rc;
-      rc = make_tmap_2d_bf16(&gm.y[q], pr.y, M, N, N * 2, 32, 32, TMAP_SW_64);
-      if (rc != SDT_OK) return rc;
     } else {
       gm.w[q] = gm.x[q];
-      gm.y[q] = gm.x[q];
     }
+    gm.y[q] = reinterpret_cast<uint8_t*>(pr.y);
     if (R > 0) {
       rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, R, C::BK, TMAP_SW_128);
       if (rc != SDT_OK) return rc;
@@ -686,10 +667,12 @@ int lora_gemm_group_bf16(const LoraProblem* probs, int n_probs, float scaling, i
   int rc = check_group(probs, n_probs, r, main);
   if (rc != SDT_OK) return rc;
   SDT_REQUIRE(n_probs == 1 || r > 0, SDT_ERR_UNSUPPORTED, "lora_gemm: grouped launches are built for r > 0 only");
-  // CTA-pair (cta_group::2) kernel when there is a base GEMM, at least one full pair of row tiles and a K loop long
-  // enough (>= 8 k-blocks) to amortise the cross-CTA hand-shakes (measured: K = 320 is faster on the single-CTA kernel);
+  // CTA-pair (cta_group::2) kernel when there is a base GEMM and at least one full pair of row tiles: each SM loads half of
+  // every B-type operand, and since the accumulator hand-over no longer carries a GPU-scope fence it wins at every K of the
+  // step (A/B in profiles/r01_gemm_ab_*.txt: K = 320 was the last hold-out).  Very short K loops stay on the single-CTA kernel.
   // sdt_debug_set(11, 1) forces the single-CTA kernel (A/B measurements)
-  if (main && M >= 256 && K >= 512 && debug_get(11) == 0)
+  const int64_t pair_min_k = debug_get(14) ? (int64_t)debug_get(14) : 256;
+  if (main && M >= 256 && K >= pair_min_k && debug_get(11) == 0)
     return lora_gemm_pair_group_bf16(probs, n_probs, scaling, M, K, N, r, st);
   const bool bn160 = !main || (N % 160 == 0) || (N % 128 != 0 && N > 128);
 #define SDT_GEMM(BN, R, G) return launch_lora_gemm<BN, R, G>(probs, n_probs, scaling, M, K, N, main, st)

@@ -22,11 +22,12 @@ struct LoraProblem {
 // Problems per launch: q/k/v of a self-attention (3), k/v of cross-attentions that read the same text context (2-4).
 constexpr int kMaxGroup = 4;
 
-// Kernel-parameter block: the tensor maps of up to G problems (G = 1: 656 bytes; G = 4: 2.6 KB, indexed dynamically in
+// Kernel-parameter block: the tensor maps of up to G problems (G = 1: 536 bytes; G = 4: 2.1 KB, indexed dynamically in
 // the parameter space -- no copy to local memory, `prefetch.tensormap` / TMA take the generic address of the entry).
 template <int G>
 struct GemmGroup {
-  CUtensorMap x[G], w[G], la[G], lb[G], y[G];
+  CUtensorMap x[G], w[G], la[G], lb[G];
+  uint8_t* y[G];               // outputs are written straight from registers (no tensor map)
   const float* bias[G];
   __nv_bfloat16* t_out[G];
 };

@@ -23,6 +23,12 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows, uint32_t box_cols, TmapSwizzle swz);
 uint64_t debug_get(int key);
 
+// debug timeline of pair 0's leader CTA (same slots as lora_gemm.cu; enabled with sdt_debug_set(10, ptr))
+#define SDT_TRACE2(slot)                                                                      \
+  do {                                                                                        \
+    if (p.trace != nullptr && blockIdx.x == 0 && (slot) < 128) p.trace[(slot)] = clock64();  \
+  } while (0)
+
 namespace pair {
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -42,6 +48,12 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
 }
 __device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Arrive WITHOUT release semantics.  `.release.cluster` compiles to MEMBAR.ALL.GPU + arrive: after the epilogue's burst of
+// global stores that barrier waited ~1700 cycles per tile for the stores to be acknowledged by L2 (timeline in profiles/),
+// although the hand-over only protects TMEM, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already order.
+__device__ __forceinline__ void remote_arrive_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-D tile load into OWN shared memory; the bytes complete on the barrier at `bar_cluster_addr` (the leader's)
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, int c_inner, int c_row, uint32_t bar_cluster_addr) {
@@ -91,8 +103,8 @@ struct PairCfg {
   static constexpr int T_SBO = (KEXT / 8) * 128;
   static constexpr int T_BYTES = (BM / 8) * T_SBO;
   static constexpr int BIAS_BYTES = (((HN + HR) * 32 + 1023) / 1024) * 1024;   // own half of the bias operand [BN/2, 16] + HR zero rows
-  static constexpr int STG_BYTES = 8 * 2 * 2048;
   static constexpr int BAR_BYTES = 256;
+  static constexpr int STG_BYTES = 8 * 4096;                        // 8 epilogue warps x [32 rows x 128 B] transpose buffers
   static constexpr int FIXED_BYTES = 1024 + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
   static constexpr int kStagesMax = (232448 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
@@ -119,6 +131,7 @@ struct PairParams {
   int n_probs;            // problems of identical shape in this launch (<= G)
   int has_bias;
   int n_tiles, n_groups, group_size, n_items;   // items are (256-row tile, problem, n-group)
+  long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
 };
 
 // item -> (problem, 256-row tile index, n-group); consecutive items share the row tile (see lora_gemm.cu)
@@ -169,11 +182,11 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
   const bool has_bias = p.has_bias != 0;
   const bool has_tail = R > 0 || has_bias;
 
+  if (threadIdx.x == 0) SDT_TRACE2(0);
   if (warp == 0 && lane == 0) {
     for (int q = 0; q < (G == 1 ? 1 : p.n_probs); ++q) {
       prefetch_tmap(&gm.x[q]);
       prefetch_tmap(&gm.w[q]);
-      prefetch_tmap(&gm.y[q]);
       if (R > 0) { prefetch_tmap(&gm.la[q]); prefetch_tmap(&gm.lb[q]); }
     }
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -204,6 +217,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
   cluster_sync_all();          // both CTAs' barriers are initialised before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 32) SDT_TRACE2(1);
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
@@ -230,6 +244,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             uint8_t* st = smem + s * C::STAGE_BYTES;
             const uint32_t full_leader = map_to_rank(&full[s], 0);
             if (leader) mbar_arrive_expect_tx(&full[s], tx);
+            if (it == 0) SDT_TRACE2(2);
             tma_load_2d_pair(st, tm_x, kb * C::BK, m0, full_leader);
             tma_load_2d_pair(st + C::X_BYTES, tm_w, kb * C::BK, n0, full_leader);
             if (first) tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES, tm_la, kb * C::BK, (int)rank * C::HR, full_leader);
@@ -278,6 +293,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           umma2_commit_both(&acc_full[pend_tile & 1]);
         }
         __syncwarp();
+        if (lane == 0 && pend_tile < 6) SDT_TRACE2(11 + 4 * pend_tile);
         pending = false;
       };
 
@@ -289,11 +305,16 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           const bool first = (nt == nt0) && R > 0;
           const uint32_t buf = tile_ctr & 1;
           const uint32_t d_main = tmem_base + buf * C::ACC1_COL;
+          // a pending tail goes out while the accumulator buffer is still with the epilogue (see lora_gemm.cu)
+          while (pending && !mbar_test(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1))
+            if (tail_ready()) issue_tail();
           mbar_wait(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1);
           tc_fence_after();
+          if (lane == 0 && tile_ctr < 6) SDT_TRACE2(8 + 4 * tile_ctr);
           for (int kb = 0; kb < nk; ++kb, ++it) {
             const int s = it % C::kStages;
             mbar_wait(&full[s], (it / C::kStages) & 1);
+            if (lane == 0 && tile_ctr < 6 && kb == 0) SDT_TRACE2(9 + 4 * tile_ctr);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
@@ -309,6 +330,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             __syncwarp();
             if (pending && (kb == nk - 1 || tail_ready())) issue_tail();
           }
+          if (lane == 0 && tile_ctr < 6) SDT_TRACE2(10 + 4 * tile_ctr);
           if (first) {
             if (elect_one()) umma2_commit_both(t_full);
             __syncwarp();
@@ -391,92 +413,83 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) remote_arrive(t_ready_leader);
+            if (warp == 2 && lane == 0 && tile_ctr < 6) SDT_TRACE2(40 + tile_ctr);
           }
         }
       }
     }
   } else {
     // ===================================== epilogue warps (both CTAs) ====================================
+    // TMEM -> registers -> bf16 -> per-warp transpose buffer -> global in [32 rows x 64 columns] blocks (see lora_gemm.cu)
     const int e = warp - 6;
     const int q = warp & 3;
     const int half = e >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* stg = stg_smem + e * 4096;
+    const uint32_t stg = smem_u32(stg_smem + e * 4096);
     uint32_t acc_empty_leader[2] = {map_to_rank(&acc_empty[0], 0), map_to_rank(&acc_empty[1], 0)};
-    uint32_t tile_ctr = 0, stores = 0;
+    uint32_t tile_ctr = 0;
     for (int item = pair_id; item < p.n_items; item += n_pairs) {
       const PairItem ic = decode_pair_item<G>(item, p);
       const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
       const int g = ic.g;
-      const CUtensorMap* tm_y = &gm.y[ic.prob];
+      uint8_t* yp = gm.y[ic.prob];
       const int nt0 = g * p.group_size;
       const int nt1 = min(nt0 + p.group_size, p.n_tiles);
       for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
         const uint32_t buf = tile_ctr & 1;
         const int n0 = nt * C::BN;
-        const bool rows_live = m0 + q * 32 < p.M;
         const int gap = (nt == nt0 && R > 0) ? C::HR : 0;      // first tile of an item: Y columns >= HN sit HR further right
         mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
+        if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(48 + 2 * tile_ctr);
         tc_fence_after();
-        int c = (tile_ctr + half) & 1;
+        const int n_sub = min(C::BN / 32, (p.N - n0 + 31) / 32);
         uint32_t v[32];
-        // 32 output columns = two 16-column TMEM loads (HN is a multiple of 16, so a half never straddles the gap)
-        auto load_chunk = [&](int cc) {
-          uint32_t(&lo)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
-          uint32_t(&hi)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[16]);
-          const int y0 = cc * 32, y1 = cc * 32 + 16;
-          tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y0 + (y0 >= C::HN ? gap : 0), lo);
-          tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y1 + (y1 >= C::HN ? gap : 0), hi);
-        };
-        bool have = c < C::BN / 32 && n0 + c * 32 < p.N;
-        if (have) load_chunk(c);
-        while (have) {
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          const int col0 = n0 + c * 32;
-          c += 2;
-          have = c < C::BN / 32 && n0 + c * 32 < p.N;
-          if (have) load_chunk(c);
-          if (rows_live) {
-            uint8_t* sb = stg + (stores & 1) * 2048;
-            if (stores >= 2) {
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-              __syncwarp();
+        for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2) {
+          const int subs = min(2, n_sub - 2 * cb);
+          for (int h = 0; h < subs; ++h) {
+            // 32 output columns: one TMEM load, or two 16-column loads where the block straddles the gap of a first tile
+            // (HN is a multiple of 16, so a half never straddles it)
+            const int y0 = (2 * cb + h) * 32, y1 = y0 + 16;
+            if (gap == 0 || y0 >= C::HN || y0 + 32 <= C::HN) {
+              tmem_ld_x32(lane_addr + buf * C::ACC1_COL + y0 + (y0 >= C::HN ? gap : 0), v);
+            } else {
+              uint32_t(&lo)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
+              uint32_t(&hi)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[16]);
+              tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y0 + (y0 >= C::HN ? gap : 0), lo);
+              tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y1 + (y1 >= C::HN ? gap : 0), hi);
             }
-            uint8_t* srow = sb + lane * 64;
-            const int sw = (lane >> 1) & 3;
+            if (warp == 6 && lane == 0 && tile_ctr == 0) SDT_TRACE2(70 + 8 * (cb >> 1) + 4 * h);
+            tmem_ld_wait();
+            if (warp == 6 && lane == 0 && tile_ctr == 0) SDT_TRACE2(71 + 8 * (cb >> 1) + 4 * h);
+            uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                               reinterpret_cast<uint64_t>(tm_y)),
-                           "r"(col0), "r"(m0 + q * 32), "r"(smem_u32(sb))
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            ++stores;
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            stage_row_chunk(stg, lane, h, pk);
+            if (warp == 6 && lane == 0 && tile_ctr == 0) SDT_TRACE2(72 + 8 * (cb >> 1) + 4 * h);
           }
+          __syncwarp();
+          write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * subs);
+          __syncwarp();
+          if (warp == 6 && lane == 0 && tile_ctr == 0) SDT_TRACE2(73 + 8 * (cb >> 1));
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) remote_arrive(acc_empty_leader[buf]);
+        if (lane == 0) remote_arrive_relaxed(acc_empty_leader[buf]);
+        if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(49 + 2 * tile_ctr);
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (warp == 6 && lane == 0) SDT_TRACE2(62);
   }
 
   // neither CTA may leave (or free TMEM) while the other can still touch its shared memory / barriers / TMEM
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
+  if (threadIdx.x == 0) SDT_TRACE2(63);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, C::TMEM_COLS);
+    if (lane == 0) SDT_TRACE2(64);
   }
 }
 
@@ -510,8 +523,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
     if (rc != SDT_OK) return rc;
     rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);
     if (rc != SDT_OK) return rc;
-    rc = make_tmap_2d_bf16(&gm.y[q], pr.y, M, N, N * 2, 32, 32, TMAP_SW_64);
-    if (rc != SDT_OK) return rc;
+    gm.y[q] = reinterpret_cast<uint8_t*>(pr.y);
     if (R > 0) {
       rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
       if (rc != SDT_OK) return rc;
@@ -529,6 +541,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.n_probs = n_probs;
   p.has_bias = probs[0].bias != nullptr ? 1 : 0;
+  p.trace = reinterpret_cast<long long*>(debug_get(10));
   const int m_tiles = (int)((M + 2 * C::BM - 1) / (2 * C::BM));
   p.n_tiles = (int)((N + BN - 1) / BN);
   const int pairs_max = num_sms() / 2;

@@ -77,8 +77,10 @@ __device__ __forceinline__ float bf16_bits_to_f32(uint32_t lo16) { return __uint
 __device__ __forceinline__ uint32_t f32_to_bf16_bits(float f) {
   return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
 }
+// two f32 -> one packed bf16 pair (round to nearest even), lo in bits [0,16): a single cvt.rn.bf16x2.f32
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  return f32_to_bf16_bits(lo) | (f32_to_bf16_bits(hi) << 16);
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 // round an f32 to the nearest bf16 value, result as f32 (what torch does after every bf16 op)
 __device__ __forceinline__ float round_bf16(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }

@@ -152,6 +152,44 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- epilogue stores ------------------------------------------------------------------------------------------------
+// A thread of an epilogue warp holds 32 consecutive output columns of ONE row (TMEM lane = row); written as they lie that
+// is 64 bytes per row and request, and the memory system then runs at about half its write bandwidth (measured: the
+// K = 320 projections were bound by exactly this, with TMA stores of 32-column boxes as much as with register stores).
+// So each warp transposes a [32 rows x 64 columns] block through 4 KiB of its own shared memory (XOR-swizzled 16-byte
+// slots, conflict-free both ways, __syncwarp only) and writes it out with 8 lanes per row: every store instruction covers
+// four full 128-byte lines.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint32_t* r) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// stage this lane's 32 packed columns (sub-chunk h = 0 / 1 of the 64-column block) of row `lane`
+__device__ __forceinline__ void stage_row_chunk(uint32_t stg, int lane, int h, const uint32_t (&pk)[16]) {
+  const uint32_t row_base = stg + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st_shared_v4(row_base + (((4 * h + j) ^ (lane & 7)) << 4), pk + 4 * j);
+}
+// write the staged block out: rows [row0, row0 + 32) x 16-byte slots [0, n_slots) starting at column col0 of a row-major
+// bf16 matrix with N columns (N % 8 == 0); rows >= M and columns >= N are clipped
+__device__ __forceinline__ void write_staged_block(uint32_t stg, int lane, uint8_t* y, int row0, int M, int col0, int N, int n_slots) {
+  const int c = lane & 7;
+  const bool col_ok = c < n_slots && col0 + 8 * c < N;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = 4 * i + (lane >> 3);
+    if (col_ok && row0 + rl < M) {
+      const uint4 v = ld_shared_v4(stg + rl * 128 + ((c ^ (rl & 7)) << 4));
+      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(y + ((size_t)(row0 + rl) * N + col0 + 8 * c) * 2), "r"(v.x),
+                   "r"(v.y), "r"(v.z), "r"(v.w)
+                   : "memory");
+    }
+  }
+}
+
 }  // namespace ptx
 
 // ---- host side: tensor-map encode through the runtime's driver entry point (no -lcuda) -----------

@@ -1,0 +1,72 @@
+"""A/B timings of the fused LoRA GEMM variants (CUPTI kernel durations, L2-warm and L2-cold) on the shapes of the step."""
+import os
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from scal_sdt_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+dev = torch.device("cuda:0")
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+
+def kernel_us(fn, iters=8, cold=False):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(iters):
+            if cold:
+                flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+    d = [e.time_range.end - e.time_range.start for e in prof.events()
+         if str(getattr(e, "device_type", "")).endswith("CUDA") and "lora_gemm" in e.name]
+    names = {e.name.split("(")[0].replace("void sdt::", "") for e in prof.events() if "lora_gemm" in e.name}
+    return sum(d) / len(d), ",".join(sorted(names))
+
+
+def case(M, K, N, R, G, settings):
+    xs = torch.randn(M, K, device=dev).bfloat16()
+    ws = [(torch.randn(N, K, device=dev) / K ** 0.5).bfloat16() for _ in range(G)]
+    bs = [torch.randn(N, device=dev) for _ in range(G)]
+    As = [(torch.randn(R, K, device=dev) / K ** 0.5).bfloat16() for _ in range(G)]
+    Bs = [(torch.randn(N, R, device=dev) * 0.1).bfloat16() for _ in range(G)]
+    ys = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(G)]
+    ts = [torch.empty(M, R, device=dev, dtype=torch.bfloat16) for _ in range(G)]
+    probs = (_lib.LoraProblem * G)(*[_lib.LoraProblem(xs.data_ptr(), ws[g].data_ptr(), bs[g].data_ptr(), As[g].data_ptr(), Bs[g].data_ptr(),
+                                                      ys[g].data_ptr(), ts[g].data_ptr()) for g in range(G)])
+    import ctypes
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        if G == 1:
+            _lib.check(lib.sdt_lora_linear_fwd(xs.data_ptr(), ws[0].data_ptr(), bs[0].data_ptr(), As[0].data_ptr(), Bs[0].data_ptr(), 0.5,
+                                               ys[0].data_ptr(), ts[0].data_ptr(), M, K, N, R, 1, st))
+        else:
+            _lib.check(lib.sdt_lora_linear_fwd_group(ctypes.addressof(probs), G, 0.5, M, K, N, R, 1, st))
+    fl = G * (2.0 * M * K * N + 2.0 * M * R * (K + N))
+    out = []
+    for name, kv in settings:
+        for k in (11, 12, 13, 14):
+            lib.sdt_debug_set(k, 0)
+        for k, v in kv.items():
+            lib.sdt_debug_set(k, v)
+        warm, kn = kernel_us(run)
+        cold, _ = kernel_us(run, cold=True)
+        out.append(f"{name}: warm {warm:6.1f} us {fl / warm / 1e6:6.0f} TF/s | cold {cold:6.1f} us {fl / cold / 1e6:6.0f} TF/s [{kn}]")
+    for k in (11, 12, 13, 14):
+        lib.sdt_debug_set(k, 0)
+    print(f"M={M} K={K} N={N} R={R} G={G}")
+    for o in out:
+        print("   ", o)
+
+
+SET = [("auto  ", {}), ("single", {11: 1}), ("pair  ", {14: 64}), ("pair160", {14: 64, 12: 1})]
+for shp in [(32768, 320, 320, 16, 1), (32768, 320, 320, 16, 3), (32768, 320, 2560, 16, 1), (32768, 1280, 320, 16, 1),
+            (8192, 640, 640, 16, 1), (8192, 640, 640, 16, 3), (8192, 640, 5120, 16, 1), (2048, 1280, 1280, 16, 1),
+            (2048, 1280, 1280, 16, 3), (2048, 1280, 10240, 16, 1), (616, 768, 1280, 16, 4), (616, 768, 320, 16, 4)]:
+    case(*shp, SET)

@@ -20,6 +20,14 @@ for t in range(6):
     NAMES[49 + 2 * t] = f"epi t{t}: drained"
 
 
+for cbi in range(3):
+    for h in range(2):
+        NAMES[70 + 8 * cbi + 4 * h] = f"  epi t0 w6 blk{cbi} sub{h}: ld issued"
+        NAMES[71 + 8 * cbi + 4 * h] = f"  epi t0 w6 blk{cbi} sub{h}: ld done"
+        NAMES[72 + 8 * cbi + 4 * h] = f"  epi t0 w6 blk{cbi} sub{h}: staged"
+    NAMES[73 + 8 * cbi] = f"  epi t0 w6 blk{cbi}: written"
+
+
 def run(M, K, N, R, bias=True):
     x = torch.randn(M, K, device=dev).bfloat16()
     w = torch.randn(N, K, device=dev).bfloat16()
@@ -47,9 +55,11 @@ def run(M, K, N, R, bias=True):
         print(f"{v - t0:8d}  {NAMES.get(slot, slot)}")
 
 
-lib.sdt_debug_set(11, 1)          # single-CTA kernel (the traced one)
-for ws_off in (1, 0):
-    lib.sdt_debug_set(13, ws_off)
-    print("==== weight-stationary", "off" if ws_off else "on")
-    for shape in [(32768, 320, 320, 16), (32768, 320, 2560, 16)]:
-        run(*shape)
+mode = sys.argv[1] if len(sys.argv) > 1 else "single"
+if mode == "single":
+    lib.sdt_debug_set(11, 1)          # force the single-CTA kernel
+else:
+    lib.sdt_debug_set(14, 64)         # CTA-pair kernel for every K
+print("==== kernel:", mode)
+for shape in [(32768, 320, 320, 16), (32768, 320, 2560, 16), (2048, 1280, 1280, 16), (8192, 640, 5120, 16)]:
+    run(*shape)
