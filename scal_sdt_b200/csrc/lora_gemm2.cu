@@ -46,8 +46,12 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(p)), "r"(rank));
   return out;
 }
+// Arrive on a barrier of the peer CTA after writing operands into OWN shared memory.  Release at CTA scope (what CUTLASS'
+// ClusterBarrier::arrive does): the writes were already pushed to the async proxy by fence.proxy.async, and the tensor core
+// that reads them is this CTA's own.  `.release.cluster` would add a MEMBAR.ALL.GPU, which queues behind the epilogue's store
+// traffic (~1000+ cycles per item, timeline in profiles/).
 __device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // Arrive WITHOUT release semantics.  `.release.cluster` compiles to MEMBAR.ALL.GPU + arrive: after the epilogue's burst of
 // global stores that barrier waited ~1700 cycles per tile for the stores to be acknowledged by L2 (timeline in profiles/),
