@@ -98,3 +98,43 @@ def test_kohya_export_key_layout():
     assert len(out) == 3 * 192 + 3
     proj = "lora_unet_mid_block_attentions_0_proj_in.lora_down.weight"
     assert out[proj].dim() == 2                     # 1x1-conv LoRA factors are emitted 2-D
+
+
+def test_svd_extraction_matches_reference_restatement():
+    """``extract_lora.py:23-39,130-154``: factors, sqrt(rank/alpha) scaling, kohya keys, 2-D conv weights."""
+    from math import sqrt
+
+    from scal_sdt_b200.export import extract_lora_state_dict, lora_approx
+    from scal_sdt_b200.targets import lora_unet_targets
+    torch.manual_seed(0)
+    base = UNet2DConditionModel(UNetConfig.tiny())
+    tuned = UNet2DConditionModel(UNetConfig.tiny())
+    tuned.load_state_dict(base.state_dict())
+    # a known rank-3 update on one Linear and one 1x1 conv, noise elsewhere
+    lin = tuned.down_blocks[0].attentions[0].transformer_blocks[0].attn1.to_q
+    conv = tuned.down_blocks[0].attentions[0].proj_in
+    u, v = torch.randn(lin.out_features, 3), torch.randn(3, lin.in_features)
+    with torch.no_grad():
+        lin.weight += u @ v
+        conv.weight += (torch.randn(conv.out_channels, 2) @ torch.randn(2, conv.in_channels))[:, :, None, None]
+    state = extract_lora_state_dict(tuned, base, lora_unet_targets(rank=4, alpha=2), dtype=torch.float32)
+    # 192 sites at SD1.5 topology -> the tiny UNet has the same topology
+    assert len(state) == 3 * 192
+    key = "lora_unet_down_blocks_0_attentions_0_transformer_blocks_0_attn1_to_q"
+    down, up, alpha = state[f"{key}.lora_down.weight"], state[f"{key}.lora_up.weight"], state[f"{key}.alpha"]
+    assert down.shape == (4, lin.in_features) and up.shape == (lin.out_features, 4)
+    assert alpha.dtype == torch.int32 and int(alpha) == 2
+    # (alpha / rank) * up @ down reproduces the rank-3 difference
+    delta = lin.weight.detach() - base.down_blocks[0].attentions[0].transformer_blocks[0].attn1.to_q.weight.detach()
+    assert torch.allclose((2 / 4) * up @ down, delta, atol=1e-4)
+    # literal restatement of the reference's lora_approx on the same delta
+    ru, rs, rvt = torch.linalg.svd(delta)
+    ref_up, ref_down = ru[:, :4] @ torch.diag(rs[:4]), rvt[:4, :]
+    assert torch.allclose(ref_up @ ref_down, (up @ down) / (sqrt(4 / 2) ** 2), atol=1e-4)
+    d2, u2 = lora_approx(delta, 4)
+    assert torch.allclose(u2 @ d2, ref_up @ ref_down, atol=1e-4)
+    ckey = "lora_unet_down_blocks_0_attentions_0_proj_in"
+    assert state[f"{ckey}.lora_down.weight"].dim() == 2 and state[f"{ckey}.lora_up.weight"].shape == (conv.out_channels, 4)
+    # untouched sites extract (numerically) nothing
+    zkey = "lora_unet_mid_block_attentions_0_transformer_blocks_0_attn2_to_v"
+    assert state[f"{zkey}.lora_up.weight"].abs().max() < 1e-6
