@@ -89,6 +89,21 @@ int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt, const voi
                         const void* t_save, float scaling, void* dx, void* g_ws, float* dA, float* dB,
                         int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* stream);
 
+/* ---- K2 (grouped): backward of projections that read ONE input (to_q / to_k / to_v) ----------------------
+ * The reference's autograd runs three backward GEMMs and two adds for dX = sum_q (dY_q W_q + s (dY_q B_q) A_q).  Here the sum
+ * is ONE K loop over the concatenated contraction (each projection is a "source" with its own rank-R accumulator in TMEM), so
+ * dX is written once; G_q is written to g_ws of each problem and the dA / dB reductions follow, one launch per projection.
+ * 2..3 problems of identical (M, K, N, r, scaling); padded rank 16 or 32; M >= 256 (sdt_lora_linear_bwd_group_supported says
+ * whether a shape qualifies; otherwise call sdt_lora_linear_bwd per site and add).  `problems` is a HOST array; bf16 only.
+ */
+typedef struct {
+  const void* dy; const void* x; const void* wt; const void* At; const void* Bt; const void* t_save;
+  void* g_ws; float* dA; float* dB;
+} sdt_lora_bwd_problem;
+int sdt_lora_linear_bwd_group_supported(int n_problems, int64_t M, int64_t K, int64_t N, int r);
+int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems /* host */, int n_problems, float scaling, void* dx,
+                              int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* stream);
+
 /* ---- LoRA operand packing (multi-tensor, one launch for all sites) ---------------------------
  * For every site i: from the f32 master lora_A[r_true,K], lora_B[N,r_true] write the four bf16
  * operand layouts the tensor-core kernels read, zero-padded to rank r:

@@ -29,6 +29,11 @@ class LoraProblem(ctypes.Structure):
                 ("t_save", c_void_p)]
 
 
+class LoraBwdProblem(ctypes.Structure):
+    _fields_ = [("dy", c_void_p), ("x", c_void_p), ("wt", c_void_p), ("At", c_void_p), ("Bt", c_void_p), ("t_save", c_void_p),
+                ("g_ws", c_void_p), ("dA", c_void_p), ("dB", c_void_p)]
+
+
 MAX_GROUP = 4
 
 
@@ -45,6 +50,9 @@ SIGNATURES = {
     "sdt_lora_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sdt_lora_linear_fwd_group": (c_int, [c_void_p, c_int, c_float, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "sdt_lora_linear_bwd_group_supported": (c_int, [c_int, c_int64, c_int64, c_int64, c_int]),
+    "sdt_lora_linear_bwd_group": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
+                                          c_void_p]),
     "sdt_lora_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                     c_void_p]),

@@ -87,6 +87,38 @@ extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt
   return SDT_ERR_UNSUPPORTED;
 }
 
+extern "C" int sdt_lora_linear_bwd_group_supported(int n_problems, int64_t M, int64_t K, int64_t N, int r) {
+  // the summed GEMM contracts over N (features of dY) and produces K columns of dX
+  return lora_gemm_pair_sum_supported(n_problems, M, N, K, r) ? 1 : 0;
+}
+
+extern "C" int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems, int n_problems, float scaling, void* dx, int64_t M,
+                                         int64_t K, int64_t N, int r, int r_true, int dtype, void* stream) {
+  SDT_REQUIRE(problems != nullptr && dx != nullptr, SDT_ERR_ARG, "sdt_lora_linear_bwd_group: null pointer");
+  SDT_REQUIRE(dtype == SDT_BF16, SDT_ERR_UNSUPPORTED, "sdt_lora_linear_bwd_group: bf16 only (there is no fallback)");
+  SDT_REQUIRE(M > 0 && K > 0 && N > 0, SDT_ERR_ARG, "sdt_lora_linear_bwd_group: bad sizes");
+  SDT_REQUIRE(lora_gemm_pair_sum_supported(n_problems, M, N, K, r), SDT_ERR_UNSUPPORTED,
+              "sdt_lora_linear_bwd_group: needs 2..3 projections, padded rank 16/32, M >= 256 (got %d, r=%d, M=%lld): use "
+              "sdt_lora_linear_bwd per site", n_problems, r, (long long)M);
+  cudaStream_t st = (cudaStream_t)stream;
+  LoraProblem pr[3];
+  for (int q = 0; q < n_problems; ++q) {
+    const sdt_lora_bwd_problem& b = problems[q];
+    SDT_REQUIRE(b.dy && b.x && b.wt && b.At && b.Bt && b.t_save && b.g_ws && b.dA && b.dB, SDT_ERR_ARG,
+                "sdt_lora_linear_bwd_group: null pointer in problem %d", q);
+    // G_q = s dY_q B_q ; dX += dY_q W_q + G_q A_q   -- the forward kernel's roles with (dY, W^T, B^T, A^T)
+    pr[q] = LoraProblem{b.dy, b.wt, nullptr, b.Bt, b.At, dx, b.g_ws};
+  }
+  int rc = lora_gemm_pair_sum_bf16(pr, n_problems, scaling, M, /*contraction*/ N, /*outputs*/ K, r, st);
+  if (rc != SDT_OK) return rc;
+  for (int q = 0; q < n_problems; ++q) {
+    const sdt_lora_bwd_problem& b = problems[q];
+    rc = lora_wgrad_pair_bf16(b.x, b.g_ws, b.dA, K, b.dy, b.t_save, b.dB, N, M, r, r_true, st);
+    if (rc != SDT_OK) return rc;
+  }
+  return SDT_OK;
+}
+
 extern "C" int sdt_debug_set(int key, uint64_t value) {
   debug_set(key, value);
   return SDT_OK;

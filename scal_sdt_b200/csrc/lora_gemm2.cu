@@ -95,15 +95,19 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
 
 using namespace pair;
 
-template <int BN_, int R_>
+// S = number of SOURCES whose products are summed into one output (S = 1: a plain projection; S = 3: the input gradient of
+// q / k / v, dX = sum_s dY_s W_s + (s dY_s B_s) A_s, as ONE K loop over the concatenated contraction).  Every source has its own
+// rank-R accumulator, lora-up tile and slice of the tail's A operand.
+template <int BN_, int R_, int S_ = 1>
 struct PairCfg {
-  static constexpr int BM = 128, BN = BN_, BK = 64, R = R_, HN = BN_ / 2, HR = R_ / 2;
+  static constexpr int BM = 128, BN = BN_, BK = 64, R = R_, HN = BN_ / 2, HR = R_ / 2, S = S_;
   static constexpr int X_BYTES = BM * BK * 2;                       // own 128 rows of X
   static constexpr int W_BYTES = HN * BK * 2;                       // own half of the W tile
   static constexpr int LA_BYTES = ((HR * BK * 2 + 1023) / 1024) * 1024;   // own half of the lora-down k-block
   static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + LA_BYTES;
-  static constexpr int LB_BYTES = (((HN + HR) * R * 2 + 1023) / 1024) * 1024;   // own half of the lora-up tile [BN/2, R] + HR zero rows
-  static constexpr int KEXT = R + 16;
+  static constexpr int LB_TILE = (((HN + HR) * R * 2 + 1023) / 1024) * 1024;    // own half of one lora-up tile [BN/2, R] + HR zero rows
+  static constexpr int LB_BYTES = S * LB_TILE;
+  static constexpr int KEXT = S * R + 16;
   static constexpr int T_SBO = (KEXT / 8) * 128;
   static constexpr int T_BYTES = (BM / 8) * T_SBO;
   static constexpr int BIAS_BYTES = (((HN + HR) * 32 + 1023) / 1024) * 1024;   // own half of the bias operand [BN/2, 16] + HR zero rows
@@ -119,8 +123,9 @@ struct PairCfg {
   // cta_group::2 the N index runs over CTA 0's rows, then CTA 1's, so the columns of such a tile are
   //   [Y 0..HN) | T 0..HR) | Y HN..BN) | T HR..R)]      (acc_col(y) = y < HN ? y : y + HR ; acc_col(t) = t < HR ? HN + t : BN + t)
   // and the tail UMMAs use the same N with zero rows appended to the lora-up / bias operands.  Other tiles are plain [Y].
-  static constexpr int ACC1_COL = BN + R;
-  static_assert(2 * BN + 2 * R <= 512, "TMEM budget");
+  // With S > 1 the tiles are never merged: main accumulator [Y 0..BN) and S rank accumulators [T_s 0..R) behind it.
+  static constexpr int ACC1_COL = BN + S * R;
+  static_assert(2 * ACC1_COL <= 512, "TMEM budget");
   static_assert(BN % 32 == 0 && HN % 8 == 0 && BN <= 256, "BN");
   static_assert(R == 0 || R == 16 || R == 32 || R == 64, "rank must be padded to 16/32/64");
   static_assert(kStages >= 3, "pipeline depth");
@@ -133,6 +138,7 @@ struct PairParams {
   float scaling;
   int M, N, K;
   int n_probs;            // problems of identical shape in this launch (<= G)
+  int n_src;              // sources summed into each output (<= S; their operands are entries 0..n_src-1 of the group)
   int has_bias;
   int n_tiles, n_groups, group_size, n_items;   // items are (256-row tile, problem, n-group)
   long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
@@ -157,10 +163,13 @@ __device__ __forceinline__ PairItem decode_pair_item(int item, const PairParams&
   return c;
 }
 
-template <int BN, int R, int G>
+template <int BN, int R, int G, int S>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams p) {
-  using C = PairCfg<BN, R>;
+  using C = PairCfg<BN, R, S>;
+  static_assert(S == 1 || (G >= S && R > 0), "summed sources live in the entries of the group");
+  constexpr bool kMerged = S == 1;             // first tile of an item: base GEMM and rank projection as one UMMA
+  const int n_src = S == 1 ? 1 : p.n_src;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* lb_smem = smem + C::kStages * C::STAGE_BYTES;
@@ -188,7 +197,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
 
   if (threadIdx.x == 0) SDT_TRACE2(0);
   if (warp == 0 && lane == 0) {
-    for (int q = 0; q < (G == 1 ? 1 : p.n_probs); ++q) {
+    for (int q = 0; q < (S > 1 ? n_src : (G == 1 ? 1 : p.n_probs)); ++q) {
       prefetch_tmap(&gm.x[q]);
       prefetch_tmap(&gm.w[q]);
       if (R > 0) { prefetch_tmap(&gm.la[q]); prefetch_tmap(&gm.lb[q]); }
@@ -205,15 +214,16 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
   if (warp >= 2 && warp < 6) {
     const int row = (warp - 2) * 32 + lane;
     uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
-    *reinterpret_cast<uint4*>(trow + (R / 8) * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // bf16 1.0, 1.0
-    *reinterpret_cast<uint4*>(trow + (R / 8 + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(trow + (S * R / 8) * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // bf16 1.0, 1.0
+    *reinterpret_cast<uint4*>(trow + (S * R / 8 + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
     for (int n = row; n < C::HN + C::HR; n += 128) {
       *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + 128 + (n & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
       if (n >= C::HN) *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     // zero rows behind the lora-up tile (rows of R*2 bytes; the TMA box only ever writes the first HN rows)
     for (int i = row; i < C::HR * R * 2 / 16; i += 128)
-      *reinterpret_cast<uint4*>(lb_smem + C::HN * R * 2 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+      for (int q = 0; q < S; ++q)
+        *reinterpret_cast<uint4*>(lb_smem + q * C::LB_TILE + C::HN * R * 2 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -232,31 +242,31 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         const PairItem ic = decode_pair_item<G>(item, p);
         const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
         const int g = ic.g;
-        const CUtensorMap* tm_x = &gm.x[ic.prob];
-        const CUtensorMap* tm_w = &gm.w[ic.prob];
-        const CUtensorMap* tm_la = &gm.la[ic.prob];
-        const CUtensorMap* tm_lb = &gm.lb[ic.prob];
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
           const int n0 = nt * C::BN + (int)rank * C::HN;
           const uint32_t tx = 2u * (C::X_BYTES + C::W_BYTES + (first ? C::HR * C::BK * 2 : 0));
-          for (int kb = 0; kb < nk; ++kb, ++it) {
-            const int s = it % C::kStages;
-            mbar_wait(&empty[s], ((it / C::kStages) & 1) ^ 1);
-            uint8_t* st = smem + s * C::STAGE_BYTES;
-            const uint32_t full_leader = map_to_rank(&full[s], 0);
-            if (leader) mbar_arrive_expect_tx(&full[s], tx);
-            if (it == 0) SDT_TRACE2(2);
-            tma_load_2d_pair(st, tm_x, kb * C::BK, m0, full_leader);
-            tma_load_2d_pair(st + C::X_BYTES, tm_w, kb * C::BK, n0, full_leader);
-            if (first) tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES, tm_la, kb * C::BK, (int)rank * C::HR, full_leader);
+          for (int src = 0; src < n_src; ++src) {
+            const int q = S > 1 ? src : ic.prob;          // operand set: the source, or the problem of a grouped launch
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+              const int s = it % C::kStages;
+              mbar_wait(&empty[s], ((it / C::kStages) & 1) ^ 1);
+              uint8_t* st = smem + s * C::STAGE_BYTES;
+              const uint32_t full_leader = map_to_rank(&full[s], 0);
+              if (leader) mbar_arrive_expect_tx(&full[s], tx);
+              if (it == 0) SDT_TRACE2(2);
+              tma_load_2d_pair(st, &gm.x[q], kb * C::BK, m0, full_leader);
+              tma_load_2d_pair(st + C::X_BYTES, &gm.w[q], kb * C::BK, n0, full_leader);
+              if (first) tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES, &gm.la[q], kb * C::BK, (int)rank * C::HR, full_leader);
+            }
           }
           if (R > 0) {
             mbar_wait(lb_empty, (tile_ctr & 1) ^ 1);
-            if (leader) mbar_arrive_expect_tx(lb_full, 2u * C::HN * R * 2);
-            tma_load_2d_pair(lb_smem, tm_lb, 0, n0, lb_full_leader);
+            if (leader) mbar_arrive_expect_tx(lb_full, 2u * n_src * C::HN * R * 2);
+            for (int src = 0; src < n_src; ++src)
+              tma_load_2d_pair(lb_smem + src * C::LB_TILE, &gm.lb[S > 1 ? src : ic.prob], 0, n0, lb_full_leader);
           }
         }
       }
@@ -267,6 +277,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
       constexpr int RR = R > 0 ? R : 16;
       constexpr uint32_t idesc_main = make_idesc_bf16(256, BN, 0, 0);
       constexpr uint32_t idesc_both = make_idesc_bf16(256, BN + R, 0, 0);    // first tile of an item: [W ; lora-down]
+      constexpr uint32_t idesc_rank = make_idesc_bf16(256, RR, 0, 0);        // S > 1: the rank projection as its own UMMA
       constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
       constexpr uint32_t lb_layout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
       constexpr uint64_t d_lb = make_smem_desc_base(16, 8 * RR * 2, lb_layout);
@@ -288,11 +299,14 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         if (elect_one()) {
           const uint32_t d = tmem_base + (pend_tile & 1) * C::ACC1_COL;
           const uint32_t ta = smem_u32(t_smem), ba = smem_u32(lb_smem);
-          const uint32_t idesc_tail = pend_first ? idesc_both : idesc_main;   // same column layout as the tile's K loop
+          const uint32_t idesc_tail = (kMerged && pend_first) ? idesc_both : idesc_main;   // same column layout as the tile's K loop
+          for (int src = 0; src < n_src; ++src) {
 #pragma unroll
-          for (int k = 0; k < R / 16; ++k)
-            umma2_f16_ss(d, smem_desc(d_t, ta + k * 256), smem_desc(d_lb, ba + k * 32), idesc_tail, 1u);
-          if (has_bias) umma2_f16_ss(d, smem_desc(d_t, ta + (R / 16) * 256), smem_desc(d_bias, smem_u32(bias_smem)), idesc_tail, 1u);
+            for (int k = 0; k < R / 16; ++k)
+              umma2_f16_ss(d, smem_desc(d_t, ta + (src * (R / 16) + k) * 256), smem_desc(d_lb, ba + src * C::LB_TILE + k * 32),
+                           idesc_tail, 1u);
+          }
+          if (has_bias) umma2_f16_ss(d, smem_desc(d_t, ta + (S * R / 16) * 256), smem_desc(d_bias, smem_u32(bias_smem)), idesc_tail, 1u);
           umma2_commit_both(lb_empty);
           umma2_commit_both(&acc_full[pend_tile & 1]);
         }
@@ -315,24 +329,32 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           mbar_wait(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1);
           tc_fence_after();
           if (lane == 0 && tile_ctr < 6) SDT_TRACE2(8 + 4 * tile_ctr);
-          for (int kb = 0; kb < nk; ++kb, ++it) {
-            const int s = it % C::kStages;
-            mbar_wait(&full[s], (it / C::kStages) & 1);
-            if (lane == 0 && tile_ctr < 6 && kb == 0) SDT_TRACE2(9 + 4 * tile_ctr);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
-              const uint32_t wa = xa + C::X_BYTES;
-              const uint32_t la = wa + C::W_BYTES;
+          for (int src = 0; src < n_src; ++src) {
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+              const int s = it % C::kStages;
+              mbar_wait(&full[s], (it / C::kStages) & 1);
+              if (lane == 0 && tile_ctr < 6 && kb == 0 && src == 0) SDT_TRACE2(9 + 4 * tile_ctr);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
+                const uint32_t wa = xa + C::X_BYTES;
+                const uint32_t la = wa + C::W_BYTES;
 #pragma unroll
-              for (int k = 0; k < C::BK / 16; ++k) {
-                const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
-                umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main, (kb | k) != 0);
+                for (int k = 0; k < C::BK / 16; ++k) {
+                  const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
+                  if (kMerged) {
+                    umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main, (kb | k) != 0);
+                  } else {
+                    // every source accumulates into the same main columns; its rank projection has its own columns
+                    umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), idesc_main, (src | kb | k) != 0);
+                    if (first) umma2_f16_ss(d_main + BN + src * R, a_desc, smem_desc(d_sw128, la + k * 32), idesc_rank, (kb | k) != 0);
+                  }
+                }
+                umma2_commit_both(&empty[s]);
               }
-              umma2_commit_both(&empty[s]);
+              __syncwarp();
+              if (pending && ((src == n_src - 1 && kb == nk - 1) || tail_ready())) issue_tail();
             }
-            __syncwarp();
-            if (pending && (kb == nk - 1 || tail_ready())) issue_tail();
           }
           if (lane == 0 && tile_ctr < 6) SDT_TRACE2(10 + 4 * tile_ctr);
           if (first) {
@@ -371,7 +393,6 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
         const int g = ic.g;
         const float* bias = gm.bias[ic.prob];
-        __nv_bfloat16* t_out = gm.t_out[ic.prob];
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -388,27 +409,32 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           if (first) {
             mbar_wait(t_full, first_ctr & 1);
             tc_fence_after();
-            uint32_t packed[RR / 2];
+            for (int src = 0; src < n_src; ++src) {
+              uint32_t packed[RR / 2];
 #pragma unroll
-            for (int c = 0; c < RR / 8; ++c) {
-              // rank column t lives at HN + t (t < HR: CTA 0's lora-down rows) or BN + t (CTA 1's)
-              const int t0 = c * 8;
-              uint32_t v[8];
-              tmem_ld_x8(lane_addr + (tile_ctr & 1) * C::ACC1_COL + (t0 < C::HR ? C::HN + t0 : C::BN + t0), v);
-              tmem_ld_wait();
+              for (int c = 0; c < RR / 8; ++c) {
+                // merged tile: rank column t lives at HN + t (t < HR: CTA 0's lora-down rows) or BN + t (CTA 1's);
+                // otherwise source src owns columns BN + src R + t
+                const int t0 = c * 8;
+                const int col = kMerged ? (t0 < C::HR ? C::HN + t0 : C::BN + t0) : C::BN + src * R + t0;
+                uint32_t v[8];
+                tmem_ld_x8(lane_addr + (tile_ctr & 1) * C::ACC1_COL + col, v);
+                tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                packed[c * 4 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling);
-            }
-            uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
-#pragma unroll
-            for (int kc = 0; kc < RR / 8; ++kc)
-              *reinterpret_cast<uint4*>(trow + kc * 128) = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
-            if (t_out != nullptr && g == 0 && m0 + row < p.M) {
-              uint4* dst = reinterpret_cast<uint4*>(t_out + (size_t)(m0 + row) * RR);
+                for (int j = 0; j < 4; ++j)
+                  packed[c * 4 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling);
+              }
+              uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16 + src * (RR / 8) * 128;
 #pragma unroll
               for (int kc = 0; kc < RR / 8; ++kc)
-                dst[kc] = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
+                *reinterpret_cast<uint4*>(trow + kc * 128) = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
+              __nv_bfloat16* t_out = gm.t_out[S > 1 ? src : ic.prob];
+              if (t_out != nullptr && g == 0 && m0 + row < p.M) {
+                uint4* dst = reinterpret_cast<uint4*>(t_out + (size_t)(m0 + row) * RR);
+#pragma unroll
+                for (int kc = 0; kc < RR / 8; ++kc)
+                  dst[kc] = make_uint4(packed[kc * 4], packed[kc * 4 + 1], packed[kc * 4 + 2], packed[kc * 4 + 3]);
+              }
             }
             ++first_ctr;
           }
@@ -442,7 +468,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
       for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
         const uint32_t buf = tile_ctr & 1;
         const int n0 = nt * C::BN;
-        const int gap = (nt == nt0 && R > 0) ? C::HR : 0;      // first tile of an item: Y columns >= HN sit HR further right
+        const int gap = (kMerged && nt == nt0 && R > 0) ? C::HR : 0;      // merged first tile: Y columns >= HN sit HR further right
         mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
         if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(48 + 2 * tile_ctr);
         tc_fence_after();
@@ -512,12 +538,13 @@ static void choose_groups_pair(int m_tiles, int n_tiles, int BN, int R, int pair
   *n_groups = (n_tiles + best_gs - 1) / best_gs;
 }
 
-template <int BN, int R, int G>
+// n_probs problems as independent work items (S == 1), or n_probs SOURCES summed into probs[0].y (S > 1)
+template <int BN, int R, int G, int S>
 static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, cudaStream_t st) {
-  using C = PairCfg<BN, R>;
+  using C = PairCfg<BN, R, S>;
   static bool attr_set = false;
   if (!attr_set) {
-    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R, G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   GemmGroup<G> gm;
@@ -527,7 +554,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
     if (rc != SDT_OK) return rc;
     rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);
     if (rc != SDT_OK) return rc;
-    gm.y[q] = reinterpret_cast<uint8_t*>(pr.y);
+    gm.y[q] = reinterpret_cast<uint8_t*>(S > 1 ? probs[0].y : pr.y);
     if (R > 0) {
       rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
       if (rc != SDT_OK) return rc;
@@ -543,16 +570,17 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
   PairParams p;
   p.scaling = scaling;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.n_probs = n_probs;
+  p.n_probs = S > 1 ? 1 : n_probs;
+  p.n_src = S > 1 ? n_probs : 1;
   p.has_bias = probs[0].bias != nullptr ? 1 : 0;
   p.trace = reinterpret_cast<long long*>(debug_get(10));
   const int m_tiles = (int)((M + 2 * C::BM - 1) / (2 * C::BM));
   p.n_tiles = (int)((N + BN - 1) / BN);
   const int pairs_max = num_sms() / 2;
-  choose_groups_pair(m_tiles * n_probs, p.n_tiles, BN, R, pairs_max, &p.group_size, &p.n_groups);
-  p.n_items = m_tiles * n_probs * p.n_groups;
+  choose_groups_pair(m_tiles * p.n_probs, p.n_tiles, BN, p.n_src * R, pairs_max, &p.group_size, &p.n_groups);
+  p.n_items = m_tiles * p.n_probs * p.n_groups;
   const int pairs = p.n_items < pairs_max ? p.n_items : pairs_max;
-  lora_gemm_pair_kernel<BN, R, G><<<2 * pairs, kPairThreads, C::SMEM_BYTES, st>>>(gm, p);
+  lora_gemm_pair_kernel<BN, R, G, S><<<2 * pairs, kPairThreads, C::SMEM_BYTES, st>>>(gm, p);
   SDT_LAUNCH_OK("lora_gemm_pair");
   return SDT_OK;
 }
@@ -561,7 +589,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
 int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, int r,
                               cudaStream_t st) {
   const bool bn160 = (N % 160 == 0) || (N % 128 != 0 && N > 128);
-#define SDT_PAIR(BN, R, G) return launch_pair<BN, R, G>(probs, n_probs, scaling, M, K, N, st)
+#define SDT_PAIR(BN, R, G) return launch_pair<BN, R, G, 1>(probs, n_probs, scaling, M, K, N, st)
 #define SDT_PAIR_R(BN, G)                                                                     \
   switch (r) { case 16: SDT_PAIR(BN, 16, G); case 32: SDT_PAIR(BN, 32, G); default: SDT_PAIR(BN, 64, G); }
   // wide tiles (more FLOP per byte brought into the SM) when the rank accumulators still fit next to two 224-column
@@ -577,6 +605,25 @@ int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scali
   if (bn160) { SDT_PAIR_R(160, kMaxGroup) } else { SDT_PAIR_R(128, kMaxGroup) }
 #undef SDT_PAIR_R
 #undef SDT_PAIR
+}
+
+// Summed sources: Y = sum_s X_s W_s^T + (scaling X_s la_s^T) lb_s^T  with T_s = scaling X_s la_s^T written to probs[s].t_out.
+// The input gradient of projections that read ONE tensor (q / k / v): X_s = dY_s, W_s = W_s^T [K,N], la_s = B_s^T, lb_s = A_s^T.
+// 2 or 3 sources, padded rank 16 or 32 (three rank-64 accumulators do not fit in TMEM next to two main accumulators).
+bool lora_gemm_pair_sum_supported(int n_src, int64_t M, int64_t K, int64_t N, int r) {
+  return n_src >= 2 && n_src <= 3 && (r == 16 || r == 32) && M >= 256 && K >= 64 && K % 8 == 0 && N % 8 == 0;
+}
+int lora_gemm_pair_sum_bf16(const LoraProblem* probs, int n_src, float scaling, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st) {
+  SDT_REQUIRE(lora_gemm_pair_sum_supported(n_src, M, K, N, r), SDT_ERR_UNSUPPORTED,
+              "lora_gemm(sum): needs 2..3 sources, padded rank 16/32, M >= 256 (got %d sources, r=%d, M=%lld)", n_src, r, (long long)M);
+  for (int q = 0; q < n_src; ++q) {
+    const LoraProblem& pr = probs[q];
+    SDT_REQUIRE(pr.x && pr.w && pr.la && pr.lb && probs[0].y && pr.bias == nullptr, SDT_ERR_ARG, "lora_gemm(sum): bad operands in source %d", q);
+    SDT_REQUIRE(aligned16(pr.x) && aligned16(pr.w) && aligned16(pr.la) && aligned16(pr.lb) && aligned16(probs[0].y) && aligned16(pr.t_out),
+                SDT_ERR_ARG, "lora_gemm(sum): pointers must be 16-byte aligned (source %d)", q);
+  }
+  if (r == 16) return launch_pair<160, 16, kMaxGroup, 3>(probs, n_src, scaling, M, K, N, st);
+  return launch_pair<160, 32, kMaxGroup, 3>(probs, n_src, scaling, M, K, N, st);
 }
 
 }  // namespace sdt

@@ -200,6 +200,38 @@ class _LoRAProjectionGroup(torch.autograd.Function):
         G = len(mods)
         saved = ctx.saved_tensors
         x2, ts, lora_params = saved[0], saved[1:1 + G], saved[1 + G:]
+        M, K = x2.shape
+        N = mods[0].out_features
+        lib = _lib.load()
+        ops = [m._packed_operands() for m in mods]
+        R = ops[0].R
+        # every projection received a gradient and the shape qualifies: dX of all of them in ONE launch (summed sources)
+        if (ctx.need_dx and all(dy is not None for dy in dys)
+                and lib.sdt_lora_linear_bwd_group_supported(G, M, K, N, R)):
+            st = _lib.stream_ptr()
+            dys = [dy.contiguous() if dy.dtype == x2.dtype else dy.to(x2.dtype).contiguous() for dy in dys]
+            dx = torch.empty_like(x2)
+            gws = [torch.empty(M, R, dtype=torch.bfloat16, device=x2.device) for _ in mods]
+            grads, dAs, dBs = [], [], []
+            for m in mods:
+                if m._grad_A is not None:
+                    dAs.append(m._grad_A); dBs.append(m._grad_B)
+                    grads += [None, None]
+                else:
+                    dA = torch.zeros(m.r, K, dtype=torch.float32, device=x2.device)
+                    dB = torch.zeros(N, m.r, dtype=torch.float32, device=x2.device)
+                    dAs.append(dA); dBs.append(dB)
+                    grads += [dA, dB]
+            probs = (_lib.LoraBwdProblem * G)(*[
+                _lib.LoraBwdProblem(dy.data_ptr(), x2.data_ptr(), m._weight_t_bf16().data_ptr(), o.At_p.data_ptr(), o.Bt_p.data_ptr(),
+                                    t.data_ptr(), g.data_ptr(), dA.data_ptr(), dB.data_ptr())
+                for dy, m, o, t, g, dA, dB in zip(dys, mods, ops, ts, gws, dAs, dBs)])
+            ev0 = _ev() if PROFILE is not None else None
+            _lib.check(lib.sdt_lora_linear_bwd_group(ctypes.addressof(probs), G, mods[0].scaling, dx.data_ptr(), M, K, N, R,
+                                                     mods[0].r, _lib.SDT_BF16, st), "sdt_lora_linear_bwd_group")
+            if ev0 is not None:
+                PROFILE.append(("bwd", M, K, N, R, G, True, ev0, _ev()))
+            return (dx, None, *grads)
         dx = None
         grads = []
         for g, (m, dy) in enumerate(zip(mods, dys)):

@@ -188,6 +188,9 @@ GROUP_CASES = [
     ((2, 77, 768), 768, 320, 4, 1, False, 4),       # k/v of two cross-attentions on one text context (M = 154 < 256)
     ((8, 77, 768), 768, 1280, 64, 64, True, 2),     # k/v, rank 64, with bias, M = 616 -> pair kernel
     ((1, 130, 1024), 1024, 640, 32, 16, False, 3),  # SD2.x context width, BN = 128 tiles
+    ((4, 128, 640), 640, 640, 32, 16, False, 3),    # rank 32: three 32-column rank accumulators fill TMEM exactly (summed dX)
+    ((2, 256, 320), 320, 640, 16, 1, False, 2),     # two sources, N != K
+    ((8, 4096, 320), 320, 320, 16, 1, False, 3),    # cfg2 level-0 q/k/v at full size (M = 32768)
 ]
 
 
