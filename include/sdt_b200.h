@@ -95,12 +95,14 @@ int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt, const voi
  * dX is written once; G_q is written to g_ws of each problem and the dA / dB reductions follow, one launch per projection.
  * 2..3 problems of identical (M, K, N, r, scaling); padded rank 16 or 32; M >= 256 (sdt_lora_linear_bwd_group_supported says
  * whether a shape qualifies; otherwise call sdt_lora_linear_bwd per site and add).  `problems` is a HOST array; bf16 only.
+ * dx == NULL (the input needs no gradient: to_k / to_v on the text context): up to SDT_MAX_GROUP problems, the rank
+ * projections G_q = s dY_q B_q run as the work items of one launch (wt may be NULL).
  */
 typedef struct {
   const void* dy; const void* x; const void* wt; const void* At; const void* Bt; const void* t_save;
   void* g_ws; float* dA; float* dB;
 } sdt_lora_bwd_problem;
-int sdt_lora_linear_bwd_group_supported(int n_problems, int64_t M, int64_t K, int64_t N, int r);
+int sdt_lora_linear_bwd_group_supported(int n_problems, int need_dx, int64_t M, int64_t K, int64_t N, int r);
 int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems /* host */, int n_problems, float scaling, void* dx,
                               int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* stream);
 

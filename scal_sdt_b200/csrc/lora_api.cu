@@ -87,29 +87,32 @@ extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt
   return SDT_ERR_UNSUPPORTED;
 }
 
-extern "C" int sdt_lora_linear_bwd_group_supported(int n_problems, int64_t M, int64_t K, int64_t N, int r) {
+extern "C" int sdt_lora_linear_bwd_group_supported(int n_problems, int need_dx, int64_t M, int64_t K, int64_t N, int r) {
+  if (!need_dx)      // G_q = s dY_q B_q of up to SDT_MAX_GROUP projections as the work items of one launch
+    return (n_problems >= 2 && n_problems <= SDT_MAX_GROUP && (r == 16 || r == 32 || r == 64)) ? 1 : 0;
   // the summed GEMM contracts over N (features of dY) and produces K columns of dX
   return lora_gemm_pair_sum_supported(n_problems, M, N, K, r) ? 1 : 0;
 }
 
 extern "C" int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems, int n_problems, float scaling, void* dx, int64_t M,
                                          int64_t K, int64_t N, int r, int r_true, int dtype, void* stream) {
-  SDT_REQUIRE(problems != nullptr && dx != nullptr, SDT_ERR_ARG, "sdt_lora_linear_bwd_group: null pointer");
+  SDT_REQUIRE(problems != nullptr, SDT_ERR_ARG, "sdt_lora_linear_bwd_group: null pointer");
   SDT_REQUIRE(dtype == SDT_BF16, SDT_ERR_UNSUPPORTED, "sdt_lora_linear_bwd_group: bf16 only (there is no fallback)");
   SDT_REQUIRE(M > 0 && K > 0 && N > 0, SDT_ERR_ARG, "sdt_lora_linear_bwd_group: bad sizes");
-  SDT_REQUIRE(lora_gemm_pair_sum_supported(n_problems, M, N, K, r), SDT_ERR_UNSUPPORTED,
-              "sdt_lora_linear_bwd_group: needs 2..3 projections, padded rank 16/32, M >= 256 (got %d, r=%d, M=%lld): use "
-              "sdt_lora_linear_bwd per site", n_problems, r, (long long)M);
+  SDT_REQUIRE(sdt_lora_linear_bwd_group_supported(n_problems, dx != nullptr, M, K, N, r), SDT_ERR_UNSUPPORTED,
+              "sdt_lora_linear_bwd_group: unsupported group (%d projections, r=%d, M=%lld, dx %s): use sdt_lora_linear_bwd per site",
+              n_problems, r, (long long)M, dx ? "wanted" : "not wanted");
   cudaStream_t st = (cudaStream_t)stream;
-  LoraProblem pr[3];
+  LoraProblem pr[SDT_MAX_GROUP];
   for (int q = 0; q < n_problems; ++q) {
     const sdt_lora_bwd_problem& b = problems[q];
-    SDT_REQUIRE(b.dy && b.x && b.wt && b.At && b.Bt && b.t_save && b.g_ws && b.dA && b.dB, SDT_ERR_ARG,
+    SDT_REQUIRE(b.dy && b.x && b.At && b.Bt && b.t_save && b.g_ws && b.dA && b.dB && (dx == nullptr || b.wt), SDT_ERR_ARG,
                 "sdt_lora_linear_bwd_group: null pointer in problem %d", q);
     // G_q = s dY_q B_q ; dX += dY_q W_q + G_q A_q   -- the forward kernel's roles with (dY, W^T, B^T, A^T)
-    pr[q] = LoraProblem{b.dy, b.wt, nullptr, b.Bt, b.At, dx, b.g_ws};
+    pr[q] = LoraProblem{b.dy, dx ? b.wt : nullptr, nullptr, b.Bt, dx ? b.At : nullptr, dx, b.g_ws};
   }
-  int rc = lora_gemm_pair_sum_bf16(pr, n_problems, scaling, M, /*contraction*/ N, /*outputs*/ K, r, st);
+  int rc = dx != nullptr ? lora_gemm_pair_sum_bf16(pr, n_problems, scaling, M, /*contraction*/ N, /*outputs*/ K, r, st)
+                         : lora_gemm_group_bf16(pr, n_problems, scaling, M, N, K, r, /*main=*/false, st);
   if (rc != SDT_OK) return rc;
   for (int q = 0; q < n_problems; ++q) {
     const sdt_lora_bwd_problem& b = problems[q];

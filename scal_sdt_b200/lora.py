@@ -205,12 +205,13 @@ class _LoRAProjectionGroup(torch.autograd.Function):
         lib = _lib.load()
         ops = [m._packed_operands() for m in mods]
         R = ops[0].R
-        # every projection received a gradient and the shape qualifies: dX of all of them in ONE launch (summed sources)
-        if (ctx.need_dx and all(dy is not None for dy in dys)
-                and lib.sdt_lora_linear_bwd_group_supported(G, M, K, N, R)):
+        # every projection received a gradient and the shape qualifies: dX of all of them in ONE launch (summed sources);
+        # without dX (text context) the rank projections G = s dY B of the group are the work items of one launch
+        if (all(dy is not None for dy in dys)
+                and lib.sdt_lora_linear_bwd_group_supported(G, int(ctx.need_dx), M, K, N, R)):
             st = _lib.stream_ptr()
             dys = [dy.contiguous() if dy.dtype == x2.dtype else dy.to(x2.dtype).contiguous() for dy in dys]
-            dx = torch.empty_like(x2)
+            dx = torch.empty_like(x2) if ctx.need_dx else None
             gws = [torch.empty(M, R, dtype=torch.bfloat16, device=x2.device) for _ in mods]
             grads, dAs, dBs = [], [], []
             for m in mods:
@@ -223,14 +224,14 @@ class _LoRAProjectionGroup(torch.autograd.Function):
                     dAs.append(dA); dBs.append(dB)
                     grads += [dA, dB]
             probs = (_lib.LoraBwdProblem * G)(*[
-                _lib.LoraBwdProblem(dy.data_ptr(), x2.data_ptr(), m._weight_t_bf16().data_ptr(), o.At_p.data_ptr(), o.Bt_p.data_ptr(),
-                                    t.data_ptr(), g.data_ptr(), dA.data_ptr(), dB.data_ptr())
+                _lib.LoraBwdProblem(dy.data_ptr(), x2.data_ptr(), m._weight_t_bf16().data_ptr() if ctx.need_dx else None,
+                                    o.At_p.data_ptr(), o.Bt_p.data_ptr(), t.data_ptr(), g.data_ptr(), dA.data_ptr(), dB.data_ptr())
                 for dy, m, o, t, g, dA, dB in zip(dys, mods, ops, ts, gws, dAs, dBs)])
             ev0 = _ev() if PROFILE is not None else None
-            _lib.check(lib.sdt_lora_linear_bwd_group(ctypes.addressof(probs), G, mods[0].scaling, dx.data_ptr(), M, K, N, R,
+            _lib.check(lib.sdt_lora_linear_bwd_group(ctypes.addressof(probs), G, mods[0].scaling, _lib.ptr(dx), M, K, N, R,
                                                      mods[0].r, _lib.SDT_BF16, st), "sdt_lora_linear_bwd_group")
             if ev0 is not None:
-                PROFILE.append(("bwd", M, K, N, R, G, True, ev0, _ev()))
+                PROFILE.append(("bwd", M, K, N, R, G, ctx.need_dx, ev0, _ev()))
             return (dx, None, *grads)
         dx = None
         grads = []

@@ -234,3 +234,23 @@ def test_group_falls_back_to_per_site_launches_on_mixed_shapes(sdt_lib):
     assert not groupable([a, b], x.reshape(-1, 320))
     ya, yb = project_group([a, b], x)
     assert torch.equal(ya, a(x)) and torch.equal(yb, b(x))
+
+
+@pytest.mark.parametrize("G,cout,rank", [(4, 320, 4), (2, 1280, 16), (3, 640, 64)])
+def test_grouped_projection_backward_without_input_gradient(sdt_lib, G, cout, rank):
+    """to_k / to_v of cross-attentions read the text context, which needs no gradient: the group's rank projections
+    G = s dY B run as one launch; dA / dB must match the oracle."""
+    from scal_sdt_b200.lora import project_group
+    pairs = [make_pair("linear", 768, cout, rank, 2, False, 300 + g, torch.bfloat16) for g in range(G)]
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(8, 77, 768, generator=gen).bfloat16().float()
+    dys = [torch.randn(8, 77, cout, generator=gen).bfloat16().float() for _ in range(G)]
+    yrs = [ref(x.double()) for ref, _ in pairs]
+    torch.autograd.backward(yrs, [d.double() for d in dys])
+    mods = [ours for _, ours in pairs]
+    yos = project_group(mods, x.to(DEV).bfloat16())            # no requires_grad on the input
+    torch.autograd.backward(yos, [d.to(DEV).bfloat16() for d in dys])
+    for g in range(G):
+        assert rel(yos[g], yrs[g]) <= 2e-2
+        assert rel(mods[g].lora_A.grad, pairs[g][0].lora_A.grad) <= 2e-2, ("dA", g, rel(mods[g].lora_A.grad, pairs[g][0].lora_A.grad))
+        assert rel(mods[g].lora_B.grad, pairs[g][0].lora_B.grad) <= 2e-2, ("dB", g)
