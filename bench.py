@@ -417,14 +417,17 @@ def ours_main(args):
         # DRAM bytes per GEMM launch from the committed ncu pass over one training step (dram__bytes_read + write summed over
         # the lora_gemm* launches / their count); bench.py cannot run ncu itself
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_v5_lora_kernels_per_step_ncu.json")
-        if os.path.exists(tpath):
+        for tname in ("r01_v15_kernels_per_step_ncu.json", "r01_v5_lora_kernels_per_step_ncu.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if not os.path.exists(tpath):
+                continue
             with open(tpath) as f:
                 tj = json.load(f)
             gl = [v for k, v in tj.items() if "lora_gemm" in k]
             if gl:
                 traffic = sum((v["dram_read_MB"] + v["dram_write_MB"]) * 1e6 for v in gl) / sum(v["launches"] for v in gl)
-                traffic_src = "profiles/r01_v5_lora_kernels_per_step_ncu.json (avg over the forward + dX GEMM launches of a step)"
+                traffic_src = f"profiles/{tname} (avg over the forward + dX GEMM launches of a step)"
+                break
         alg_bytes = sum(2.0 * (M * K + G * (K * N + R * (K + N) + M * N + M * R)) for kind, M, K, N, R, G, *_ in fwd_sites) / max(n_fwd, 1)
         dx_flops = sum(G * (2.0 * M * K * N + 2.0 * M * R * (K + N)) for kind, M, K, N, R, G, dx, *_ in bwd_sites if dx) + \
             sum(G * 2.0 * M * R * N for kind, M, K, N, R, G, dx, *_ in bwd_sites if not dx)
