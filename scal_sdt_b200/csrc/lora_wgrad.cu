@@ -185,9 +185,12 @@ static int launch_wgrad_pair(const void* u0, const void* v0, float* out0, int64_
   p.M = (int)M; p.r_true = r_true;
   const int f_blocks = p.prob[0].f_blocks + p.prob[1].f_blocks;
   const int m_chunks = (int)((M + C::BMK - 1) / C::BMK);
-  // enough CTAs for ~2 per SM, but at least 8 stages of work each
-  int splits = (2 * num_sms() + f_blocks - 1) / f_blocks;
-  if (splits > (m_chunks + 7) / 8) splits = (m_chunks + 7) / 8;
+  // enough CTAs for one per SM, at least 8 stages of work each (tools/wgrad_ab.py: one CTA per SM beats two by ~10 % on the
+  // 22-190 MB shapes -- fewer red.global.add partials -- and ties on the small ones).  sdt_debug_set(15, min | per_sm << 8) overrides.
+  const int min_chunks = (g_dbg[15] & 0xff) ? (int)(g_dbg[15] & 0xff) : 8;
+  const int per_sm = (g_dbg[15] >> 8) ? (int)(g_dbg[15] >> 8) : 1;
+  int splits = (per_sm * num_sms() + f_blocks - 1) / f_blocks;
+  if (splits > (m_chunks + min_chunks - 1) / min_chunks) splits = (m_chunks + min_chunks - 1) / min_chunks;
   if (splits < 1) splits = 1;
   const int chunks_per_split = (m_chunks + splits - 1) / splits;
   p.rows_per_split = chunks_per_split * C::BMK;
