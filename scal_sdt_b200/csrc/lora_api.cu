@@ -14,6 +14,8 @@ int lora_fwd_f32(const float* x, const float* w, const float* bias, const float*
 int lora_bwd_f32(const float* dy, const float* x, const float* w, const float* A, const float* B, const float* t_save,
                  float scaling, float* dx, float* g_ws, float* dA, float* dB, int64_t M, int64_t K, int64_t N, int r,
                  cudaStream_t st);
+struct WgradSite { const void* x; const void* g; float* dA; const void* dy; const void* ts; float* dB; };
+int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, cudaStream_t st);
 void debug_set(int key, uint64_t value);
 }  // namespace sdt
 
@@ -114,12 +116,13 @@ extern "C" int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems, i
   int rc = dx != nullptr ? lora_gemm_pair_sum_bf16(pr, n_problems, scaling, M, /*contraction*/ N, /*outputs*/ K, r, st)
                          : lora_gemm_group_bf16(pr, n_problems, scaling, M, N, K, r, /*main=*/false, st);
   if (rc != SDT_OK) return rc;
+  // the dA / dB reductions of the whole group: one launch
+  WgradSite sites[SDT_MAX_GROUP];
   for (int q = 0; q < n_problems; ++q) {
     const sdt_lora_bwd_problem& b = problems[q];
-    rc = lora_wgrad_pair_bf16(b.x, b.g_ws, b.dA, K, b.dy, b.t_save, b.dB, N, M, r, r_true, st);
-    if (rc != SDT_OK) return rc;
+    sites[q] = WgradSite{b.x, b.g_ws, b.dA, b.dy, b.t_save, b.dB};
   }
-  return SDT_OK;
+  return lora_wgrad_multi_bf16(sites, n_problems, K, N, M, r, r_true, st);
 }
 
 extern "C" int sdt_debug_set(int key, uint64_t value) {

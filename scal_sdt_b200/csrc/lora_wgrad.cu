@@ -31,12 +31,18 @@ struct WgradCfg {
   static constexpr int TMEM_COLS = R < 32 ? 32 : R;
 };
 
-struct WgradProblem {
-  float* out;             // dA [r_true,F] (transposed = 1) or dB [F,r_true] (transposed = 0)
-  int F, transposed, f_blocks;
+// One launch covers the dA and dB reductions of up to kWgradSites sites (q / k / v of a self-attention, k / v of two
+// cross-attentions): 2 sub-problems per site, each a range of blockIdx.x.  The tensor maps and pointers sit in one
+// __grid_constant__ block that is indexed in parameter space.
+constexpr int kWgradSites = 4, kWgradSubs = 2 * kWgradSites;
+struct WgradGroup {
+  CUtensorMap u[kWgradSubs], v[kWgradSubs];
+  float* out[kWgradSubs];          // dA [r_true,F] (transposed = 1) or dB [F,r_true] (transposed = 0)
+  int F[kWgradSubs], transposed[kWgradSubs];
+  int f_begin[kWgradSubs + 1];     // first blockIdx.x of every sub-problem (prefix sums of its 128-feature blocks)
+  int n_subs;
 };
 struct WgradParams {
-  WgradProblem prob[2];   // one launch covers dA (problem 0) and dB (problem 1): blockIdx.x < prob[0].f_blocks -> problem 0
   int M, r_true;
   int rows_per_split;     // multiple of 64
   // descriptors are host-built so that the layout constants live in one place (and can be probed)
@@ -46,8 +52,7 @@ struct WgradParams {
 
 template <int R>
 __global__ void __launch_bounds__(128, 1)
-lora_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__ CUtensorMap tm_v0,
-                  const __grid_constant__ CUtensorMap tm_u1, const __grid_constant__ CUtensorMap tm_v1, const WgradParams p) {
+lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
   using C = WgradCfg<R>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -58,14 +63,13 @@ lora_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u0, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int which = (int)blockIdx.x >= p.prob[0].f_blocks ? 1 : 0;
-  WgradProblem pr;        // explicit selects: dynamic indexing of the param struct would spill it to local memory
-  pr.out = which ? p.prob[1].out : p.prob[0].out;
-  pr.F = which ? p.prob[1].F : p.prob[0].F;
-  pr.transposed = which ? p.prob[1].transposed : p.prob[0].transposed;
-  const CUtensorMap* tm_u = which ? &tm_u1 : &tm_u0;
-  const CUtensorMap* tm_v = which ? &tm_v1 : &tm_v0;
-  const int f0 = ((int)blockIdx.x - (which ? p.prob[0].f_blocks : 0)) * C::BF;
+  int which = 0;
+  while (which + 1 < gw.n_subs && (int)blockIdx.x >= gw.f_begin[which + 1]) ++which;
+  float* const out = gw.out[which];
+  const int F = gw.F[which], transposed = gw.transposed[which];
+  const CUtensorMap* tm_u = &gw.u[which];
+  const CUtensorMap* tm_v = &gw.v[which];
+  const int f0 = ((int)blockIdx.x - gw.f_begin[which]) * C::BF;
   const int m_begin = blockIdx.y * p.rows_per_split;
   const int m_end = min(m_begin + p.rows_per_split, p.M);
   const int nk = (m_end - m_begin + C::BMK - 1) / C::BMK;
@@ -127,12 +131,12 @@ lora_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u0, const __grid_consta
       uint32_t v[16];
       tmem_ld_x16(taddr + c * 16, v);
       tmem_ld_wait();
-      if (f < pr.F) {
+      if (f < F) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int jj = c * 16 + j;
           if (jj < p.r_true) {
-            float* dst = pr.transposed ? pr.out + (size_t)jj * pr.F + f : pr.out + (size_t)f * p.r_true + jj;
+            float* dst = transposed ? out + (size_t)jj * F + f : out + (size_t)f * p.r_true + jj;
             atomicAdd(dst, __uint_as_float(v[j]));
           }
         }
@@ -152,10 +156,13 @@ static uint64_t g_dbg[16] = {0};
 void debug_set(int key, uint64_t value) { if (key >= 0 && key < 16) g_dbg[key] = value; }
 uint64_t debug_get(int key) { return (key >= 0 && key < 16) ? g_dbg[key] : 0; }
 
+struct WgradSite {       // one LoRA site: dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]
+  const void* x; const void* g; float* dA;
+  const void* dy; const void* ts; float* dB;
+};
+
 template <int R>
-static int launch_wgrad_pair(const void* u0, const void* v0, float* out0, int64_t F0, bool tr0,
-                             const void* u1, const void* v1, float* out1, int64_t F1, bool tr1,
-                             int64_t M, int r_true, cudaStream_t st) {
+static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r_true, cudaStream_t st) {
   using C = WgradCfg<R>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -163,27 +170,28 @@ static int launch_wgrad_pair(const void* u0, const void* v0, float* out0, int64_
     attr_set = true;
   }
   const TmapSwizzle vsw = R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32);
-  CUtensorMap tm_u0, tm_v0, tm_u1, tm_v1;
-  int rc = make_tmap_2d_bf16(&tm_u0, u0, M, F0, F0 * 2, C::BMK, 64, TMAP_SW_128);
-  if (rc != SDT_OK) return rc;
-  rc = make_tmap_2d_bf16(&tm_v0, v0, M, R, (uint64_t)R * 2, C::BMK, R, vsw);
-  if (rc != SDT_OK) return rc;
-  if (u1 != nullptr) {
-    rc = make_tmap_2d_bf16(&tm_u1, u1, M, F1, F1 * 2, C::BMK, 64, TMAP_SW_128);
+  WgradGroup gw;
+  gw.n_subs = 2 * n_sites;
+  int f_blocks = 0;
+  for (int q = 0; q < kWgradSubs; ++q) {
+    const WgradSite& site = sites[q / 2 < n_sites ? q / 2 : 0];       // unused slots repeat site 0 (never selected)
+    const bool is_dA = (q & 1) == 0;
+    const void* u = is_dA ? site.x : site.dy;
+    const void* v = is_dA ? site.g : site.ts;
+    const int64_t F = is_dA ? K : N;
+    int rc = make_tmap_2d_bf16(&gw.u[q], u, M, F, F * 2, C::BMK, 64, TMAP_SW_128);
     if (rc != SDT_OK) return rc;
-    rc = make_tmap_2d_bf16(&tm_v1, v1, M, R, (uint64_t)R * 2, C::BMK, R, vsw);
+    rc = make_tmap_2d_bf16(&gw.v[q], v, M, R, (uint64_t)R * 2, C::BMK, R, vsw);
     if (rc != SDT_OK) return rc;
-  } else {
-    tm_u1 = tm_u0;
-    tm_v1 = tm_v0;
+    gw.out[q] = is_dA ? site.dA : site.dB;
+    gw.F[q] = (int)F;
+    gw.transposed[q] = is_dA ? 1 : 0;
+    gw.f_begin[q] = f_blocks;
+    if (q < gw.n_subs) f_blocks += (int)((F + C::BF - 1) / C::BF);
   }
+  gw.f_begin[kWgradSubs] = f_blocks;
   WgradParams p;
-  p.prob[0].out = out0; p.prob[0].F = (int)F0; p.prob[0].transposed = tr0 ? 1 : 0;
-  p.prob[0].f_blocks = (int)((F0 + C::BF - 1) / C::BF);
-  p.prob[1].out = out1; p.prob[1].F = (int)F1; p.prob[1].transposed = tr1 ? 1 : 0;
-  p.prob[1].f_blocks = u1 != nullptr ? (int)((F1 + C::BF - 1) / C::BF) : 0;
   p.M = (int)M; p.r_true = r_true;
-  const int f_blocks = p.prob[0].f_blocks + p.prob[1].f_blocks;
   const int m_chunks = (int)((M + C::BMK - 1) / C::BMK);
   // enough CTAs for one per SM, at least 8 stages of work each (tools/wgrad_ab.py: one CTA per SM beats two by ~10 % on the
   // 22-190 MB shapes -- fewer red.global.add partials -- and ties on the small ones).  sdt_debug_set(15, min | per_sm << 8) overrides.
@@ -209,25 +217,35 @@ static int launch_wgrad_pair(const void* u0, const void* v0, float* out0, int64_
   if (g_dbg[4]) p.a_step = (uint32_t)g_dbg[5];
   if (g_dbg[6]) p.b_step = (uint32_t)g_dbg[7];
   if (g_dbg[8]) p.idesc = (uint32_t)g_dbg[9];
-  lora_wgrad_kernel<R><<<dim3(f_blocks, splits), 128, C::SMEM_BYTES, st>>>(tm_u0, tm_v0, tm_u1, tm_v1, p);
+  lora_wgrad_kernel<R><<<dim3(f_blocks, splits), 128, C::SMEM_BYTES, st>>>(gw, p);
   SDT_LAUNCH_OK("lora_wgrad");
   return SDT_OK;
+}
+
+// dA / dB of n_sites same-shape sites (1..kWgradSites) in ONE launch
+int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, cudaStream_t st) {
+  SDT_REQUIRE(sites != nullptr && n_sites >= 1 && n_sites <= kWgradSites, SDT_ERR_ARG, "lora_wgrad: 1..%d sites per launch (got %d)",
+              kWgradSites, n_sites);
+  for (int q = 0; q < n_sites; ++q)
+    SDT_REQUIRE(sites[q].x && sites[q].g && sites[q].dA && sites[q].dy && sites[q].ts && sites[q].dB, SDT_ERR_ARG,
+                "lora_wgrad: null pointer (site %d)", q);
+  SDT_REQUIRE(M > 0 && K > 0 && N > 0 && K % 8 == 0 && N % 8 == 0, SDT_ERR_ARG, "lora_wgrad: bad sizes M=%lld K=%lld N=%lld",
+              (long long)M, (long long)K, (long long)N);
+  SDT_REQUIRE(r_true >= 1 && r_true <= r, SDT_ERR_ARG, "lora_wgrad: r_true=%d outside [1,%d]", r_true, r);
+  switch (r) {
+    case 16: return launch_wgrad<16>(sites, n_sites, K, N, M, r_true, st);
+    case 32: return launch_wgrad<32>(sites, n_sites, K, N, M, r_true, st);
+    case 64: return launch_wgrad<64>(sites, n_sites, K, N, M, r_true, st);
+  }
+  set_error("lora_wgrad: padded rank must be 16, 32 or 64 (got %d)", r);
+  return SDT_ERR_UNSUPPORTED;
 }
 
 // dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]  in ONE launch
 int lora_wgrad_pair_bf16(const void* x, const void* g, float* dA, int64_t K, const void* dy, const void* ts, float* dB,
                          int64_t N, int64_t M, int r, int r_true, cudaStream_t st) {
-  SDT_REQUIRE(x && g && dA && dy && ts && dB, SDT_ERR_ARG, "lora_wgrad: null pointer");
-  SDT_REQUIRE(M > 0 && K > 0 && N > 0 && K % 8 == 0 && N % 8 == 0, SDT_ERR_ARG, "lora_wgrad: bad sizes M=%lld K=%lld N=%lld",
-              (long long)M, (long long)K, (long long)N);
-  SDT_REQUIRE(r_true >= 1 && r_true <= r, SDT_ERR_ARG, "lora_wgrad: r_true=%d outside [1,%d]", r_true, r);
-  switch (r) {
-    case 16: return launch_wgrad_pair<16>(x, g, dA, K, true, dy, ts, dB, N, false, M, r_true, st);
-    case 32: return launch_wgrad_pair<32>(x, g, dA, K, true, dy, ts, dB, N, false, M, r_true, st);
-    case 64: return launch_wgrad_pair<64>(x, g, dA, K, true, dy, ts, dB, N, false, M, r_true, st);
-  }
-  set_error("lora_wgrad: padded rank must be 16, 32 or 64 (got %d)", r);
-  return SDT_ERR_UNSUPPORTED;
+  const WgradSite site{x, g, dA, dy, ts, dB};
+  return lora_wgrad_multi_bf16(&site, 1, K, N, M, r, r_true, st);
 }
 
 }  // namespace sdt
