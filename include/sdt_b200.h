@@ -188,13 +188,18 @@ int sdt_geglu(const void* proj, const void* dout, void* out_or_dproj, int64_t M,
               void* stream);
 
 /* ---- f2: GroupNorm (+ SiLU) on channels-last bf16 activations [B, HW, C], frozen affine (gamma, beta f32[C]) ----
- * forward : stats f32[B,G,2] (written: per-group sum, sum of squares); y = act((x - mean) * rstd * gamma + beta)
- * backward: dx from (x, dout, stats); bstats f32[B,G,2] is scratch.  Needs C % 8 == 0 and C / G >= 8.
+ * chan_bias (NULL or bf16 [B, C]): the tensor that is normalised is x + chan_bias[b, c] -- the time-embedding add in front of
+ * norm2 of a ResNet block (diffusers ResnetBlock2D: hidden = hidden + temb[:, :, None, None]; hidden = norm2(hidden)) folded
+ * into the norm; x itself is not rewritten.
+ * forward : stats f32[B,G,2] (written: per-group sum, sum of squares); y = act((x' - mean) * rstd * gamma + beta), x' = x + chan_bias
+ * backward: dx (= dx') from (x, chan_bias, dout, stats); bstats f32[B,G,2] is scratch.  d chan_bias = sum over HW of dx (caller).
+ * Needs C % 8 == 0 and C / G >= 8.
  */
-int sdt_group_norm_nhwc(const void* x, const float* gamma, const float* beta, float* stats, void* y, int64_t B, int64_t HW,
-                        int C, int G, float eps, int silu, void* stream);
-int sdt_group_norm_nhwc_bwd(const void* x, const void* dout, const float* gamma, const float* beta, const float* stats,
-                            float* bstats, void* dx, int64_t B, int64_t HW, int C, int G, float eps, int silu, void* stream);
+int sdt_group_norm_nhwc(const void* x, const void* chan_bias, const float* gamma, const float* beta, float* stats, void* y,
+                        int64_t B, int64_t HW, int C, int G, float eps, int silu, void* stream);
+int sdt_group_norm_nhwc_bwd(const void* x, const void* chan_bias, const void* dout, const float* gamma, const float* beta,
+                            const float* stats, float* bstats, void* dx, int64_t B, int64_t HW, int C, int G, float eps, int silu,
+                            void* stream);
 
 /* ---- f2: LayerNorm over C of token-major bf16 activations [M, C], frozen affine (gamma, beta f32[C]), fused residual add ----
  * diffusers BasicTransformerBlock (the UNet loaded at modules/model.py:82-91): x = x + attn(...); h = norm(x).

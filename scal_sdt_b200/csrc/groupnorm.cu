@@ -59,15 +59,17 @@ enum { T_A = 0, T_BC = 1, T_SC = 2, T_SH = 3, T_D = 2, T_E = 3 };
 // one global-memory latency per CTA instead of C / blockDim of them (C = 2560 with 160 threads was 16 dependent rounds).
 //   kStatsBwd: rows A, Bc, Sc, Sh (backward statistics pass)        kApplyBwd: rows A, Bc, D, E        neither: A, Bc
 //   kHalf (SiLU variants): A and Bc are stored halved
+//   cbias (optional, bf16 [B, C]): the tensor that is normalised is x + cbias[b, c] (the time-embedding add in front of norm2
+//   of a ResNet block); every row is an affine function of x, so the bias folds into the constant terms
 template <bool kStatsBwd, bool kApplyBwd, bool kHalf>
 __device__ __forceinline__ void build_table(float* tab, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            const float* __restrict__ fstats, const float* __restrict__ bstats, int b,
-                                            const GnShape& s, float eps) {
+                                            const float* __restrict__ fstats, const float* __restrict__ bstats,
+                                            const uint16_t* __restrict__ cbias, int b, const GnShape& s, float eps) {
   constexpr int TU = 8;
   const float inv_n = 1.0f / ((float)s.HW * (float)s.cpg);
   const float ab = kHalf ? 0.5f : 1.0f;
   for (int cb = threadIdx.x; cb < s.C; cb += TU * blockDim.x) {
-    float gm[TU], bt[TU], f0[TU], f1[TU], b0[TU], b1[TU];
+    float gm[TU], bt[TU], f0[TU], f1[TU], b0[TU], b1[TU], tb[TU];
 #pragma unroll
     for (int t = 0; t < TU; ++t) {
       const int c = cb + t * blockDim.x;
@@ -75,6 +77,7 @@ __device__ __forceinline__ void build_table(float* tab, const float* __restrict_
         const size_t gi = ((size_t)b * s.G + c / s.cpg) * 2;
         gm[t] = __ldg(gamma + c);
         bt[t] = __ldg(beta + c);
+        tb[t] = cbias != nullptr ? __uint_as_float((uint32_t)cbias[(size_t)b * s.C + c] << 16) : 0.f;
         f0[t] = fstats[gi];
         f1[t] = fstats[gi + 1];
         if (kApplyBwd) { b0[t] = bstats[gi]; b1[t] = bstats[gi + 1]; }
@@ -87,17 +90,18 @@ __device__ __forceinline__ void build_table(float* tab, const float* __restrict_
         const float mean = f0[t] * inv_n;
         const float var = fmaxf(f1[t] * inv_n - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
+        // with x' = x + tb:  z = x' A + Bc = x A + (Bc + tb A);  xhat = x Sc + (Sh + tb Sc);  dx = A dz - (D + E tb) - E x
         tab[T_A * s.C + c] = ab * rstd * gm[t];
-        tab[T_BC * s.C + c] = ab * (bt[t] - mean * rstd * gm[t]);
+        tab[T_BC * s.C + c] = ab * (bt[t] + (tb[t] - mean) * rstd * gm[t]);
         if (kStatsBwd) {
           tab[T_SC * s.C + c] = rstd;
-          tab[T_SH * s.C + c] = -mean * rstd;
+          tab[T_SH * s.C + c] = (tb[t] - mean) * rstd;
         }
         if (kApplyBwd) {
           // group means of dzg and dzg*xhat (the statistics pass accumulated them times rstd)
           const float p1 = b0[t] * inv_n / rstd;
           const float p2 = b1[t] * inv_n / rstd;
-          tab[T_D * s.C + c] = rstd * (p1 - p2 * mean * rstd);
+          tab[T_D * s.C + c] = rstd * (p1 + p2 * (tb[t] - mean) * rstd);
           tab[T_E * s.C + c] = rstd * rstd * p2;
         }
       }
@@ -109,17 +113,22 @@ __device__ __forceinline__ void build_table(float* tab, const float* __restrict_
 template <bool BWD, bool SILU>
 __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dout, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ fstats, float* __restrict__ out_stats,
-                                GnShape s, float eps) {
+                                const uint16_t* __restrict__ cbias, GnShape s, float eps) {
   extern __shared__ float tab[];                 // BWD: [4][C] (A, Bc, Sc, Sh)
   __shared__ float acc[2 * 128];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) acc[i] = 0.f;
-  if (BWD) build_table<true, false, SILU>(tab, gamma, beta, fstats, nullptr, b, s, eps);
+  if (BWD) build_table<true, false, SILU>(tab, gamma, beta, fstats, nullptr, cbias, b, s, eps);
   __syncthreads();
   const int v = threadIdx.x % s.vecs, rp = threadIdx.x / s.vecs;
   const int c0 = v * 8;
   if (rp < s.rows_par) {
-    float tA[8], tB[8], tS[8], tH[8];
+    float tA[8], tB[8], tS[8], tH[8], tb[8];
+    if (!BWD) {                 // forward statistics of x + cbias
+      uint4 tbv = make_uint4(0, 0, 0, 0);
+      if (cbias != nullptr) tbv = *reinterpret_cast<const uint4*>(cbias + (size_t)b * s.C + c0);
+      unpack8(tbv, tb);
+    }
     if (BWD) {
       load8(tab + T_A * s.C + c0, tA);
       load8(tab + T_BC * s.C + c0, tB);
@@ -145,8 +154,9 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (!BWD) {
-          S[j] += xe[j];
-          Q[j] = fmaf(xe[j], xe[j], Q[j]);
+          const float xb = xe[j] + tb[j];
+          S[j] += xb;
+          Q[j] = fmaf(xb, xb, Q[j]);
         } else {
           float dz = de[j];
           if (SILU) dz *= silu_grad_x2(fmaf(xe[j], tA[j], tB[j]));      // 2 dz, against the halved A
@@ -194,10 +204,10 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* 
 template <bool BWD, bool SILU>
 __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dout, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ fstats, const float* __restrict__ bstats,
-                                uint16_t* __restrict__ out, GnShape s, float eps) {
+                                uint16_t* __restrict__ out, const uint16_t* __restrict__ cbias, GnShape s, float eps) {
   extern __shared__ float tab[];                 // forward [2][C] (A, Bc); backward [4][C] (A, Bc, D, E); A, Bc halved for SiLU
   const int b = blockIdx.y;
-  build_table<false, BWD, SILU>(tab, gamma, beta, fstats, bstats, b, s, eps);
+  build_table<false, BWD, SILU>(tab, gamma, beta, fstats, bstats, cbias, b, s, eps);
   __syncthreads();
   const int r_begin = blockIdx.x * s.rows_per_cta;
   const int n_rows = min(s.rows_per_cta, (int)(s.HW - r_begin));
@@ -303,14 +313,15 @@ using namespace sdt;
     GnShape sk = s;                                                          \
     dim3 grid;                                                               \
     if ((rc = gn_grid(KERNEL, &sk, B, SMEM, &grid)) != SDT_OK) return rc;    \
-    KERNEL<<<grid, sk.threads, SMEM, st>>>(__VA_ARGS__, sk, eps);            \
+    KERNEL<<<grid, sk.threads, SMEM, st>>>(__VA_ARGS__, cb, sk, eps);        \
     SDT_LAUNCH_OK(WHAT);                                                     \
   } while (0)
 
-extern "C" int sdt_group_norm_nhwc(const void* x, const float* gamma, const float* beta, float* stats, void* y, int64_t B,
-                                   int64_t HW, int C, int G, float eps, int silu, void* stream) {
+extern "C" int sdt_group_norm_nhwc(const void* x, const void* chan_bias, const float* gamma, const float* beta, float* stats, void* y,
+                                   int64_t B, int64_t HW, int C, int G, float eps, int silu, void* stream) {
   SDT_REQUIRE(x && gamma && beta && stats && y, SDT_ERR_ARG, "sdt_group_norm_nhwc: null pointer");
-  SDT_REQUIRE(aligned16(x) && aligned16(y), SDT_ERR_ARG, "sdt_group_norm_nhwc: pointers must be 16-byte aligned");
+  SDT_REQUIRE(aligned16(x) && aligned16(y) && aligned16(chan_bias), SDT_ERR_ARG, "sdt_group_norm_nhwc: pointers must be 16-byte aligned");
+  const uint16_t* cb = (const uint16_t*)chan_bias;
   GnShape s;
   int rc = gn_shape(&s, B, HW, C, G);
   if (rc != SDT_OK) return rc;
@@ -326,11 +337,13 @@ extern "C" int sdt_group_norm_nhwc(const void* x, const float* gamma, const floa
   return SDT_OK;
 }
 
-extern "C" int sdt_group_norm_nhwc_bwd(const void* x, const void* dout, const float* gamma, const float* beta,
+extern "C" int sdt_group_norm_nhwc_bwd(const void* x, const void* chan_bias, const void* dout, const float* gamma, const float* beta,
                                        const float* stats, float* bstats, void* dx, int64_t B, int64_t HW, int C, int G,
                                        float eps, int silu, void* stream) {
   SDT_REQUIRE(x && dout && gamma && beta && stats && bstats && dx, SDT_ERR_ARG, "sdt_group_norm_nhwc_bwd: null pointer");
-  SDT_REQUIRE(aligned16(x) && aligned16(dout) && aligned16(dx), SDT_ERR_ARG, "sdt_group_norm_nhwc_bwd: pointers must be 16-byte aligned");
+  SDT_REQUIRE(aligned16(x) && aligned16(dout) && aligned16(dx) && aligned16(chan_bias), SDT_ERR_ARG,
+              "sdt_group_norm_nhwc_bwd: pointers must be 16-byte aligned");
+  const uint16_t* cb = (const uint16_t*)chan_bias;
   GnShape s;
   int rc = gn_shape(&s, B, HW, C, G);
   if (rc != SDT_OK) return rc;

@@ -42,22 +42,27 @@ def geglu(proj: torch.Tensor) -> torch.Tensor:
 
 
 class _GroupNormNHWC(torch.autograd.Function):
-    """GroupNorm with frozen affine parameters (+ optional SiLU) on a channels-last bf16 tensor."""
+    """GroupNorm with frozen affine parameters (+ optional SiLU) on a channels-last bf16 tensor; ``chan_bias`` [B, C] (optional)
+    is added to the input on the fly (the time-embedding add of a ResNet block)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups, eps, silu):
+    def forward(ctx, x, chan_bias, gamma, beta, groups, eps, silu):
         B, C, H, W = x.shape
         y = torch.empty_like(x, memory_format=torch.channels_last)
         stats = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().sdt_group_norm_nhwc(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), y.data_ptr(),
-                                                   B, H * W, C, groups, eps, int(silu), _lib.stream_ptr()), "sdt_group_norm_nhwc")
-        ctx.save_for_backward(x, gamma, beta, stats)
+        cb = chan_bias.contiguous() if chan_bias is not None else None
+        _lib.check(_lib.load().sdt_group_norm_nhwc(x.data_ptr(), _lib.ptr(cb), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+                                                   y.data_ptr(), B, H * W, C, groups, eps, int(silu), _lib.stream_ptr()),
+                   "sdt_group_norm_nhwc")
+        ctx.save_for_backward(x, gamma, beta, stats, *([cb] if cb is not None else []))
         ctx.cfg = (groups, eps, silu)
+        ctx.has_bias = cb is not None
         return y
 
     @staticmethod
     def backward(ctx, dout):
-        x, gamma, beta, stats = ctx.saved_tensors
+        x, gamma, beta, stats, *rest = ctx.saved_tensors
+        cb = rest[0] if ctx.has_bias else None
         groups, eps, silu = ctx.cfg
         B, C, H, W = x.shape
         d = dout.contiguous(memory_format=torch.channels_last)
@@ -65,10 +70,13 @@ class _GroupNormNHWC(torch.autograd.Function):
             d = d.to(x.dtype)
         dx = torch.empty_like(x, memory_format=torch.channels_last)
         bstats = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().sdt_group_norm_nhwc_bwd(x.data_ptr(), d.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+        _lib.check(_lib.load().sdt_group_norm_nhwc_bwd(x.data_ptr(), _lib.ptr(cb), d.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                                        stats.data_ptr(), bstats.data_ptr(), dx.data_ptr(), B, H * W, C, groups,
                                                        eps, int(silu), _lib.stream_ptr()), "sdt_group_norm_nhwc_bwd")
-        return dx, None, None, None, None, None
+        dcb = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            dcb = dx.sum(dim=(2, 3), dtype=torch.float32).to(cb.dtype)      # the backward of the broadcast add
+        return dx, dcb, None, None, None, None, None
 
 
 def group_norm_nhwc_supported(norm: torch.nn.GroupNorm, x: torch.Tensor) -> bool:
@@ -78,15 +86,19 @@ def group_norm_nhwc_supported(norm: torch.nn.GroupNorm, x: torch.Tensor) -> bool
             and c <= 4096)
 
 
-def group_norm_act(norm: torch.nn.GroupNorm, x: torch.Tensor, silu: bool) -> torch.Tensor:
-    """``silu(norm(x))`` / ``norm(x)``: fused channels-last kernels when they apply, torch otherwise (host model code)."""
-    if group_norm_nhwc_supported(norm, x):
+def group_norm_act(norm: torch.nn.GroupNorm, x: torch.Tensor, silu: bool, chan_bias: torch.Tensor | None = None) -> torch.Tensor:
+    """``silu(norm(x + chan_bias[:, :, None, None]))`` / without SiLU / without the bias: fused channels-last kernels when they
+    apply, torch otherwise (host model code)."""
+    if group_norm_nhwc_supported(norm, x) and (chan_bias is None or (chan_bias.is_cuda and chan_bias.dtype == x.dtype
+                                                                       and chan_bias.shape == x.shape[:2])):
         cache = getattr(norm, "_sdt_affine_f32", None)
         key = (norm.weight.data_ptr(), norm.weight._version, norm.bias._version)
         if cache is None or cache[0] != key:
             cache = (key, norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous())
             norm._sdt_affine_f32 = cache
-        return _GroupNormNHWC.apply(x, cache[1], cache[2], norm.num_groups, float(norm.eps), bool(silu))
+        return _GroupNormNHWC.apply(x, chan_bias, cache[1], cache[2], norm.num_groups, float(norm.eps), bool(silu))
+    if chan_bias is not None:
+        x = x + chan_bias[:, :, None, None]
     y = norm(x)
     return torch.nn.functional.silu(y) if silu else y
 

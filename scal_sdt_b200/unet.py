@@ -81,8 +81,8 @@ class ResnetBlock2D(nn.Module):
 
     def forward(self, x, temb):
         h = self.conv1(group_norm_act(self.norm1, x, True))
-        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
-        h = self.conv2(group_norm_act(self.norm2, h, True))
+        # h + temb only feeds norm2: the broadcast add is folded into the norm (torch runs it as a non-vectorised kernel)
+        h = self.conv2(group_norm_act(self.norm2, h, True, chan_bias=self.time_emb_proj(F.silu(temb))))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h

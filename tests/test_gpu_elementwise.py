@@ -230,3 +230,35 @@ def test_group_norm_nhwc_forward_backward(sdt_lib, C, G, H, W, silu):
     yo.backward(dout.to(DEV))
     assert (yo.double().cpu() - yr).norm() <= 1e-2 * yr.norm()
     assert (xo.grad.double().cpu() - xr.grad).norm() <= 1e-2 * xr.grad.norm()
+
+
+@pytest.mark.parametrize("C,G,H,W,silu", [(320, 32, 16, 16, True), (1280, 32, 8, 8, True), (640, 32, 7, 5, False)])
+def test_group_norm_with_folded_time_embedding_bias(sdt_lib, C, G, H, W, silu):
+    """``silu(norm(h + temb[:, :, None, None]))`` with the broadcast add folded into the norm kernels: output, dX and the
+    bias gradient against fp64 autograd on the same bf16 operands."""
+    from scal_sdt_b200.fused import group_norm_act
+    torch.manual_seed(C + W)
+    norm = torch.nn.GroupNorm(G, C, eps=1e-5)
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.3)
+        norm.bias.normal_(0.0, 0.3)
+    x = (torch.randn(3, C, H, W) * 1.3 - 0.2).bfloat16()
+    tb = (torch.randn(3, C) * 0.8).bfloat16()
+    dout = torch.randn(3, C, H, W).bfloat16()
+    ref_norm = torch.nn.GroupNorm(G, C, eps=1e-5).double()
+    with torch.no_grad():
+        ref_norm.weight.copy_(norm.weight.bfloat16().double())
+        ref_norm.bias.copy_(norm.bias.bfloat16().double())
+    xr, tr = x.double().requires_grad_(True), tb.double().requires_grad_(True)
+    yr = ref_norm(xr + tr[:, :, None, None])
+    if silu:
+        yr = torch.nn.functional.silu(yr)
+    yr.backward(dout.double())
+    gn = norm.to(DEV).to(torch.bfloat16).requires_grad_(False)
+    xo = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    to = tb.to(DEV).requires_grad_(True)
+    yo = group_norm_act(gn, xo, silu, chan_bias=to)
+    yo.backward(dout.to(DEV))
+    assert (yo.double().cpu() - yr).norm() <= 1e-2 * yr.norm()
+    assert (xo.grad.double().cpu() - xr.grad).norm() <= 1e-2 * xr.grad.norm()
+    assert (to.grad.double().cpu() - tr.grad).norm() <= 2e-2 * tr.grad.norm()
