@@ -201,6 +201,12 @@ int sdt_group_norm_nhwc_bwd(const void* x, const void* chan_bias, const void* do
                             const float* stats, float* bstats, void* dx, int64_t B, int64_t HW, int C, int G, float eps, int silu,
                             void* stream);
 
+/* ---- f2: residual add with folded per-channel bias on channels-last bf16 [rows, C]: out = a + b + bias[c] (bias f32[C]) ----
+ * End of diffusers ResnetBlock2D: out = shortcut(x) + conv2(h); the convolutions run without bias and their frozen biases are
+ * added in this pass (torch adds each conv bias as a separate non-vectorised broadcast kernel).  C % 8 == 0.
+ */
+int sdt_residual_bias_add(const void* a, const void* b, const float* bias, void* out, int64_t rows, int C, void* stream);
+
 /* ---- f2: LayerNorm over C of token-major bf16 activations [M, C], frozen affine (gamma, beta f32[C]), fused residual add ----
  * diffusers BasicTransformerBlock (the UNet loaded at modules/model.py:82-91): x = x + attn(...); h = norm(x).
  * forward : res != NULL: xs_out = bf16(x + res) (the new residual stream) and y = LN(xs_out); res == NULL: y = LN(x).

@@ -682,3 +682,55 @@ extern "C" int sdt_geglu(const void* proj, const void* dout, void* out_or_dproj,
   SDT_LAUNCH_OK("geglu");
   return SDT_OK;
 }
+
+
+// ---- f2: residual add with a folded per-channel bias, channels-last / token-major bf16 [rows, C] --------------------------
+// out = a + b + bias[c].  diffusers ResnetBlock2D ends with  hidden = conv2(hidden); out = shortcut(x) + hidden , and torch adds
+// every convolution's bias as a separate broadcast kernel (aten::add_ with a [1,C,1,1] operand: non-vectorised, 22 us on a
+// 21 MB tensor).  The convolutions run without bias and the (frozen) biases are added here, in the pass that the residual add
+// needs anyway.  HBM-bound: 3 tensors of rows*C bf16.
+namespace sdt {
+__global__ void __launch_bounds__(kThreads)
+residual_bias_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const float4* __restrict__ bias,
+                         uint4* __restrict__ out, int64_t n_vec, int C8) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  constexpr int U = 4;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_vec; i += U * stride) {
+    uint4 av[U], bv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i + u * stride < n_vec) { av[u] = ld_stream(a + i + u * stride); bv[u] = ld_stream(b + i + u * stride); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t iu = i + u * stride;
+      if (iu >= n_vec) break;
+      const int c = (int)(iu % C8);
+      const float4 b0 = __ldg(bias + 2 * c), b1 = __ldg(bias + 2 * c + 1);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const uint32_t* aw = reinterpret_cast<const uint32_t*>(&av[u]);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv[u]);
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(aw[j] << 16) + __uint_as_float(bw[j] << 16) + bb[2 * j];
+        const float hi = __uint_as_float(aw[j] & 0xffff0000u) + __uint_as_float(bw[j] & 0xffff0000u) + bb[2 * j + 1];
+        o[j] = pack_bf16x2(lo, hi);
+      }
+      st_stream(out + iu, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+}  // namespace sdt
+
+extern "C" int sdt_residual_bias_add(const void* a, const void* b, const float* bias, void* out, int64_t rows, int C, void* stream) {
+  SDT_REQUIRE(a && b && bias && out, SDT_ERR_ARG, "sdt_residual_bias_add: null pointer");
+  SDT_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, SDT_ERR_UNSUPPORTED, "sdt_residual_bias_add: needs C %% 8 == 0 (got C=%d)", C);
+  SDT_REQUIRE(aligned16(a) && aligned16(b) && aligned16(bias) && aligned16(out), SDT_ERR_ARG,
+              "sdt_residual_bias_add: pointers must be 16-byte aligned");
+  const int64_t n_vec = rows * (C / 8);
+  const int grid = grid_for(n_vec, kThreads, 8);
+  sdt::residual_bias_add_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (const float4*)bias,
+                                                                         (uint4*)out, n_vec, C / 8);
+  SDT_LAUNCH_OK("residual_bias_add");
+  return SDT_OK;
+}

@@ -178,3 +178,28 @@ def add_layer_norm(norm: torch.nn.LayerNorm, x: torch.Tensor, res: torch.Tensor 
         return norm(x)
     xs = x + res
     return xs, norm(xs)
+
+
+class _ResidualBiasAdd(torch.autograd.Function):
+    """``a + b + bias[None, :, None, None]`` on channels-last bf16 tensors, frozen bias (f32 [C]); one vectorised pass."""
+
+    @staticmethod
+    def forward(ctx, a, b, bias_f32):
+        B, C, H, W = a.shape
+        out = torch.empty_like(a, memory_format=torch.channels_last)
+        _lib.check(_lib.load().sdt_residual_bias_add(a.data_ptr(), b.data_ptr(), bias_f32.data_ptr(), out.data_ptr(), B * H * W, C,
+                                                     _lib.stream_ptr()), "sdt_residual_bias_add")
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        return dout, dout, None
+
+
+def residual_bias_add(a: torch.Tensor, b: torch.Tensor, bias_f32: torch.Tensor) -> torch.Tensor:
+    """``a + b + bias`` (per channel) for two channels-last bf16 NCHW tensors; torch otherwise (host-model code)."""
+    cl = torch.channels_last
+    if (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape == b.shape and a.dim() == 4
+            and a.shape[1] % 8 == 0 and a.is_contiguous(memory_format=cl) and b.is_contiguous(memory_format=cl) and a.numel() > 0):
+        return _ResidualBiasAdd.apply(a, b, bias_f32)
+    return a + b + bias_f32.to(a.dtype)[None, :, None, None]

@@ -19,7 +19,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .fused import add_layer_norm, group_norm_act
+from .fused import add_layer_norm, group_norm_act, residual_bias_add
 from .lora import project_group
 
 
@@ -79,13 +79,39 @@ class ResnetBlock2D(nn.Module):
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
+    def _frozen_biases(self):
+        """(conv1.bias as the activation dtype, conv2.bias [+ conv_shortcut.bias] as f32) when every conv bias is frozen: the
+        biases are then folded into the passes that follow the convolutions instead of torch's per-conv broadcast add."""
+        convs = [self.conv1, self.conv2] + ([self.conv_shortcut] if self.conv_shortcut is not None else [])
+        if any(c.bias is None or c.bias.requires_grad for c in convs):
+            return None
+        key = tuple((c.bias.data_ptr(), c.bias._version) for c in convs)
+        cache = getattr(self, "_bias_cache", None)
+        if cache is None or cache[0] != key:
+            tail = self.conv2.bias.detach().float()
+            if self.conv_shortcut is not None:
+                tail = tail + self.conv_shortcut.bias.detach().float()
+            cache = (key, self.conv1.bias.detach(), tail.contiguous())
+            self._bias_cache = cache
+        return cache[1], cache[2]
+
     def forward(self, x, temb):
-        h = self.conv1(group_norm_act(self.norm1, x, True))
-        # h + temb only feeds norm2: the broadcast add is folded into the norm (torch runs it as a non-vectorised kernel)
-        h = self.conv2(group_norm_act(self.norm2, h, True, chan_bias=self.time_emb_proj(F.silu(temb))))
+        folded = self._frozen_biases() if (x.is_cuda and x.dtype == torch.bfloat16) else None
+        if folded is None:                          # CPU oracle arm / trainable convolutions: the plain module calls
+            h = self.conv1(group_norm_act(self.norm1, x, True))
+            # h + temb only feeds norm2: the broadcast add is folded into the norm (torch runs it as a non-vectorised kernel)
+            h = self.conv2(group_norm_act(self.norm2, h, True, chan_bias=self.time_emb_proj(F.silu(temb))))
+            if self.conv_shortcut is not None:
+                x = self.conv_shortcut(x)
+            return x + h
+        b1, b_tail = folded
+        h = F.conv2d(group_norm_act(self.norm1, x, True), self.conv1.weight, None, 1, 1)
+        # conv1's bias and the time embedding are both per-(sample, channel) constants in front of norm2
+        h = group_norm_act(self.norm2, h, True, chan_bias=self.time_emb_proj(F.silu(temb)) + b1)
+        h = F.conv2d(h, self.conv2.weight, None, 1, 1)
         if self.conv_shortcut is not None:
-            x = self.conv_shortcut(x)
-        return x + h
+            x = F.conv2d(x, self.conv_shortcut.weight, None)
+        return residual_bias_add(x, h, b_tail)
 
 
 class CrossAttention(nn.Module):

@@ -262,3 +262,53 @@ def test_group_norm_with_folded_time_embedding_bias(sdt_lib, C, G, H, W, silu):
     assert (yo.double().cpu() - yr).norm() <= 1e-2 * yr.norm()
     assert (xo.grad.double().cpu() - xr.grad).norm() <= 1e-2 * xr.grad.norm()
     assert (to.grad.double().cpu() - tr.grad).norm() <= 2e-2 * tr.grad.norm()
+
+
+def test_residual_bias_add_kernel(sdt_lib):
+    from scal_sdt_b200.fused import residual_bias_add
+    g = torch.Generator().manual_seed(4)
+    a = torch.randn(3, 320, 9, 7, generator=g).bfloat16().to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    b = torch.randn(3, 320, 9, 7, generator=g).bfloat16().to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bias = torch.randn(320, generator=g).to(DEV)
+    out = residual_bias_add(a, b, bias)
+    ref = a.float() + b.float() + bias[None, :, None, None]
+    assert out.dtype == torch.bfloat16 and out.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(out, ref.bfloat16())                         # one rounding of the exact f32 sum
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    assert torch.equal(a.grad, dout) and torch.equal(b.grad, dout)
+
+
+@pytest.mark.parametrize("cin,cout", [(320, 320), (320, 640)])
+def test_resnet_block_with_folded_biases_matches_plain_evaluation(sdt_lib, cin, cout):
+    """ResnetBlock2D with frozen parameters (conv biases + time embedding folded into norm2 / the residual add) against the
+    plain module-by-module evaluation in fp64 on the same bf16-rounded parameters and inputs."""
+    import copy
+
+    import torch.nn.functional as F
+    from scal_sdt_b200.unet import ResnetBlock2D
+    torch.manual_seed(cin + cout)
+    blk = ResnetBlock2D(cin, cout, 1280, 32)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(p.bfloat16().float())
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.1).copy_(p.bfloat16().float())
+    ref = copy.deepcopy(blk).double()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, cin, 16, 16, generator=g).bfloat16()
+    temb = torch.randn(2, 1280, generator=g).bfloat16()
+    dout = torch.randn(2, cout, 16, 16, generator=g).bfloat16()
+    xr = x.double().requires_grad_(True)
+    h = ref.conv1(F.silu(ref.norm1(xr)))
+    h = h + ref.time_emb_proj(F.silu(temb.double()))[:, :, None, None]
+    h = ref.conv2(F.silu(ref.norm2(h)))
+    yr = (ref.conv_shortcut(xr) if ref.conv_shortcut is not None else xr) + h
+    yr.backward(dout.double())
+    gpu = blk.to(DEV).to(torch.bfloat16).to(memory_format=torch.channels_last).requires_grad_(False)
+    assert gpu._frozen_biases() is not None
+    xo = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    yo = gpu(xo, temb.to(DEV))
+    yo.backward(dout.to(DEV))
+    assert (yo.double().cpu() - yr).norm() <= 2e-2 * yr.norm(), (yo.double().cpu() - yr).norm() / yr.norm()
+    assert (xo.grad.double().cpu() - xr.grad).norm() <= 3e-2 * xr.grad.norm(), (xo.grad.double().cpu() - xr.grad).norm() / xr.grad.norm()
