@@ -587,6 +587,14 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
   p.n_tiles = (int)((N + BN - 1) / BN);
   const int pairs_max = num_sms() / 2;
   choose_groups_pair(m_tiles * p.n_probs, p.n_tiles, BN, p.n_src * R, pairs_max, &p.group_size, &p.n_groups);
+  // Many column tiles (the FF up-projections: 23 / 46 tiles of 224): every tile is its own work item.  Recomputing the rank
+  // projection costs R / BN of a merged UMMA, and measured (tools/gemm_ab.py groups) it is 8-13 % faster than sharing it:
+  // 8192x640x5120 57.0 -> 49.4 us, 2048x1280x10240 46.6 -> 42.9 us (1270 TF/s).  With few column tiles sharing still wins.
+  if (S == 1 && p.n_tiles >= 16) { p.group_size = 1; p.n_groups = p.n_tiles; }
+  if (debug_get(20) && (int)debug_get(20) <= p.n_tiles) {          // A/B: force the number of n-tiles per work item
+    p.group_size = (int)debug_get(20);
+    p.n_groups = (p.n_tiles + p.group_size - 1) / p.group_size;
+  }
   p.n_items = m_tiles * p.n_probs * p.n_groups;
   const int pairs = p.n_items < pairs_max ? p.n_items : pairs_max;
   lora_gemm_pair_kernel<BN, R, G, S><<<2 * pairs, kPairThreads, C::SMEM_BYTES, st>>>(gm, p);

@@ -152,9 +152,9 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
 }
 
 // debug overrides (sdt_debug_set): lets the GPU tests probe descriptor hypotheses without a rebuild
-static uint64_t g_dbg[16] = {0};
-void debug_set(int key, uint64_t value) { if (key >= 0 && key < 16) g_dbg[key] = value; }
-uint64_t debug_get(int key) { return (key >= 0 && key < 16) ? g_dbg[key] : 0; }
+static uint64_t g_dbg[32] = {0};
+void debug_set(int key, uint64_t value) { if (key >= 0 && key < 32) g_dbg[key] = value; }
+uint64_t debug_get(int key) { return (key >= 0 && key < 32) ? g_dbg[key] : 0; }
 
 struct WgradSite {       // one LoRA site: dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]
   const void* x; const void* g; float* dA;

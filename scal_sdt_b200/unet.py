@@ -347,14 +347,15 @@ class UNet2DConditionModel(nn.Module):
         each attention picks its pair up when it runs.  Only LoRA sites on CUDA take part (``project_group`` decides)."""
         from . import _lib
         from .lora import LoRALinear
-        if not ctx.is_cuda:
-            return
+        attn2s = self.__dict__.get("_attn2_modules")
+        if attn2s is None:                        # module tree walk once, not per forward
+            attn2s = [m.attn2 for m in self.modules() if isinstance(m, BasicTransformerBlock)]
+            self.__dict__["_attn2_modules"] = attn2s
         by_width: dict[int, list] = {}
-        for m in self.modules():
-            if isinstance(m, BasicTransformerBlock):
-                a = m.attn2
-                if isinstance(a.to_k, LoRALinear) and isinstance(a.to_v, LoRALinear):
-                    by_width.setdefault(a.to_k.out_features, []).append(a)
+        for a in attn2s:
+            a._kv_pre = None                      # never reuse a pair from an earlier (possibly interrupted) forward
+            if ctx.is_cuda and isinstance(a.to_k, LoRALinear) and isinstance(a.to_v, LoRALinear):
+                by_width.setdefault(a.to_k.out_features, []).append(a)
         per = _lib.MAX_GROUP // 2
         for attns in by_width.values():
             for i in range(0, len(attns), per):

@@ -51,14 +51,14 @@ def case(M, K, N, R, G, settings):
     fl = G * (2.0 * M * K * N + 2.0 * M * R * (K + N))
     out = []
     for name, kv in settings:
-        for k in (11, 12, 13, 14):
+        for k in (11, 12, 13, 14, 20):
             lib.sdt_debug_set(k, 0)
         for k, v in kv.items():
             lib.sdt_debug_set(k, v)
         warm, kn = kernel_us(run)
         cold, _ = kernel_us(run, cold=True)
         out.append(f"{name}: warm {warm:6.1f} us {fl / warm / 1e6:6.0f} TF/s | cold {cold:6.1f} us {fl / cold / 1e6:6.0f} TF/s [{kn}]")
-    for k in (11, 12, 13, 14):
+    for k in (11, 12, 13, 14, 20):
         lib.sdt_debug_set(k, 0)
     print(f"M={M} K={K} N={N} R={R} G={G}")
     for o in out:
@@ -66,6 +66,8 @@ def case(M, K, N, R, G, settings):
 
 
 SET = [("auto  ", {}), ("single", {11: 1}), ("pair  ", {14: 64}), ("pair160", {14: 64, 12: 1})]
+if len(sys.argv) > 1 and sys.argv[1] == "groups":
+    SET = [("auto", {}), ("gs1 ", {20: 1}), ("gs2 ", {20: 2}), ("gs3 ", {20: 3}), ("gs4 ", {20: 4}), ("gs6 ", {20: 6})]
 for shp in [(32768, 320, 320, 16, 1), (32768, 320, 320, 16, 3), (32768, 320, 2560, 16, 1), (32768, 1280, 320, 16, 1),
             (8192, 640, 640, 16, 1), (8192, 640, 640, 16, 3), (8192, 640, 5120, 16, 1), (2048, 1280, 1280, 16, 1),
             (2048, 1280, 1280, 16, 3), (2048, 1280, 10240, 16, 1), (616, 768, 1280, 16, 4), (616, 768, 320, 16, 4)]:
