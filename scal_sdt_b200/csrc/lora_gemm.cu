@@ -55,7 +55,10 @@ struct LoraGemmCfg {
   static constexpr int T_BYTES = (BM / 8) * T_SBO;
   static constexpr int BIAS_BYTES = ((BN * 32 + 1023) / 1024) * 1024;    // [BN,16] bf16, un-swizzled cores
   static constexpr int BAR_BYTES = 256;
-  static constexpr int STG_BYTES = 8 * 4096;               // 8 epilogue warps x [32 rows x 128 B] transpose buffers
+  // 8 epilogue warps x ONE [32 rows x 128 B] transpose buffer (the CTA-pair kernel, which runs every large launch, stages a
+  // warp's whole share of the tile and releases the accumulator before storing; here the ring needs the shared memory)
+  static constexpr int STG_BLOCKS = 1;
+  static constexpr int STG_BYTES = 8 * STG_BLOCKS * 4096;
   static constexpr int FIXED_BYTES = 1024 /*align slack*/ + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
   static constexpr int RING_BYTES = ((232448 - FIXED_BYTES) / 1024) * 1024;   // everything else feeds the TMA ring
   static constexpr int kStages = RING_BYTES / STAGE_BYTES > 6 ? 6 : RING_BYTES / STAGE_BYTES;
@@ -415,7 +418,7 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int half = e >> 2;                      // which of the two warps of this quarter
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t stg = smem_u32(stg_smem + e * 4096);
+    const uint32_t stg = smem_u32(stg_smem + e * C::STG_BLOCKS * 4096);
     uint32_t tile_ctr = 0;
     if (has_main) {
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {

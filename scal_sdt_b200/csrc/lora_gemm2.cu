@@ -112,7 +112,10 @@ struct PairCfg {
   static constexpr int T_BYTES = (BM / 8) * T_SBO;
   static constexpr int BIAS_BYTES = (((HN + HR) * 32 + 1023) / 1024) * 1024;   // own half of the bias operand [BN/2, 16] + HR zero rows
   static constexpr int BAR_BYTES = 256;
-  static constexpr int STG_BYTES = 8 * 4096;                        // 8 epilogue warps x [32 rows x 128 B] transpose buffers
+  // 64-column blocks of staging per epilogue warp.  2 (a warp's whole share of a <= 160-wide tile: the accumulator is handed
+  // back before the stores, which pays for K = 320) or 1 (224-wide tiles: a pipeline stage is worth more there -- measured)
+  static constexpr int STG_BLOCKS = BN <= 160 ? 2 : 1;
+  static constexpr int STG_BYTES = 8 * STG_BLOCKS * 4096;           // 8 epilogue warps x their [32 rows x 128 B] transpose buffers
   static constexpr int FIXED_BYTES = 1024 + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
   static constexpr int kStagesMax = (232448 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
@@ -464,7 +467,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
     const int q = warp & 3;
     const int half = e >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t stg = smem_u32(stg_smem + e * 4096);
+    const uint32_t stg = smem_u32(stg_smem + e * C::STG_BLOCKS * 4096);
     uint32_t acc_empty_leader[2] = {map_to_rank(&acc_empty[0], 0), map_to_rank(&acc_empty[1], 0)};
     uint32_t tile_ctr = 0;
     for (int item = pair_id; item < p.n_items; item += n_pairs) {
@@ -483,38 +486,65 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         tc_fence_after();
         const int n_sub = min(C::BN / 32, (p.N - n0 + 31) / 32);
         uint32_t v[32];
-        for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2) {
-          const int subs = min(2, n_sub - 2 * cb);
-          for (int h = 0; h < subs; ++h) {
-            // 32 output columns: one TMEM load, or two 16-column loads where the block straddles the gap of a first tile
-            // (HN is a multiple of 16, so a half never straddles it)
-            const int y0 = (2 * cb + h) * 32, y1 = y0 + 16;
-            if (gap == 0 || y0 >= C::HN || y0 + 32 <= C::HN) {
-              tmem_ld_x32(lane_addr + buf * C::ACC1_COL + y0 + (y0 >= C::HN ? gap : 0), v);
-            } else {
-              uint32_t(&lo)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
-              uint32_t(&hi)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[16]);
-              tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y0 + (y0 >= C::HN ? gap : 0), lo);
-              tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y1 + (y1 >= C::HN ? gap : 0), hi);
-            }
-            if (warp == 6 && lane == 0 && tile_ctr == 0) SDT_TRACE2(70 + 8 * (cb >> 1) + 4 * h);
-            tmem_ld_wait();
-            if (warp == 6 && lane == 0 && tile_ctr == 0) SDT_TRACE2(71 + 8 * (cb >> 1) + 4 * h);
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-            stage_row_chunk(stg, lane, h, pk);
-            if (warp == 6 && lane == 0 && tile_ctr == 0) SDT_TRACE2(72 + 8 * (cb >> 1) + 4 * h);
+        // 32 output columns of this tile -> registers: one TMEM load, or two 16-column loads where the block straddles the gap of
+        // a merged first tile (HN is a multiple of 16, so a half never straddles it)
+        auto load_sub = [&](int sub) {
+          const int y0 = sub * 32, y1 = y0 + 16;
+          if (gap == 0 || y0 >= C::HN || y0 + 32 <= C::HN) {
+            tmem_ld_x32(lane_addr + buf * C::ACC1_COL + y0 + (y0 >= C::HN ? gap : 0), v);
+          } else {
+            uint32_t(&lo)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
+            uint32_t(&hi)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[16]);
+            tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y0 + (y0 >= C::HN ? gap : 0), lo);
+            tmem_ld_x16(lane_addr + buf * C::ACC1_COL + y1 + (y1 >= C::HN ? gap : 0), hi);
           }
+          tmem_ld_wait();
+        };
+        if constexpr (C::STG_BLOCKS >= 2) {
+          // Phase 1: drain this warp's share of the accumulator into its staging buffers and hand the TMEM buffer back at once.
+          // Store-bound shapes (K = 320: 8x more bytes out than in per tile) spend ~3000 cycles per tile on the stores; holding
+          // the accumulator that long left the MMA warp idle and the store stream with gaps (timeline in profiles/).
+          int slot = 0;
+          for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot) {
+            const int subs = min(2, n_sub - 2 * cb);
+            for (int h = 0; h < subs; ++h) {
+              load_sub(2 * cb + h);
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              stage_row_chunk(stg + slot * 4096, lane, h, pk);
+            }
+          }
+          tc_fence_before();
           __syncwarp();
-          write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * subs);
+          if (lane == 0) remote_arrive_relaxed(acc_empty_leader[buf]);
+          if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(49 + 2 * tile_ctr);
+          // Phase 2: stream the staged blocks out (full 128-byte lines); the next tile's phase 1 follows in program order
+          slot = 0;
+          for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot)
+            write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * min(2, n_sub - 2 * cb));
           __syncwarp();
-          if (warp == 6 && lane == 0 && tile_ctr == 0) SDT_TRACE2(73 + 8 * (cb >> 1));
+          if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(70 + tile_ctr);
+        } else {
+          // one staging block per warp: stage and store block by block, release the accumulator after the last load
+          for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2) {
+            const int subs = min(2, n_sub - 2 * cb);
+            for (int h = 0; h < subs; ++h) {
+              load_sub(2 * cb + h);
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              stage_row_chunk(stg, lane, h, pk);
+            }
+            __syncwarp();
+            write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * subs);
+            __syncwarp();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) remote_arrive_relaxed(acc_empty_leader[buf]);
+          if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(49 + 2 * tile_ctr);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) remote_arrive_relaxed(acc_empty_leader[buf]);
-        if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(49 + 2 * tile_ctr);
       }
     }
     if (warp == 6 && lane == 0) SDT_TRACE2(62);

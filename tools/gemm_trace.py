@@ -17,10 +17,12 @@ for t in range(6):
     NAMES[11 + 4 * t] = f"mma t{t}: tail issued"
     NAMES[40 + t] = f"side t{t}: tail operands ready"
     NAMES[48 + 2 * t] = f"epi t{t}: acc_full"
-    NAMES[49 + 2 * t] = f"epi t{t}: drained"
+    NAMES[49 + 2 * t] = f"epi t{t}: accumulator released"
 
 
-for cbi in range(3):
+for t in range(6):
+    NAMES[70 + t] = f"epi t{t}: stores issued"
+for cbi in range(0):
     for h in range(2):
         NAMES[70 + 8 * cbi + 4 * h] = f"  epi t0 w6 blk{cbi} sub{h}: ld issued"
         NAMES[71 + 8 * cbi + 4 * h] = f"  epi t0 w6 blk{cbi} sub{h}: ld done"
