@@ -417,7 +417,7 @@ def ours_main(args):
         # DRAM bytes per GEMM launch from the committed ncu pass over one training step (dram__bytes_read + write summed over
         # the lora_gemm* launches / their count); bench.py cannot run ncu itself
         traffic, traffic_src = None, None
-        for tname in ("r01_v15_kernels_per_step_ncu.json", "r01_v5_lora_kernels_per_step_ncu.json"):
+        for tname in ("r01_v21_kernels_per_step_ncu.json", "r01_v15_kernels_per_step_ncu.json", "r01_v5_lora_kernels_per_step_ncu.json"):
             tpath = os.path.join(ROOT, "profiles", tname)
             if not os.path.exists(tpath):
                 continue
