@@ -236,7 +236,15 @@ int sdt_simt_gemm_f32(const float* A, int64_t lda_m, int64_t lda_k, const float*
                       float* C, int64_t ldc, const float* bias, float alpha, float beta,
                       int64_t M, int64_t N, int64_t K, void* stream);
 
-/* test support: override shared-memory descriptor constants of the weight-gradient kernel (probing) */
+/* test / measurement support (tools/): process-wide switches, 0 = default behaviour.
+ *   0..9   weight-gradient kernel: override shared-memory / instruction descriptor constants (layout probing)
+ *   10     device pointer to 128 int64 slots: clock64 timeline of CTA 0 of the next GEMM launches (tools/gemm_trace.py)
+ *   11     1: force the single-CTA GEMM kernel          12  1: never use 224-wide tiles
+ *   13     2: weight-stationary schedule of the single-CTA kernel (K <= 320; measured: no gain)
+ *   14     K threshold above which the CTA-pair kernel is used (default 256)
+ *   15     weight-gradient grid: min 64-token chunks per CTA | CTAs per SM << 8
+ *   20     force the number of column tiles per work item in the CTA-pair kernel (tools/gemm_ab.py groups)
+ */
 int sdt_debug_set(int key, uint64_t value);
 
 #ifdef __cplusplus
