@@ -620,7 +620,9 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
   // Many column tiles (the FF up-projections: 23 / 46 tiles of 224): every tile is its own work item.  Recomputing the rank
   // projection costs R / BN of a merged UMMA, and measured (tools/gemm_ab.py groups) it is 8-13 % faster than sharing it:
   // 8192x640x5120 57.0 -> 49.4 us, 2048x1280x10240 46.6 -> 42.9 us (1270 TF/s).  With few column tiles sharing still wins.
-  if (S == 1 && p.n_tiles >= 16) { p.group_size = 1; p.n_groups = p.n_tiles; }
+  // The same holds for long K loops (K >= 2048, the FF down-projections and their input gradients): 32768x2560x320 63.2 -> 57.6 us,
+  // 8192x5120x640 54.7 -> 51.3 us.  Short K loops with few column tiles keep the shared intermediate.
+  if (S == 1 && (p.n_tiles >= 16 || K >= 2048)) { p.group_size = 1; p.n_groups = p.n_tiles; }
   if (debug_get(20) && (int)debug_get(20) <= p.n_tiles) {          // A/B: force the number of n-tiles per work item
     p.group_size = (int)debug_get(20);
     p.n_groups = (p.n_tiles + p.group_size - 1) / p.group_size;

@@ -68,6 +68,12 @@ def case(M, K, N, R, G, settings):
 SET = [("auto  ", {}), ("single", {11: 1}), ("pair  ", {14: 64}), ("pair160", {14: 64, 12: 1})]
 if len(sys.argv) > 1 and sys.argv[1] == "groups":
     SET = [("auto", {}), ("gs1 ", {20: 1}), ("gs2 ", {20: 2}), ("gs3 ", {20: 3}), ("gs4 ", {20: 4}), ("gs6 ", {20: 6})]
+SHAPES_BWD = [(32768, 320, 1280, 16, 1), (8192, 640, 2560, 16, 1), (2048, 1280, 5120, 16, 1), (32768, 2560, 320, 16, 1),
+              (8192, 5120, 640, 16, 1), (2048, 10240, 1280, 16, 1)]      # dX of ff.net.2 / ff.net.0.proj: (M, contraction, outputs)
+if len(sys.argv) > 2 and sys.argv[2] == "bwd":
+    for shp in SHAPES_BWD:
+        case(*shp, SET)
+    sys.exit(0)
 for shp in [(32768, 320, 320, 16, 1), (32768, 320, 320, 16, 3), (32768, 320, 2560, 16, 1), (32768, 1280, 320, 16, 1),
             (8192, 640, 640, 16, 1), (8192, 640, 640, 16, 3), (8192, 640, 5120, 16, 1), (2048, 1280, 1280, 16, 1),
             (2048, 1280, 1280, 16, 3), (2048, 1280, 10240, 16, 1), (616, 768, 1280, 16, 4), (616, 768, 320, 16, 4)]:
