@@ -63,5 +63,12 @@ if mode == "single":
 else:
     lib.sdt_debug_set(14, 64)         # CTA-pair kernel for every K
 print("==== kernel:", mode)
+if len(sys.argv) > 2 and sys.argv[2] == "gs":
+    for gs in (2, 1):
+        lib.sdt_debug_set(20, gs)
+        print("==== column tiles per work item:", gs)
+        run(32768, 2560, 320, 16)
+    lib.sdt_debug_set(20, 0)
+    sys.exit(0)
 for shape in [(32768, 320, 320, 16), (32768, 320, 2560, 16), (2048, 1280, 1280, 16), (8192, 640, 5120, 16)]:
     run(*shape)
