@@ -642,10 +642,13 @@ int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scali
 #define SDT_PAIR_R(BN, G)                                                                     \
   switch (r) { case 16: SDT_PAIR(BN, 16, G); case 32: SDT_PAIR(BN, 32, G); default: SDT_PAIR(BN, 64, G); }
   // wide tiles (more FLOP per byte brought into the SM) when the rank accumulators still fit next to two 224-column
-  // main accumulators (2*224 + 2*R <= 512), the ragged last tile wastes little and there are enough column tiles to keep
-  // every pair busy (measured: N = 640 / 1280 are faster with 160-wide tiles)
+  // main accumulators (2*224 + 2*R <= 512), the ragged last tile wastes little and there are enough tiles to keep every
+  // pair busy: N >= 2048, or N >= 1280 with at least four rounds of tiles (measured: 32768x320x1280 41.3 -> 36.7 us, while
+  // 2048x*x1280 -- 48 tiles on 74 pairs -- is faster with 160-wide tiles)
   const int64_t n224 = (N + 223) / 224 * 224;
-  const bool wide = r <= 32 && N >= 2048 && n224 * 100 <= N * 106 && debug_get(12) == 0;
+  const int64_t tiles224 = ((M + 255) / 256) * (n224 / 224);
+  const int64_t wide_min_n = debug_get(22) ? (int64_t)debug_get(22) : ((N >= 1280 && tiles224 >= 4 * (num_sms() / 2)) ? 1280 : 2048);
+  const bool wide = r <= 32 && N >= wide_min_n && n224 * 100 <= N * 106 && debug_get(12) == 0;
   if (n_probs == 1) {
     if (wide) { switch (r) { case 0: SDT_PAIR(224, 0, 1); case 16: SDT_PAIR(224, 16, 1); default: SDT_PAIR(224, 32, 1); } }
     if (r == 0) { if (bn160) SDT_PAIR(160, 0, 1); else SDT_PAIR(128, 0, 1); }
