@@ -114,3 +114,33 @@ def ref_lora_linear_grads_closed_form(x, w, A, B, scaling, dy):
     dA = scaling * (g.T @ x2)
     dB = scaling * (dy2.T @ (x2 @ A.T))
     return dx.reshape(x.shape), dA, dB
+
+
+def ref_lora_weight_grads_chunked(x, A, B, scaling, dy, chunk=16384):
+    """dA, dB of the closed forms above, accumulated over row chunks in fp64 -- the full reductions over M without ever
+    holding ``[M, *]`` in double precision (the benchmark-size parity tests: M up to 98,304 tokens).  ``x`` / ``dy`` may live
+    on any device and in any dtype; every chunk is brought to the CPU and widened before it is used."""
+    A64, B64 = A.detach().double().cpu(), B.detach().double().cpu()
+    dA = torch.zeros_like(A64)
+    dB = torch.zeros_like(B64)
+    M = x.shape[0]
+    for i in range(0, M, chunk):
+        xc = x[i:i + chunk].detach().double().cpu()
+        dyc = dy[i:i + chunk].detach().double().cpu()
+        g = dyc @ B64
+        dA += scaling * (g.T @ xc)
+        dB += scaling * (dyc.T @ (xc @ A64.T))
+    return dA, dB
+
+
+def ref_rows_matvec(t, vec, chunk=16384):
+    """``t.double() @ vec`` on the CPU, row chunk by row chunk (``t`` any device / dtype)."""
+    return torch.cat([t[i:i + chunk].detach().double().cpu() @ vec for i in range(0, t.shape[0], chunk)])
+
+
+def ref_cols_vecmat(u, t, chunk=16384):
+    """``u @ t.double()`` on the CPU, accumulated over row chunks."""
+    out = torch.zeros(t.shape[1], dtype=torch.float64)
+    for i in range(0, t.shape[0], chunk):
+        out += u[i:i + chunk] @ t[i:i + chunk].detach().double().cpu()
+    return out

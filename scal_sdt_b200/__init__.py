@@ -7,8 +7,8 @@ module-injection / loss / EMA interfaces.  All arithmetic runs in ``libsdt_b200.
 """
 from ._lib import SdtError, library_path  # noqa: F401
 from .lora import LoRAConv2d, LoRALinear, get_lora, get_linears, lora_modules  # noqa: F401
-from .module_config import (apply_module_config, config_module, freeze_permanently, merge_config,  # noqa: F401
-                            set_submodule)
+from .module_config import (Selection, apply_module_config, config_module, freeze_permanently,  # noqa: F401
+                            merge_config, plan_module_config, set_submodule)
 from .ema import ExponentialMovingAverage  # noqa: F401
 from .diffusion import DenoiseLoss, NoiseScheduler, scaled_linear_alphas_cumprod  # noqa: F401
 from .arena import LoraArena, ParamArena  # noqa: F401

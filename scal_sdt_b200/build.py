@@ -18,10 +18,12 @@ INCLUDE_DIR = PKG_DIR.parent / "include"
 
 SOURCES = ["api.cu", "elementwise.cu", "groupnorm.cu", "layernorm.cu", "comm.cu", "simt_gemm.cu", "lora_gemm.cu", "lora_gemm2.cu", "lora_wgrad.cu", "lora_api.cu"]
 
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = COMPILE_FLAGS + ["-shared"]      # kept for tools that compile a single file against the same flags
 
 
 def _nvcc() -> str:
@@ -39,20 +41,41 @@ def _stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the library if it is missing or older than its sources; return its path."""
-    if not force and not _stale():
-        return LIB_PATH
-    BUILD_DIR.mkdir(parents=True, exist_ok=True)
-    tmp = BUILD_DIR / "libsdt_b200.so.tmp"
-    cmd = [_nvcc(), *NVCC_FLAGS, *(str(CSRC / s) for s in SOURCES), "-o", str(tmp)]
+def _compile_one(nvcc: str, src: Path, obj: Path, verbose: bool) -> str:
+    cmd = [nvcc, *COMPILE_FLAGS, "-c", str(src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+        raise RuntimeError(f"nvcc failed on {src.name}:\n" + proc.stdout + proc.stderr)
+    return proc.stderr
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the library if it is missing or older than its sources; return its path.  Every ``.cu`` becomes its own
+    object (compiled in parallel, rebuilt only when it or a header is newer), then one link."""
+    if not force and not _stale():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = BUILD_DIR / "obj"
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+    headers = list(CSRC.glob("*.cuh")) + list(INCLUDE_DIR.glob("*.h"))
+    t_hdr = max(h.stat().st_mtime for h in headers)
+    jobs = []
+    for s in SOURCES:
+        src, obj = CSRC / s, obj_dir / (s[:-3] + ".o")
+        if force or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, t_hdr):
+            jobs.append((src, obj))
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1) or 1) as pool:
+        logs = list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs))
     if verbose:
-        print(proc.stderr)
+        print("\n".join(logs))
+    tmp = BUILD_DIR / "libsdt_b200.so.tmp"
+    cmd = [nvcc, *LINK_FLAGS, *(str(obj_dir / (s[:-3] + ".o")) for s in SOURCES), "-o", str(tmp)]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + proc.stdout + proc.stderr)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

@@ -2,6 +2,7 @@
 #include "sdt_common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 #include <mutex>
 
 namespace sdt {
@@ -18,6 +19,20 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+uint64_t debug_get(int key);   // lora_wgrad.cu
+
+bool pdl_enabled() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("SDT_PDL");
+    env = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const uint64_t dbg = debug_get(24);      // 1: off, 2: on (overrides the environment; A/B inside one process)
+  if (dbg == 1) return false;
+  if (dbg == 2) return true;
+  return env != 0;
+}
 
 int num_sms() {
   static int cached[64];

@@ -440,6 +440,8 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // proj [M, 2I] bf16 -> out [M, I] bf16; one 16-byte vector (8 elements) of h and of gate per thread per iteration
 __global__ void __launch_bounds__(kThreads)
 geglu_fwd_bf16_kernel(const uint16_t* __restrict__ proj, uint16_t* __restrict__ out, int64_t M, int64_t I8) {
+  pdl_wait();                 // PDL (sdt_common.cuh)
+  pdl_launch_dependents();
   const int64_t total = M * I8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / I8, c = i - row * I8;
@@ -463,6 +465,8 @@ geglu_fwd_bf16_kernel(const uint16_t* __restrict__ proj, uint16_t* __restrict__ 
 __global__ void __launch_bounds__(kThreads)
 geglu_bwd_bf16_kernel(const uint16_t* __restrict__ proj, const uint16_t* __restrict__ dout, uint16_t* __restrict__ dproj,
                       int64_t M, int64_t I8) {
+  pdl_wait();                 // PDL (sdt_common.cuh)
+  pdl_launch_dependents();
   const int64_t total = M * I8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / I8, c = i - row * I8;
@@ -670,8 +674,12 @@ extern "C" int sdt_geglu(const void* proj, const void* dout, void* out_or_dproj,
     SDT_REQUIRE(I % 8 == 0 && aligned16(proj) && aligned16(out_or_dproj) && aligned16(dout), SDT_ERR_UNSUPPORTED,
                 "sdt_geglu(bf16): inner width must be a multiple of 8 and pointers 16-byte aligned");
     const int grid = grid_for(M * (I / 8), kThreads, 8);
-    if (!backward) geglu_fwd_bf16_kernel<<<grid, kThreads, 0, st>>>((const uint16_t*)proj, (uint16_t*)out_or_dproj, M, I / 8);
-    else geglu_bwd_bf16_kernel<<<grid, kThreads, 0, st>>>((const uint16_t*)proj, (const uint16_t*)dout, (uint16_t*)out_or_dproj, M, I / 8);
+    if (!backward)
+      SDT_CUDA_OK(launch_kernel(geglu_fwd_bf16_kernel, dim3(grid), dim3(kThreads), 0, st, true, (const uint16_t*)proj,
+                                (uint16_t*)out_or_dproj, M, I / 8));
+    else
+      SDT_CUDA_OK(launch_kernel(geglu_bwd_bf16_kernel, dim3(grid), dim3(kThreads), 0, st, true, (const uint16_t*)proj,
+                                (const uint16_t*)dout, (uint16_t*)out_or_dproj, M, I / 8));
   } else if (dtype == SDT_F32) {
     const int grid = grid_for(M * I, kThreads, 8);
     geglu_f32_kernel<<<grid, kThreads, 0, st>>>((const float*)proj, (const float*)dout, (float*)out_or_dproj, M, I, backward);

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(kLnThreads)
 ln_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, const float4* __restrict__ gamma,
               const float4* __restrict__ beta, uint4* __restrict__ xs_out, uint4* __restrict__ y, float2* __restrict__ stats,
               int64_t M, int C8, float eps, float inv_C) {
+  pdl_wait();                 // PDL (sdt_common.cuh): inputs come from the kernel in front of us
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (kLnThreads / 32);
@@ -111,6 +113,8 @@ __global__ void __launch_bounds__(kLnThreads)
 ln_bwd_kernel(const uint4* __restrict__ xs, const uint4* __restrict__ dy, const uint4* __restrict__ dres,
               const float4* __restrict__ gamma, const float2* __restrict__ stats, uint4* __restrict__ dx, int64_t M, int C8,
               float inv_C) {
+  pdl_wait();                 // PDL (sdt_common.cuh): inputs come from the kernel in front of us
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (kLnThreads / 32);
@@ -191,10 +195,10 @@ using namespace sdt;
 #define SDT_LN_DISPATCH(KERNEL, RES, ...)                                                                     \
   do {                                                                                                        \
     const int nch = (C8 + 31) / 32;                                                                           \
-    if (nch <= 2) KERNEL<2, 2, RES><<<ln_grid(M, 2), kLnThreads, 0, st>>>(__VA_ARGS__);                       \
-    else if (nch <= 3) KERNEL<3, 1, RES><<<ln_grid(M, 1), kLnThreads, 0, st>>>(__VA_ARGS__);                  \
-    else if (nch <= 5) KERNEL<5, 1, RES><<<ln_grid(M, 1), kLnThreads, 0, st>>>(__VA_ARGS__);                  \
-    else KERNEL<8, 1, RES><<<ln_grid(M, 1), kLnThreads, 0, st>>>(__VA_ARGS__);                                \
+    if (nch <= 2) SDT_CUDA_OK(launch_kernel(KERNEL<2, 2, RES>, dim3(ln_grid(M, 2)), dim3(kLnThreads), 0, st, true, __VA_ARGS__));      \
+    else if (nch <= 3) SDT_CUDA_OK(launch_kernel(KERNEL<3, 1, RES>, dim3(ln_grid(M, 1)), dim3(kLnThreads), 0, st, true, __VA_ARGS__)); \
+    else if (nch <= 5) SDT_CUDA_OK(launch_kernel(KERNEL<5, 1, RES>, dim3(ln_grid(M, 1)), dim3(kLnThreads), 0, st, true, __VA_ARGS__)); \
+    else SDT_CUDA_OK(launch_kernel(KERNEL<8, 1, RES>, dim3(ln_grid(M, 1)), dim3(kLnThreads), 0, st, true, __VA_ARGS__));               \
   } while (0)
 
 extern "C" int sdt_layer_norm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* xs_out, void* y,

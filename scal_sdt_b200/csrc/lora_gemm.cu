@@ -178,6 +178,9 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
   tc_fence_after();
   const uint32_t tmem_base = warp == 0 ? 0u : *tmem_slot;
   if (threadIdx.x == 32) SDT_TRACE(1);
+  // PDL: the prologue above is independent of the predecessor's results; global memory is touched only from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -637,7 +640,7 @@ static int launch_lora_gemm(const LoraProblem* probs, int n_probs, float scaling
       grid = g;
     }
   }
-  lora_gemm_kernel<BN, R, G><<<grid, kGemmThreads, C::SMEM_BYTES, st>>>(gm, p);
+  SDT_CUDA_OK(launch_kernel(lora_gemm_kernel<BN, R, G>, dim3(grid), dim3(kGemmThreads), C::SMEM_BYTES, st, true, gm, p));
   SDT_LAUNCH_OK("lora_gemm");
   return SDT_OK;
 }

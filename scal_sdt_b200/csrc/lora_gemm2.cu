@@ -244,6 +244,11 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
   tc_fence_after();
   const uint32_t tmem_base = warp == 0 ? 0u : *tmem_slot;
   if (threadIdx.x == 32) SDT_TRACE2(1);
+  // PDL: everything above touched only shared memory, TMEM and the kernel parameters.  From here on the kernel reads what its
+  // predecessor in the stream wrote (and overwrites buffers it may still be reading), so wait for it -- and let our own
+  // dependent start its prologue on every SM this grid has already left.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
@@ -629,7 +634,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
   }
   p.n_items = m_tiles * p.n_probs * p.n_groups;
   const int pairs = p.n_items < pairs_max ? p.n_items : pairs_max;
-  lora_gemm_pair_kernel<BN, R, G, S><<<2 * pairs, kPairThreads, C::SMEM_BYTES, st>>>(gm, p);
+  SDT_CUDA_OK(launch_kernel(lora_gemm_pair_kernel<BN, R, G, S>, dim3(2 * pairs), dim3(kPairThreads), C::SMEM_BYTES, st, true, gm, p));
   SDT_LAUNCH_OK("lora_gemm_pair");
   return SDT_OK;
 }

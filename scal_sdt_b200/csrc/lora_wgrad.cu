@@ -86,6 +86,8 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // PDL: U / V come from the kernels in front of us; the prologue above did not need them
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -217,7 +219,7 @@ static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t 
   if (g_dbg[4]) p.a_step = (uint32_t)g_dbg[5];
   if (g_dbg[6]) p.b_step = (uint32_t)g_dbg[7];
   if (g_dbg[8]) p.idesc = (uint32_t)g_dbg[9];
-  lora_wgrad_kernel<R><<<dim3(f_blocks, splits), 128, C::SMEM_BYTES, st>>>(gw, p);
+  SDT_CUDA_OK(launch_kernel(lora_wgrad_kernel<R>, dim3(f_blocks, splits), dim3(128), C::SMEM_BYTES, st, true, gw, p));
   SDT_LAUNCH_OK("lora_wgrad");
   return SDT_OK;
 }

@@ -47,7 +47,36 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int num_sms();   // cached multiProcessorCount of the current device (api.cu)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// Kernels that call pdl_wait() before their first global-memory access may be launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the grid is then scheduled while its predecessor in the stream is
+// still draining, runs its prologue (barrier init, TMEM allocation, tensor-map prefetch, constant operands) and blocks in
+// `griddepcontrol.wait` until the predecessor has completed and flushed.  Works inside stream capture (the edge becomes a
+// programmatic dependency of the graph).  SDT_PDL=0 in the environment or sdt_debug_set(24, 1) turns it off (A/B).
+bool pdl_enabled();   // api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers -----------------------------------------------------------------------
+// PDL: block until every prerequisite grid has completed and its memory is visible (no-op without the launch attribute)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// PDL: this CTA no longer holds back the launch of the dependent grid (it still waits for our completion in ITS pdl_wait)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -5,9 +5,45 @@ gradient halves in backward; here each direction is ONE 128-bit vectorised pass 
 """
 from __future__ import annotations
 
+import contextlib
+import logging
+
 import torch
 
 from . import _lib
+
+_log = logging.getLogger("scal_sdt_b200.fused")
+_torch_only = False
+_noted: set = set()
+
+
+@contextlib.contextmanager
+def torch_only():
+    """Route every helper of this file through plain torch ops.  Used by the comparators that time / check the reference's
+    own eager torch path on the same GPU (``bench.py`` ``torch_gpu_baseline``, ``tests/test_gpu_sd15_step.py``): none of this
+    repo's kernels may run on that arm."""
+    global _torch_only
+    saved, _torch_only = _torch_only, True
+    try:
+        yield
+    finally:
+        _torch_only = saved
+
+
+def fused_enabled() -> bool:
+    return not _torch_only
+
+
+def _note_torch_path(what: str, x: torch.Tensor) -> None:
+    """A CUDA tensor took the torch path of a host-model helper (shape / dtype / layout / trainable affine did not qualify):
+    say so once per helper and reason instead of silently changing the kernels that run."""
+    if not x.is_cuda or _torch_only:
+        return
+    key = (what, x.dtype, x.dim())
+    if key not in _noted:
+        _noted.add(key)
+        _log.warning("%s: %s %s tensor does not qualify for the fused kernel; using torch ops for it (host-model code)",
+                     what, tuple(x.shape), x.dtype)
 
 
 class _GEGLU(torch.autograd.Function):
@@ -39,6 +75,10 @@ def geglu(proj: torch.Tensor) -> torch.Tensor:
     """``h * gelu(gate)`` for ``proj = [h | gate]`` along the last dimension (CUDA tensors, bf16 or fp32)."""
     _lib.require_cuda(proj)
     return _GEGLU.apply(proj)
+
+
+def geglu_supported(proj: torch.Tensor) -> bool:
+    return fused_enabled() and proj.is_cuda and proj.dtype in (torch.bfloat16, torch.float32)
 
 
 class _GroupNormNHWC(torch.autograd.Function):
@@ -81,7 +121,7 @@ class _GroupNormNHWC(torch.autograd.Function):
 
 def group_norm_nhwc_supported(norm: torch.nn.GroupNorm, x: torch.Tensor) -> bool:
     c, g = norm.num_channels, norm.num_groups
-    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+    return (fused_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
             and not norm.weight.requires_grad and not norm.bias.requires_grad and c % 8 == 0 and c // g >= 8 and g <= 128
             and c <= 4096)
 
@@ -97,6 +137,7 @@ def group_norm_act(norm: torch.nn.GroupNorm, x: torch.Tensor, silu: bool, chan_b
             cache = (key, norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous())
             norm._sdt_affine_f32 = cache
         return _GroupNormNHWC.apply(x, chan_bias, cache[1], cache[2], norm.num_groups, float(norm.eps), bool(silu))
+    _note_torch_path("group_norm_act", x)
     if chan_bias is not None:
         x = x + chan_bias[:, :, None, None]
     y = norm(x)
@@ -154,7 +195,7 @@ class _AddLayerNorm(torch.autograd.Function):
 
 def layer_norm_supported(norm: torch.nn.LayerNorm, x: torch.Tensor) -> bool:
     c = x.shape[-1]
-    return (x.is_cuda and x.dtype == torch.bfloat16 and len(norm.normalized_shape) == 1 and norm.normalized_shape[0] == c
+    return (fused_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and len(norm.normalized_shape) == 1 and norm.normalized_shape[0] == c
             and norm.weight is not None and norm.bias is not None and not norm.weight.requires_grad
             and not norm.bias.requires_grad and c % 8 == 0 and c <= 2048 and x.numel() > 0)
 
@@ -174,6 +215,7 @@ def add_layer_norm(norm: torch.nn.LayerNorm, x: torch.Tensor, res: torch.Tensor 
     if layer_norm_supported(norm, x) and (res is None or (res.shape == x.shape and res.dtype == x.dtype and res.is_cuda)):
         g, b = _ln_affine(norm)
         return _AddLayerNorm.apply(x, res, g, b, float(norm.eps))
+    _note_torch_path("add_layer_norm", x)
     if res is None:
         return norm(x)
     xs = x + res
@@ -199,7 +241,8 @@ class _ResidualBiasAdd(torch.autograd.Function):
 def residual_bias_add(a: torch.Tensor, b: torch.Tensor, bias_f32: torch.Tensor) -> torch.Tensor:
     """``a + b + bias`` (per channel) for two channels-last bf16 NCHW tensors; torch otherwise (host-model code)."""
     cl = torch.channels_last
-    if (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape == b.shape and a.dim() == 4
+    if (fused_enabled() and a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape == b.shape and a.dim() == 4
             and a.shape[1] % 8 == 0 and a.is_contiguous(memory_format=cl) and b.is_contiguous(memory_format=cl) and a.numel() > 0):
         return _ResidualBiasAdd.apply(a, b, bias_f32)
+    _note_torch_path("residual_bias_add", a)
     return a + b + bias_f32.to(a.dtype)[None, :, None, None]

@@ -19,7 +19,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .fused import add_layer_norm, group_norm_act, residual_bias_add
+from .fused import add_layer_norm, fused_enabled, geglu, geglu_supported, group_norm_act, residual_bias_add
 from .lora import project_group
 
 
@@ -96,7 +96,7 @@ class ResnetBlock2D(nn.Module):
         return cache[1], cache[2]
 
     def forward(self, x, temb):
-        folded = self._frozen_biases() if (x.is_cuda and x.dtype == torch.bfloat16) else None
+        folded = self._frozen_biases() if (x.is_cuda and x.dtype == torch.bfloat16 and fused_enabled()) else None
         if folded is None:                          # CPU oracle arm / trainable convolutions: the plain module calls
             h = self.conv1(group_norm_act(self.norm1, x, True))
             # h + temb only feeds norm2: the broadcast add is folded into the norm (torch runs it as a non-vectorised kernel)
@@ -155,8 +155,7 @@ class GEGLU(nn.Module):
 
     def forward(self, x):
         y = self.proj(x)
-        if y.is_cuda and y.dtype in (torch.bfloat16, torch.float32):
-            from .fused import geglu           # one vectorised pass per direction
+        if geglu_supported(y):                 # one vectorised pass per direction
             return geglu(y)
         h, gate = y.chunk(2, dim=-1)           # host model on the CPU (oracle / reference arm)
         return h * F.gelu(gate)

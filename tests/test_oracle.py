@@ -155,3 +155,26 @@ def test_prior_preservation_reduction():
     r = diffusion_ref.ref_reduce_loss(loss, True, 0.3)
     assert torch.allclose(r, loss[:3].mean() + 0.3 * loss[3:].mean())
     assert torch.allclose(diffusion_ref.ref_reduce_loss(loss), loss.mean())
+
+
+def test_chunked_weight_grads_and_projection_identities():
+    """The helpers the benchmark-size GPU tests lean on: chunked dA/dB == autograd, and the +-1 projection closed forms
+    (Y v, u^T Y, dX v, u^T dX) hold for the oracle's own outputs to fp64 round-off."""
+    from oracle import lora_ref
+    g = torch.Generator().manual_seed(0)
+    M, K, N, r, s = 300, 40, 56, 8, 0.75
+    x, dy = torch.randn(M, K, generator=g).double(), torch.randn(M, N, generator=g).double()
+    w, b = torch.randn(N, K, generator=g).double(), torch.randn(N, generator=g).double()
+    A, B = torch.randn(r, K, generator=g).double(), torch.randn(N, r, generator=g).double()
+    y, dx, dA, dB = lora_ref.ref_lora_linear_grads(x, w, b, A, B, s, dy)
+    dA_c, dB_c = lora_ref.ref_lora_weight_grads_chunked(x.float(), A, B, s, dy.float(), chunk=64)
+    assert torch.allclose(dA_c, dA, rtol=1e-6, atol=1e-6) and torch.allclose(dB_c, dB, rtol=1e-6, atol=1e-6)
+    vN, vK, uM = torch.randn(N, generator=g).double(), torch.randn(K, generator=g).double(), torch.randn(M, generator=g).double()
+    yv = lora_ref.ref_rows_matvec(x, w.T @ vN, chunk=64) + float(b @ vN) + s * lora_ref.ref_rows_matvec(x, A.T @ (B.T @ vN), chunk=64)
+    assert torch.allclose(yv, y @ vN, rtol=1e-10, atol=1e-10)
+    ux = lora_ref.ref_cols_vecmat(uM, x, chunk=64)
+    assert torch.allclose(ux @ w.T + uM.sum() * b + s * ((ux @ A.T) @ B.T), uM @ y, rtol=1e-10, atol=1e-10)
+    dxv = lora_ref.ref_rows_matvec(dy, w @ vK, chunk=64) + s * lora_ref.ref_rows_matvec(dy, B @ (A @ vK), chunk=64)
+    assert torch.allclose(dxv, dx @ vK, rtol=1e-10, atol=1e-10)
+    udy = lora_ref.ref_cols_vecmat(uM, dy, chunk=64)
+    assert torch.allclose(udy @ w + s * ((udy @ B) @ A), uM @ dx, rtol=1e-10, atol=1e-10)
