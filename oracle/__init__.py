@@ -25,14 +25,21 @@ oracle module          follows
 
 Pinning status
 --------------
-* EMA, bucket/rank sharding, target-selection DSL: PINNED -- golden files under
-  ``tests/golden/`` were produced by executing the reference's own source
-  (``oracle/make_golden.py``), and the restatements are checked against them.
-* LoRA arithmetic (loralib 0.1) and DDIM ``add_noise``/``get_velocity``
-  (unpinned diffusers fork): the arithmetic lives in third-party packages that
-  are absent from ``/root/reference`` and from this image, and the reference
-  ships no tests or golden vectors: PARITY UNPINNED by the reference.  The
-  restatement follows the published algorithm of the pinned version and is
-  cross-checked by closed-form identities (merged-weight equivalence, fp64
-  autograd, ``alpha_bar`` analytic properties) in ``tests/test_oracle.py``.
+* EMA, bucket / rank sharding, DreamBooth sampler, target-selection DSL: PINNED -- golden files under ``tests/golden/``
+  were produced by executing the reference's own source (``oracle/make_golden.py``); restatements and product host
+  code are checked against them.
+* The reference's own GLUE around the third-party arithmetic: PINNED since round 2.  ``oracle/reference_shim.py``
+  executes ``modules/lora.py`` (``get_lora``) and, by AST extraction, ``modules/model.py``'s ``get_optimizer``,
+  ``config_module`` and ``LatentDiffusionModel`` (``_denoise_loss``, ``training_step``, ``on_save_checkpoint``) with
+  stand-ins for ``loralib`` / ``diffusers`` / ``pytorch_lightning`` / ``omegaconf``.  Recorded in ``lora_glue.pt``,
+  ``denoise_steps.pt``, ``config_module.json`` and checked by ``tests/test_reference_glue.py`` (CPU: oracle + product host
+  code; GPU: the CUDA path): the isinstance switch, weight / bias aliasing, the int32 ``lora_alpha`` buffer, the state-dict
+  keys, the order of the random draws, the ``"v"`` spelling of the target switch, the NaN guards and their messages, the
+  ``chunk`` / ``mean`` prior-preservation reduction, the param groups, the LR / weight-decay scaling, the checkpoint keys.
+* RESIDUE THAT STAYS UNPINNED BY THE REFERENCE: the arithmetic *inside* loralib-0.1's ``Linear`` / ``Conv2d`` forward and
+  *inside* diffusers' ``DDIMScheduler.add_noise`` / ``get_velocity`` (and the ``scaled_linear`` beta schedule).  Those
+  packages are absent from ``/root/reference`` and from this image (no network), and the reference ships no test or golden
+  vector for them.  The stand-ins are the restatements in ``lora_ref.py`` / ``diffusion_ref.py`` of the published
+  algorithms of the pinned versions (``requirements.txt:13,16``), cross-checked by closed-form identities
+  (merged-weight equivalence, fp64 autograd vs closed forms, ``alpha_bar`` analytic properties) in ``tests/test_oracle.py``.
 """

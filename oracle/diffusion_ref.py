@@ -96,3 +96,21 @@ def ref_training_step(unet, alphas_cumprod, prediction_type, batch, noise, times
     if torch.any(torch.isnan(loss)):
         raise Exception("NaN element discovered in loss")
     return ref_reduce_loss(loss, prior_preservation, prior_loss_weight)
+
+
+class RefDDIMScheduler:
+    """The slice of diffusers' ``DDIMScheduler`` the training path touches (``modules/model.py:297,302,306,312``):
+    ``config.num_train_timesteps``, ``config.prediction_type``, ``add_noise``, ``get_velocity`` -- restated, [ext]-unpinned."""
+
+    def __init__(self, prediction_type="epsilon", beta_start=SD1_BETA_START, beta_end=SD1_BETA_END,
+                 num_train_timesteps=SD1_TRAIN_STEPS):
+        from types import SimpleNamespace
+        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, prediction_type=prediction_type,
+                                      beta_start=beta_start, beta_end=beta_end, beta_schedule="scaled_linear")
+        self.alphas_cumprod = ref_alphas_cumprod(beta_start, beta_end, num_train_timesteps)
+
+    def add_noise(self, original_samples, noise, timesteps):
+        return ref_add_noise(self.alphas_cumprod, original_samples, noise, timesteps)
+
+    def get_velocity(self, sample, noise, timesteps):
+        return ref_get_velocity(self.alphas_cumprod, sample, noise, timesteps)

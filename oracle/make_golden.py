@@ -9,6 +9,14 @@ travel with the repo; the GPU box never reads ``/root/reference``.
 * ``walker.json``          modules visited by ``apply_module_config`` (``modules/utils/torch/module.py:14-63``) for every
                            ``configs/optim_targets/*.yaml`` over the UNet skeleton (+ a CLIP-named text-encoder skeleton)
 * ``ema_reference.pt``     shadow parameters produced by the reference ``modules/ema.py`` on an all-trainable module
+* ``lora_glue.pt``         the reference's own ``modules/lora.py::get_lora`` (loralib stand-in = the restated layers): attribute /
+                           state-dict / aliasing contract, forward + gradients on seeded inputs, the error on other module types
+* ``denoise_steps.pt``     the reference's own ``LatentDiffusionModel._denoise_loss`` / ``training_step``
+                           (``modules/model.py:289-348``) executed on a toy UNet for every prediction type, with and without
+                           prior preservation: the draws it made, what it fed the UNet, per-element loss, reduced loss
+* ``config_module.json``   the reference's own ``config_module`` (``modules/model.py:136-164``) on the UNet skeleton for every
+                           optim_target YAML: param groups (names, optimizer overrides), trainable set, checkpoint keys written
+                           by its ``on_save_checkpoint``; and ``get_optimizer``'s LR / weight-decay scaling
 """
 from __future__ import annotations
 
@@ -182,6 +190,164 @@ def make_ema_fixture():
     (GOLDEN / "ema_reference_partial_freeze.json").write_text(json.dumps({"reference_raises": crashed}))
 
 
+def make_lora_glue_fixture():
+    ref = shim.load_reference_lora()
+    cases = {}
+    specs = {"linear_bias_r2_a4": (lambda: nn.Linear(6, 5), 2, 4, (3, 7, 6)),
+             "linear_nobias_r4_a1": (lambda: nn.Linear(8, 3, bias=False), 4, 1, (5, 8)),
+             "conv1x1_r2_a2": (lambda: nn.Conv2d(4, 6, 1), 2, 2, (2, 4, 3, 3))}
+    for name, (make, rank, alpha, xshape) in specs.items():
+        torch.manual_seed(11)
+        base = make()
+        base.requires_grad_(False)                     # config_module froze the whole network first (model.py:137)
+        lora = ref.get_lora(base, rank, alpha)
+        g = torch.Generator().manual_seed(12)
+        with torch.no_grad():
+            lora.lora_A.copy_(torch.randn(lora.lora_A.shape, generator=g) * 0.3)
+            lora.lora_B.copy_(torch.randn(lora.lora_B.shape, generator=g) * 0.3)
+        x = torch.randn(*xshape, generator=g, requires_grad=True)
+        y = lora(x)
+        dy = torch.randn(y.shape, generator=g)
+        y.backward(dy)
+        cases[name] = {
+            "rank": rank, "alpha": alpha,
+            "base_state": {k: v.clone() for k, v in base.state_dict().items()},
+            "state_keys": sorted(lora.state_dict().keys()),
+            "state_dtypes": {k: str(v.dtype) for k, v in lora.state_dict().items()},
+            "buffers": sorted(n for n, _ in lora.named_buffers()),
+            "requires_grad": {n: bool(p.requires_grad) for n, p in lora.named_parameters()},
+            "weight_is_aliased": lora.weight is base.weight, "bias_is_aliased": lora.bias is base.bias,
+            "scaling": float(lora.scaling), "lora_alpha": lora.lora_alpha.clone(),
+            "has_python_lora_alpha_attr": "lora_alpha" in lora.__dict__,
+            "lora_A": lora.lora_A.detach().clone(), "lora_B": lora.lora_B.detach().clone(),
+            "x": x.detach().clone(), "dy": dy, "y": y.detach().clone(), "dx": x.grad.clone(),
+            "dA": lora.lora_A.grad.clone(), "dB": lora.lora_B.grad.clone(),
+            "frozen_grads_none": lora.weight.grad is None,
+        }
+    torch.manual_seed(0)
+    fresh = ref.get_lora(nn.Linear(64, 32), 4, 1)
+    cases["init"] = {"lora_B_all_zero": bool(torch.count_nonzero(fresh.lora_B) == 0),
+                     "lora_A_absmax": float(fresh.lora_A.detach().abs().max()), "bound": 1 / 8}
+    try:
+        ref.get_lora(nn.LayerNorm(8))
+        cases["other_module_error"] = None
+    except Exception as e:  # noqa: BLE001
+        cases["other_module_error"] = str(e)
+    torch.save(cases, GOLDEN / "lora_glue.pt")
+
+
+def make_denoise_fixture():
+    from types import SimpleNamespace
+
+    from oracle.diffusion_ref import RefDDIMScheduler
+    model = shim.load_reference_model()
+
+    class ToyUNet(nn.Module):
+        """Stands where diffusers' UNet2DConditionModel stands: ``unet(noisy, t, conds).sample``; records what it was fed."""
+
+        def __init__(self):
+            super().__init__()
+            self.mix = nn.Conv2d(4, 4, 1)
+            self.seen = None
+
+        dtype = torch.float32
+
+        @property
+        def device(self):
+            return self.mix.weight.device
+
+        def forward(self, noisy, timesteps, conds):
+            self.seen = (noisy.detach().clone(), timesteps.detach().clone(), conds.detach().clone())
+            shift = conds.mean(dim=(1, 2))[:, None, None, None]
+            return SimpleNamespace(sample=self.mix(noisy) * (1 + 1e-3 * timesteps[:, None, None, None].float()) + shift)
+
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    for ptype in ("epsilon", "sample", "v"):
+        for prior in (None, 0.6):
+            B = 4
+            torch.manual_seed(5)
+            unet = ToyUNet()
+            latents = torch.randn(B, 4, 6, 10, generator=g)
+            conds = torch.randn(B, 7, 12, generator=g)
+            cfg = shim.AttrDict({"prior_preservation": {"enabled": prior is not None, "prior_loss_weight": prior or 1.0}})
+            me = shim.bare_lightning_module(model, unet=unet, scheduler=RefDDIMScheduler(ptype), config=cfg)
+            seed = 1000 + len(out)
+            torch.manual_seed(seed)
+            loss_elem = me._denoise_loss(latents, conds)
+            noisy, t_seen, conds_seen = unet.seen
+            torch.manual_seed(seed)             # the draws of model.py:294,297-298, in the reference's order
+            noise = torch.randn_like(latents)
+            t = torch.randint(0, 1000, (B,), dtype=torch.int64)
+            assert torch.equal(t, t_seen) and torch.equal(conds_seen, conds)
+            pred = unet(noisy, t, conds).sample.detach()
+            torch.manual_seed(seed)
+            loss = me.training_step({"latents": latents, "conds": conds, "ids": list(range(B))}, 0)
+            out[f"{ptype}_prior{prior}"] = {
+                "prediction_type": ptype, "prior_loss_weight": prior, "seed": seed,
+                "latents": latents, "conds": conds, "noise": noise, "timesteps": t, "noisy": noisy, "pred": pred,
+                "loss_elem": loss_elem.detach().clone(), "loss": loss.detach().clone(), "logged": me.logged[-1]["train_loss"],
+            }
+    # the guards (model.py:324,332,336) and the unknown-type branch (:313-314)
+    errs = {}
+    me = shim.bare_lightning_module(model, unet=ToyUNet(), scheduler=RefDDIMScheduler("v_prediction"),
+                                    config=shim.AttrDict({"prior_preservation": {"enabled": False}}))
+    for name, batch in (("unknown_type", {"latents": torch.zeros(2, 4, 2, 2), "conds": torch.zeros(2, 3, 12)}),
+                        ("nan_latents", {"latents": torch.full((2, 4, 2, 2), float("nan")), "conds": torch.zeros(2, 3, 12)}),
+                        ("nan_conds", {"latents": torch.zeros(2, 4, 2, 2), "conds": torch.full((2, 3, 12), float("nan"))})):
+        try:
+            me.training_step(batch, 0)
+            errs[name] = None
+        except Exception as e:  # noqa: BLE001
+            errs[name] = str(e)
+    out["errors"] = errs
+    torch.save(out, GOLDEN / "denoise_steps.pt")
+
+
+def make_config_module_fixture():
+    from types import SimpleNamespace
+
+    from scal_sdt_b200.config import load_yaml
+    from scal_sdt_b200.unet import UNet2DConditionModel, UNetConfig
+    model = shim.load_reference_model()
+    out = {"targets": {}}
+    tdir = shim.REFERENCE_ROOT / "configs" / "optim_targets"
+    for path in sorted(tdir.glob("*.yaml")):
+        cfg = load_yaml(path)
+        if cfg.get("unet") is None:
+            continue
+        torch.manual_seed(0)
+        unet = UNet2DConditionModel(UNetConfig.tiny())
+        groups = model.config_module(unet, cfg["unet"]["targets"])
+        names = {id(p): n for n, p in unet.named_parameters()}
+        rec = [{"params": [names[id(p)] for p in g["params"]], "overrides": {k: v for k, v in g.items() if k != "params"}}
+               for g in groups]
+        # on_save_checkpoint (model.py:378-391) on a module that holds this unet
+        me = shim.bare_lightning_module(model, unet=unet)
+        me.unet_ema = None
+        ckpt = {}
+        me.on_save_checkpoint(ckpt)
+        out["targets"][path.stem] = {
+            "groups": rec, "trainable": sorted(n for n, p in unet.named_parameters() if p.requires_grad),
+            "injected": sorted(n for n, m in unet.named_modules() if hasattr(m, "lora_A")),
+            "checkpoint_keys": sorted(ckpt["state_dict"].keys()),
+        }
+    # get_optimizer (model.py:33-64): AdamW by class name, beta1/beta2 -> betas, LR / weight-decay scaling
+    scal = {}
+    for method in ("sqrt", "linear"):
+        p1, p2 = nn.Parameter(torch.zeros(3)), nn.Parameter(torch.zeros(2))
+        conf = shim.AttrDict({"batch_size": 4, "optimizer": {
+            "name": "torch.optim.AdamW", "params": {"lr": 5e-4, "beta1": 0.9, "beta2": 0.999, "weight_decay": 2e-2, "eps": 1e-7},
+            "lr_scale": {"enabled": True, "method": method}}})
+        trainer = SimpleNamespace(accumulate_grad_batches=2, num_nodes=1, num_devices=8)
+        opt = model.get_optimizer([{"params": [p1], "lr": 1e-4, "weight_decay": 1e-2}, {"params": [p2]}], conf, trainer)
+        scal[method] = [{"lr": g["lr"], "weight_decay": g["weight_decay"], "betas": list(g["betas"]), "eps": g["eps"]}
+                        for g in opt.param_groups]
+        scal[method + "_class"] = type(opt).__name__
+    out["get_optimizer"] = {"accumulate": 2, "batch_size": 4, "nodes": 1, "devices": 8, "result": scal}
+    (GOLDEN / "config_module.json").write_text(json.dumps(out))
+
+
 def main():
     if not shim.available():
         raise SystemExit("/root/reference is not present: golden fixtures can only be generated in the build container")
@@ -190,6 +356,9 @@ def main():
     make_sampler_fixture()
     make_walker_fixture()
     make_ema_fixture()
+    make_lora_glue_fixture()
+    make_denoise_fixture()
+    make_config_module_fixture()
     for f in sorted(GOLDEN.iterdir()):
         print(f"{f.name}: {f.stat().st_size} bytes")
 

@@ -69,3 +69,25 @@ def test_sampler_db_live():
     random.seed(7)
     b = [(x.value, tuple(x.size), y.value) for x, y in B.AspectSamplerDB(inst, cls, 512, B.DEFAULT_BUCKET_CONFIG, 2, 5, 1, 0)]
     assert a == b
+
+
+def test_glue_goldens_regenerate_from_the_reference(tmp_path, monkeypatch):
+    """``lora_glue.pt`` / ``denoise_steps.pt`` / ``config_module.json`` are what the reference's own source produces today."""
+    import json
+
+    from oracle import make_golden
+    monkeypatch.setattr(make_golden, "GOLDEN", tmp_path)
+    make_golden.make_lora_glue_fixture()
+    make_golden.make_denoise_fixture()
+    make_golden.make_config_module_fixture()
+    real = make_golden.ROOT / "tests" / "golden"
+
+    def same(a, b):
+        if isinstance(a, torch.Tensor):
+            return torch.equal(a, b)
+        if isinstance(a, dict):
+            return a.keys() == b.keys() and all(same(a[k], b[k]) for k in a)
+        return a == b
+    for name in ("lora_glue.pt", "denoise_steps.pt"):
+        assert same(torch.load(tmp_path / name), torch.load(real / name)), name
+    assert json.loads((tmp_path / "config_module.json").read_text()) == json.loads((real / "config_module.json").read_text())
