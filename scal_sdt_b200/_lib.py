@@ -135,9 +135,48 @@ def ptr(t) -> int:
 
 
 def require_cuda(*tensors) -> None:
+    """Every tensor handed to the library must live on the CURRENT CUDA device: the kernels are enqueued on the current
+    device's stream (``stream_ptr``), one process per GPU.  A tensor on another GPU is an error, not a silent cross-device
+    launch."""
+    import torch
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise SdtError("scal_sdt_b200 runs on CUDA (sm_100a) tensors only; got a CPU tensor and there is no CPU path")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise SdtError(f"tensor lives on cuda:{t.device.index} but the current device is cuda:{cur}: call "
+                           "torch.cuda.set_device first (one process per GPU; kernels go to the current device's stream)")
+
+
+class PinnedRing:
+    """A few pinned host slots for small per-step scalars that a captured graph reads from a fixed device buffer.
+
+    ``push(values)`` writes the next slot and issues the async H2D copy into ``dev``; before a slot is rewritten the event
+    recorded after its previous copy is waited for, so the host can run several steps ahead of the GPU without a DMA ever
+    reading values of a later step."""
+
+    def __init__(self, dev, slots: int = 4):
+        import torch
+        self.dev = dev
+        self.host = [torch.zeros(dev.shape, dtype=dev.dtype).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.next = 0
+
+    def push(self, fill) -> None:
+        import torch
+        i = self.next
+        self.next = (i + 1) % len(self.host)
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        fill(self.host[i])
+        self.dev.copy_(self.host[i], non_blocking=True)
+        ev = self.events[i] or torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
 
 
 _checked_devices = set()

@@ -9,6 +9,7 @@ and shapes, so ``state_dict`` / checkpoint layout are unchanged.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Iterable, Optional
 
 import torch
@@ -105,6 +106,7 @@ class LoraArena(ParamArena):
             ops = PackedOperands(m.in_features, m.out_features, m.r, self.device, self.packed[off:off + n])
             off += n
             m._ops, m._ops_external = ops, True
+            m._arena_ref = weakref.ref(self)
             m._grad_A, m._grad_B = self.grad_view(m.lora_A), self.grad_view(m.lora_B)
             recs.append(ops.site(m.lora_A.detach(), m.lora_B.detach()))
             self._max_elems = max(self._max_elems, ops.R * (m.in_features + m.out_features))

@@ -183,6 +183,10 @@ class CachedBatchLoader:
     def _to_device(self, host: dict[str, Any]) -> dict[str, Any]:
         slot = host.pop("_slot")
         if self.device is None:
+            # the consumer copies from the pinned slot itself (LatentDiffusionTrainer.graphed_step): it records an event after
+            # its copy into slot["_event"], which _staging waits for before the slot is rewritten
+            if self._pin:
+                host["_host_slot"] = slot
             return host
         out = {"ids": host["ids"]}
         if self._stream is not None:

@@ -126,10 +126,16 @@ class ExponentialMovingAverage:
                                                 _CHUNK_ELEMS, omd, None, _lib.dtype_code(dtype), _lib.stream_ptr()),
                        "sdt_ema_update_multi")
 
+    def _masters_changed(self) -> None:
+        """The fp32 masters were written behind the optimizer's back: refresh the bf16 operands the kernels read."""
+        from .lora import refresh_packed_operands
+        refresh_packed_operands(self.module)
+
     def apply(self):
         """``ema.py:63-69``."""
         for name, p in self._tracked():
             p.data.copy_(self.shadow_params[name].data)
+        self._masters_changed()
 
     @contextlib.contextmanager
     def average_parameters(self):
@@ -141,6 +147,7 @@ class ExponentialMovingAverage:
         finally:
             for name, p in self._tracked():
                 p.data.copy_(saved[name].data)
+            self._masters_changed()
 
     def to(self, device=None, dtype=None) -> None:
         """``ema.py:87-99``.  Kept for API parity; the update itself needs the shadows on the GPU."""

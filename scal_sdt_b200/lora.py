@@ -297,6 +297,7 @@ class _LoRABase(nn.Module):
         self._b_cache = None
         self._ops: Optional[PackedOperands] = None
         self._ops_external = False           # True when a LoraArena owns (and refreshes) the packed operands
+        self._arena_ref = None               # weakref to that arena (refresh_packed_operands)
         self._grad_A = None
         self._grad_B = None
 
@@ -419,6 +420,25 @@ def get_linears(module: nn.Module):
     for name, sub in module.named_children():
         if isinstance(sub, nn.Linear):
             yield name, sub
+
+
+def refresh_packed_operands(module: nn.Module) -> None:
+    """Bring the bf16 tensor-core operands of every LoRA site under ``module`` back in line with the fp32 masters.
+
+    The kernels read packed bf16 copies (``A_p / At_p / B_p / Bt_p``), refreshed after ``optimizer.step`` by
+    ``LoraArena.pack()``.  Anything ELSE that writes the masters -- ``ExponentialMovingAverage.apply`` /
+    ``average_parameters``, ``load_state_dict``, manual ``p.data.copy_`` -- must call this, otherwise the next bf16 forward
+    silently runs with the old factors (``.data`` writes do not bump ``Parameter._version``)."""
+    arenas = {}
+    for _, m in lora_modules(module):
+        if m._ops_external:
+            arena = m._arena_ref() if m._arena_ref is not None else None
+            if arena is not None:
+                arenas[id(arena)] = arena
+        elif m._ops is not None:
+            m._ops.versions = (-1, -1)         # repacked lazily by the next forward
+    for arena in arenas.values():
+        arena.pack()
 
 
 def lora_modules(module: nn.Module):

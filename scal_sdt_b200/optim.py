@@ -42,12 +42,14 @@ class FlatAdamW:
         """Write the hyper-parameters of optimizer step number `step` (1-based) to the device table (async copy)."""
         n = len(self.param_groups)
         if self._hyper_host is None:
-            self._hyper_host = torch.zeros(n, 8, dtype=torch.float32).pin_memory()
             self._hyper_dev = torch.zeros(n, 8, dtype=torch.float32, device=self.arena.params.device)
-        for i, g in enumerate(self.param_groups):
-            b1, b2 = g["betas"]
-            self._hyper_host[i, :7] = torch.tensor([g["lr"], b1, b2, g["eps"], g["weight_decay"], 1.0 - b1 ** step, 1.0 - b2 ** step])
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_host = _lib.PinnedRing(self._hyper_dev)      # event-guarded slots: the host may run steps ahead
+
+        def fill(host):
+            for i, g in enumerate(self.param_groups):
+                b1, b2 = g["betas"]
+                host[i, :7] = torch.tensor([g["lr"], b1, b2, g["eps"], g["weight_decay"], 1.0 - b1 ** step, 1.0 - b2 ** step])
+        self._hyper_host.push(fill)
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.arena.zero_grad()

@@ -106,6 +106,8 @@ class LatentDiffusionTrainer:
         self.exchange.all_reduce_mean_(self.arena.grads)
         if self.unet_ema is not None and self.unet_ema._shadow_flat is not None:
             ema = self.unet_ema
+            if not ema._shadow_flat.is_cuda:        # a caller mirrored the reference's ``unet_ema.to("cpu")`` (model.py:412)
+                ema.to(self.device)
             if ema.num_updates is not None:
                 ema.num_updates += 1
             self.optimizer.step(ema_shadow=ema._shadow_flat, ema_one_minus_decay=ema.current_one_minus_decay())
@@ -139,7 +141,8 @@ class LatentDiffusionTrainer:
         self._g_noise = torch.empty_like(self._g_lat)
         self._g_t = torch.zeros(self._g_lat.shape[0], dtype=torch.int64, device=dev)
         self._g_omd = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._g_omd_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        from ._lib import PinnedRing
+        self._g_omd_host = PinnedRing(self._g_omd)
         fused_ema = self.unet_ema is not None and self.unet_ema._shadow_flat is not None
         if self.unet_ema is not None and not fused_ema:
             raise NotImplementedError("CUDA-graph stepping needs the EMA shadow on the flat arena")
@@ -155,6 +158,9 @@ class LatentDiffusionTrainer:
                 self.arena.pack()
             return loss.detach()
 
+        # Warm-up replays the step for real (allocator, cuDNN autotune, tensor-map caches), so everything it trains is put
+        # back afterwards: enabling the graph must not move the parameters, the moments, the EMA or any counter.
+        saved = self._snapshot_train_state()
         self._refresh_step_inputs()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -170,7 +176,32 @@ class LatentDiffusionTrainer:
             self._g_loss = body()
         # kernels of libsdt_b200 recorded into the graph = launched on every replay
         self.graph_launches_per_step = int(_lib.load().sdt_launch_count() - before)
-        self.global_step += warmup + 1
+        self._restore_train_state(saved)
+
+    def _snapshot_train_state(self) -> dict:
+        ema = self.unet_ema
+        return {"params": self.arena.params.clone(), "exp_avg": self.optimizer.exp_avg.clone(),
+                "exp_avg_sq": self.optimizer.exp_avg_sq.clone(), "step_count": self.optimizer.step_count,
+                "shadow": None if ema is None or ema._shadow_flat is None else ema._shadow_flat.clone(),
+                "num_updates": None if ema is None else ema.num_updates, "rng": self.generator.get_state(),
+                "global_step": self.global_step}
+
+    def _restore_train_state(self, saved: dict) -> None:
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            self.arena.params.copy_(saved["params"])
+            self.optimizer.exp_avg.copy_(saved["exp_avg"])
+            self.optimizer.exp_avg_sq.copy_(saved["exp_avg_sq"])
+            if saved["shadow"] is not None:
+                self.unet_ema._shadow_flat.copy_(saved["shadow"])
+        self.optimizer.step_count = saved["step_count"]
+        if self.unet_ema is not None:
+            self.unet_ema.num_updates = saved["num_updates"]
+        self.generator.set_state(saved["rng"])
+        self.global_step = saved["global_step"]
+        self.arena.grads.zero_()
+        if isinstance(self.arena, LoraArena):
+            self.arena.pack()
 
     def release_cuda_graph(self) -> None:
         """Drop the captured graph (it pins the NCCL communicator and a private memory pool)."""
@@ -189,13 +220,18 @@ class LatentDiffusionTrainer:
             ema = self.unet_ema
             if ema.num_updates is not None:
                 ema.num_updates += 1
-            self._g_omd_host[0] = ema.current_one_minus_decay()
-            self._g_omd.copy_(self._g_omd_host, non_blocking=True)
+            omd = ema.current_one_minus_decay()
+            self._g_omd_host.push(lambda host: host.fill_(omd))
 
     def graphed_step(self, batch: dict) -> torch.Tensor:
         """Same contract as ``step`` (returns the device-resident loss), replaying the captured graph."""
         self._g_lat.copy_(batch["latents"], non_blocking=True)
         self._g_cond.copy_(batch["conds"], non_blocking=True)
+        slot = batch.get("_host_slot")
+        if slot is not None:                     # pinned staging slot of a CachedBatchLoader: free to be rewritten after this
+            ev = torch.cuda.Event()
+            ev.record()
+            slot["_event"] = ev
         self._refresh_step_inputs()
         self._graph.replay()
         self.global_step += 1
@@ -217,5 +253,5 @@ class LatentDiffusionTrainer:
             for k, v in sd.items():
                 if k.startswith("unet.") and k[5:] in own:
                     own[k[5:]].copy_(v)
-        if isinstance(self.arena, LoraArena):
-            self.arena.pack()
+        from .lora import refresh_packed_operands
+        refresh_packed_operands(self.unet)

@@ -102,3 +102,96 @@ def test_cuda_graph_step_matches_eager(sdt_lib):
     for _ in range(20):
         last = tr2.graphed_step(batch).item()
     assert tr2.optimizer.step_count >= 21 and tr2.unet_ema.num_updates >= 21
+
+
+def _tiny_trainer(lr, seed=3, ema=True):
+    import copy
+
+    import torch
+
+    from scal_sdt_b200 import NoiseScheduler
+    from scal_sdt_b200.targets import lora_unet_targets
+    from scal_sdt_b200.trainer import LatentDiffusionTrainer
+    from scal_sdt_b200.unet import UNet2DConditionModel, UNetConfig
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    base = UNet2DConditionModel(UNetConfig.tiny()).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    tr = LatentDiffusionTrainer(copy.deepcopy(base), NoiseScheduler(), lora_unet_targets(rank=8, alpha=8, lr=lr),
+                                optimizer_params={"lr": lr, "beta1": 0.9, "beta2": 0.999, "weight_decay": 1e-2, "eps": 1e-8},
+                                ema={"enabled": ema, "decay": 0.99}, seed=seed)
+    g = torch.Generator(device=dev).manual_seed(1)
+    with torch.no_grad():
+        for _, m in tr.arena.sites:
+            m.lora_B.normal_(0, 0.05, generator=g)
+    tr.arena.pack()
+    return tr
+
+
+def test_enabling_the_graph_does_not_train(sdt_lib):
+    """Warm-up + capture leave parameters, AdamW moments, EMA shadow, counters and the noise generator exactly where they
+    were; graphed steps then follow the eager trainer's trajectory (same seeds) instead of being three updates ahead."""
+    import torch
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(2)
+    batch = {"latents": torch.randn(2, 4, 16, 16, generator=g).to(dev), "conds": torch.randn(2, 7, 64, generator=g).to(dev)}
+    tr = _tiny_trainer(1e-3)
+    before = (tr.arena.params.clone(), tr.optimizer.exp_avg.clone(), tr.optimizer.exp_avg_sq.clone(),
+              tr.unet_ema._shadow_flat.clone(), tr.generator.get_state().clone())
+    tr.enable_cuda_graph(batch)
+    assert torch.equal(tr.arena.params, before[0]) and torch.equal(tr.optimizer.exp_avg, before[1])
+    assert torch.equal(tr.optimizer.exp_avg_sq, before[2]) and torch.equal(tr.unet_ema._shadow_flat, before[3])
+    assert torch.equal(tr.generator.get_state(), before[4])
+    assert tr.global_step == 0 and tr.optimizer.step_count == 0 and tr.unet_ema.num_updates == 0
+    eager = _tiny_trainer(1e-3)
+    for i in range(3):
+        lg = tr.graphed_step(batch).item()
+        le = eager.step(batch).item()
+        assert abs(lg - le) <= 2e-3 * abs(le), (i, lg, le)
+    assert tr.global_step == eager.global_step == 3 and tr.optimizer.step_count == eager.optimizer.step_count == 3
+    assert tr.unet_ema.num_updates == eager.unet_ema.num_updates == 3
+    # Adam's first steps move every element by ~lr * sign(g): compare the trajectories by the moments, not by sign flips
+    assert (tr.optimizer.exp_avg - eager.optimizer.exp_avg).norm() <= 2e-2 * eager.optimizer.exp_avg.norm()
+    assert (tr.unet_ema._shadow_flat - eager.unet_ema._shadow_flat).norm() <= 1e-3 * eager.unet_ema._shadow_flat.norm()
+
+
+def test_bf16_forward_under_ema_weights_uses_the_ema_weights(sdt_lib):
+    """``average_parameters()`` / ``apply()`` write the fp32 masters behind the optimizer's back; the bf16 operands the
+    kernels read must follow (arena-owned operands and the per-module cache alike), and be restored on exit."""
+    import torch
+    from torch import nn
+
+    from scal_sdt_b200 import ExponentialMovingAverage, get_lora
+    dev = torch.device("cuda:0")
+    tr = _tiny_trainer(1e-3)
+    g = torch.Generator().manual_seed(2)
+    lat = torch.randn(2, 4, 16, 16, generator=g).to(dev).bfloat16()
+    cond = torch.randn(2, 7, 64, generator=g).to(dev).bfloat16()
+    t = torch.tensor([5, 500], device=dev)
+    with torch.no_grad():
+        tr.unet_ema._shadow_flat.mul_(0.5)                     # shadow != parameters
+        y_train = tr.unet(lat, t, cond).sample.clone()
+        with tr.unet_ema.average_parameters():
+            y_ema = tr.unet(lat, t, cond).sample.clone()
+        y_back = tr.unet(lat, t, cond).sample.clone()
+        # the same EMA values loaded the "official" way: copy into the masters, repack
+        tr.arena.params.copy_(tr.unet_ema._shadow_flat)
+        tr.arena.pack()
+        y_loaded = tr.unet(lat, t, cond).sample
+    assert torch.equal(y_back, y_train)
+    assert torch.equal(y_ema, y_loaded)
+    assert not torch.equal(y_ema, y_train)
+    # module without an arena: the per-module operand cache is keyed on Parameter versions, which .data writes do not bump
+    torch.manual_seed(0)
+    lin = get_lora(nn.Linear(64, 32).to(dev).requires_grad_(False), 4, 4)
+    with torch.no_grad():
+        lin.lora_B.normal_(0, 0.3)
+    ema = ExponentialMovingAverage(lin, 0.9)
+    x = torch.randn(8, 64, device=dev, dtype=torch.bfloat16)
+    with torch.no_grad():
+        y0 = lin(x).clone()
+        for s in ema.shadow_params.values():
+            s.mul_(0.25)
+        with ema.average_parameters():
+            y1 = lin(x).clone()
+        y2 = lin(x).clone()
+    assert torch.equal(y0, y2) and not torch.equal(y0, y1)
