@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the LoRA train-step hot path (BASELINE.json metric: LoRA train latents/sec, SD1.5, 512^2).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one process per GPU)
-    python bench.py --impl reference --steps K --warmup W    # reference arm: the CPU path on the host cores
+    python bench.py --gpus N --steps K --warmup W                 # our arm (CUDA, one process per GPU), workload cfg2
+    python bench.py --workload cfg3|cfg4|cfg5 ...                 # the other BASELINE configs (not the driver's line)
+    python bench.py --impl reference --steps K --warmup W         # reference arm: the CPU path on the host cores
 
-Workload at every N (weak scaling, per-GPU work fixed): BASELINE configs[1] -- SD1.5-shaped UNet (859.5 M frozen
-parameters, random init), LoRA rank 16 on all 12 targets of the stock ``lora`` optim_target (192 sites), per-GPU
-batch 8 of 4x64x64 latents + 77x768 text embeddings, bf16 compute, fp32 LoRA masters, AdamW.  One step =
-noise/target -> UNet forward -> MSE loss -> backward -> gradient all-reduce -> AdamW -> operand repack.
+Default workload at every N (weak scaling, per-GPU work fixed): BASELINE configs[1] -- SD1.5-shaped UNet (859.5 M frozen
+parameters, random init), LoRA rank 16 on all 12 targets of the stock ``lora`` optim_target (192 sites), per-GPU batch 8 of
+4x64x64 latents + 77x768 text embeddings, bf16 compute, fp32 LoRA masters, AdamW.  One step = noise/target -> UNet forward
+-> MSE loss -> backward -> gradient all-reduce -> AdamW -> operand repack.
 
-One JSON line on stdout (rank 0).  ``value`` = whole-job latents/s with inputs resident in HBM; ``e2e`` = the same
-through the public API with pinned-host inputs copied in and the loss read back every step; ``roofline`` = the fused
-LoRA forward GEMM launches of the timed workload measured with CUDA events inside this process; ``cpu_baseline`` =
-the oracle port of the reference's torch path on the host cores (bounded sample: batch 1 of the same workload).
+One JSON line on stdout (rank 0).  ``value`` = whole-job latents/s with inputs resident in HBM; ``e2e`` = the same through
+the public API with pinned-host inputs copied in and the loss read back every step; ``roofline`` = the fused LoRA forward
+GEMM launches of the timed workload measured with CUPTI inside this process; ``cpu_baseline`` = the oracle port of the
+reference's torch path on the host cores (bounded sample: batch 1 of the same workload); ``torch_gpu_baseline`` = the same
+oracle trainer run as eager torch under autocast(bf16) on this GPU (what the reference would execute on this machine).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import random
 import statistics
 import sys
 import threading
@@ -43,8 +46,27 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SEED = 114514  # the reference's own seed (configs/lora.yaml:11)
-WORKLOAD = dict(name="cfg2: SD1.5 LoRA r16 (192 sites: attn q/k/v/out + FF + proj_in/out), batch 8/GPU, 64x64 latents, bf16",
-                rank=16, alpha=1, batch=8, h=64, w=64, ctx_len=77, ctx_dim=768)
+
+# BASELINE.json configs[1..4].  cfg2 is the driver's line; the others are measured with --workload and committed under profiles/.
+WORKLOADS = {
+    "cfg2": dict(name="cfg2: SD1.5 LoRA r16 (192 sites: attn q/k/v/out + FF + proj_in/out), batch 8/GPU, 64x64 latents, bf16",
+                 unet="sd15", rank=16, alpha=1, projections=True, batch=8, h=64, w=64, ctx_len=77, ctx_dim=768,
+                 ema=None, prediction_type="epsilon"),
+    "cfg3": dict(name="cfg3: SD1.5 LoRA r64 on attention + FF (160 sites) with EMA 0.995, batch 8/GPU, 64x64 latents, bf16",
+                 unet="sd15", rank=64, alpha=1, projections=False, batch=8, h=64, w=64, ctx_len=77, ctx_dim=768,
+                 ema=0.995, prediction_type="epsilon"),
+    "cfg4": dict(name="cfg4: aspect-ratio-bucketed mixed resolution (23-bucket grid, 512^2 .. 768x1024) SD1.5 LoRA r16 (192 sites) "
+                      "with DreamBooth prior preservation, batch 4 instance + 4 class per GPU, bf16",
+                 unet="sd15", rank=16, alpha=1, projections=True, batch=8, h=64, w=64, ctx_len=77, ctx_dim=768,
+                 ema=None, prediction_type="epsilon", bucketed=True, prior_loss_weight=1.0),
+    "cfg5": dict(name="cfg5: SD2.x-shaped UNet (1024-dim text embeddings, linear proj_in/out, v-prediction), native full "
+                      "fine-tune (fp32 masters, autocast bf16) + EMA 0.995, batch 4/GPU, 96x96 latents",
+                 unet="sd2x", rank=None, batch=4, h=96, w=96, ctx_len=77, ctx_dim=1024, ema=0.995, prediction_type="v",
+                 full_finetune=True),
+}
+WORKLOAD = WORKLOADS["cfg2"]
+# synthetic image sizes of the bucketed workload (assigned to buckets by the bit-exact BucketManager)
+CFG4_SIZES = [(512, 512), (768, 512), (512, 768), (640, 448), (1024, 576), (576, 1024), (768, 1024), (1024, 768)]
 
 
 def load_peaks():
@@ -115,25 +137,61 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # synthetic data
 # ------------------------------------------------------------------------------------------------------------
-def synthetic_batches(n: int, batch: int, rank: int, pin: bool):
+def synthetic_batches(wl: dict, n: int, batch: int, rank: int, pin: bool, h=None, w=None):
     g = torch.Generator().manual_seed(SEED + 1000 * rank)
     out = []
     for _ in range(n):
-        lat = torch.randn(batch, 4, WORKLOAD["h"], WORKLOAD["w"], generator=g)
-        cond = torch.randn(batch, WORKLOAD["ctx_len"], WORKLOAD["ctx_dim"], generator=g)
+        lat = torch.randn(batch, 4, h or wl["h"], w or wl["w"], generator=g)
+        cond = torch.randn(batch, wl["ctx_len"], wl["ctx_dim"], generator=g)
         if pin:
             lat, cond = lat.pin_memory(), cond.pin_memory()
         out.append({"latents": lat, "conds": cond})
     return out
 
 
+def bucketed_schedule(wl: dict, rank: int, world: int, n_steps: int):
+    """The per-step (w, h) of THIS rank: DreamBooth instance/class pairs drawn by the bit-exact ``AspectSamplerDB``
+    (``modules/dataset/samplers.py:108-170`` over ``bucket.py:110-207``) from a synthetic id -> image-size map; every rank
+    shards the same id list with its own (world, rank).  Returns [(ids in collate order, (w, h))] of length n_steps."""
+    import numpy as np
+
+    from scal_sdt_b200.bucket import DEFAULT_BUCKET_CONFIG, AspectSamplerDB, collate_order
+    per_rank = wl["batch"] // 2                                   # instance items per batch; the class half doubles it
+    n_inst, n_cls = 16 * per_rank * world, 32 * per_rank * world
+    rs = np.random.RandomState(0)
+    inst = {i: CFG4_SIZES[int(k)] for i, k in enumerate(rs.randint(0, len(CFG4_SIZES), size=n_inst))}
+    cls = {i: CFG4_SIZES[int(k)] for i, k in enumerate(rs.randint(0, len(CFG4_SIZES), size=n_cls))}
+    cfg = dict(DEFAULT_BUCKET_CONFIG, manual={"max_size": 786432})   # the 23-bucket grid incl. 768x1024 (SURVEY 8 a-7)
+    random.seed(SEED)
+    sampler = AspectSamplerDB(inst, cls, 512, cfg, per_rank, SEED, world_size=world, global_rank=rank)
+    sched = []
+    while len(sched) < n_steps:                                   # epochs follow each other; the PRNG streams carry over
+        pairs = list(sampler)
+        if not pairs:
+            raise RuntimeError("empty shard: not enough synthetic ids for this world size")
+        for i in range(0, len(pairs) - per_rank + 1, per_rank):
+            order = collate_order(pairs[i:i + per_rank])
+            sched.append(([ix.value for ix in order], tuple(order[0].size)))
+    return sched[:n_steps]
+
+
 # ------------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port of the reference's torch path, on the host cores
+# the reference's torch path: CPU (oracle port, --impl reference / cpu_baseline) and eager torch on this GPU
 # ------------------------------------------------------------------------------------------------------------
-def run_cpu_reference(steps: int, warmup: int, sample_batch: int = 1):
-    from oracle.ref_trainer import RefTrainer
-    from scal_sdt_b200.targets import lora_unet_targets
+def make_targets(wl: dict):
+    from scal_sdt_b200.targets import full_unet_targets, lora_unet_targets
+    if wl.get("full_finetune"):
+        return full_unet_targets(lr=5e-6, weight_decay=1e-2)
+    return lora_unet_targets(wl["rank"], wl["alpha"], projections=wl["projections"])
+
+
+def make_unet(wl: dict):
     from scal_sdt_b200.unet import UNet2DConditionModel, UNetConfig
+    return UNet2DConditionModel(UNetConfig.sd15() if wl["unet"] == "sd15" else UNetConfig.sd2x())
+
+
+def run_cpu_reference(wl: dict, steps: int, warmup: int, sample_batch: int = 1):
+    from oracle.ref_trainer import RefTrainer
     cores = os.cpu_count() or 1
     try:
         import psutil
@@ -142,10 +200,12 @@ def run_cpu_reference(steps: int, warmup: int, sample_batch: int = 1):
         pass
     torch.set_num_threads(cores)
     torch.manual_seed(SEED)
-    unet = UNet2DConditionModel(UNetConfig.sd15())
-    tr = RefTrainer(unet, lora_unet_targets(WORKLOAD["rank"], WORKLOAD["alpha"]))
+    unet = make_unet(wl)
+    sample_batch = 2 if wl.get("bucketed") else sample_batch    # prior preservation needs an instance and a class half
+    tr = RefTrainer(unet, make_targets(wl), prediction_type=wl["prediction_type"], ema_decay=wl["ema"],
+                    prior_preservation=bool(wl.get("bucketed")), prior_loss_weight=wl.get("prior_loss_weight", 1.0))
     g = torch.Generator().manual_seed(SEED)
-    batches = synthetic_batches(2, sample_batch, 0, pin=False)
+    batches = synthetic_batches(wl, 2, sample_batch, 0, pin=False)
 
     def one(i):
         b = batches[i % len(batches)]
@@ -160,20 +220,69 @@ def run_cpu_reference(steps: int, warmup: int, sample_batch: int = 1):
         loss = one(i)
     dt = time.perf_counter() - t0
     return dict(value=sample_batch * steps / dt, seconds=dt, cores=torch.get_num_threads(), loss=float(loss),
-                sample=f"{steps} step(s) of batch {sample_batch} x 4x64x64 latents, same UNet/LoRA config, fp32 torch CPU "
-                       f"(oracle port: loralib/diffusers/lightning are not installable offline)")
+                sample=f"{steps} step(s) of batch {sample_batch} x 4x{wl['h']}x{wl['w']} latents, same UNet / target config, fp32 "
+                       f"torch CPU (oracle port: loralib/diffusers/lightning are not installable offline)")
+
+
+def run_torch_gpu_reference(wl: dict, device, steps: int = 5, warmup: int = 3):
+    """The comparator SURVEY 2.1 / BASELINE.md 5 name: the oracle trainer (fp32 modules, restated loralib layers =
+    F.linear + two matmuls + mul + add per site, torch AdamW, per-tensor EMA) as EAGER torch under autocast(bf16) on this
+    GPU, same batch as our arm.  None of this repo's kernels run on it (``fused.torch_only``)."""
+    from oracle.ref_trainer import RefTrainer
+    from scal_sdt_b200 import fused
+    torch.manual_seed(SEED)
+    with torch.device(device):
+        unet = make_unet(wl)
+    unet = unet.to(memory_format=torch.channels_last)
+    tr = RefTrainer(unet, make_targets(wl), prediction_type=wl["prediction_type"], ema_decay=wl["ema"],
+                    prior_preservation=bool(wl.get("bucketed")), prior_loss_weight=wl.get("prior_loss_weight", 1.0))
+    B = wl["batch"]
+    batches = [{k: v.to(device) for k, v in b.items()} for b in synthetic_batches(wl, 2, B, 0, pin=False)]
+    g = torch.Generator(device=device).manual_seed(SEED)
+
+    def one(i):
+        b = batches[i % len(batches)]
+        noise = torch.randn(b["latents"].shape, generator=g, device=device)
+        t = torch.randint(0, 1000, (B,), generator=g, dtype=torch.int64, device=device)
+        tr.optimizer.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = tr.training_step(b, noise, t)
+        loss.backward()
+        tr.optimizer.step()
+        if tr.ema is not None:
+            tr.ema.update()
+        return loss.detach()
+
+    with fused.torch_only():
+        for i in range(warmup):
+            one(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss = one(i)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": B / (ms * 1e-3), "unit": "latents/s", "ms_per_step": ms, "steps": steps, "loss": float(loss),
+           "what": "oracle trainer (restated loralib layers, torch AdamW, per-tensor EMA) as eager torch 2.11 / cuBLAS / cuDNN "
+                   "under torch.autocast(bfloat16) on this GPU, fp32 master weights, same batch; no kernel of this repo"}
+    del tr, unet, batches
+    torch.cuda.empty_cache()
+    return out
 
 
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = run_cpu_reference(args.steps, args.warmup)
+    wl = WORKLOADS[args.workload]
+    r = run_cpu_reference(wl, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "LoRA train latents/sec SD1.5 512^2", "value": r["value"], "unit": "latents/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD["name"] + " [reference arm: CPU, bounded sample batch 1]"},
+        "config": {"workload": wl["name"] + " [reference arm: CPU, bounded sample]"},
         "cpu_baseline": {"value": r["value"], "unit": "latents/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -185,24 +294,30 @@ def reference_main(args):
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
-def build_trainer(device, exchange):
+def build_trainer(wl: dict, device, exchange):
     from scal_sdt_b200 import NoiseScheduler
-    from scal_sdt_b200.targets import lora_unet_targets
     from scal_sdt_b200.trainer import LatentDiffusionTrainer
-    from scal_sdt_b200.unet import UNet2DConditionModel, UNetConfig
     torch.manual_seed(SEED)                                   # identical init on every rank (DDP broadcast equivalent)
     with torch.device(device):
-        unet = UNet2DConditionModel(UNetConfig.sd15())
-    unet = unet.to(torch.bfloat16)                                          # frozen base held in bf16
+        unet = make_unet(wl)
+    full = bool(wl.get("full_finetune"))
+    if not full:
+        unet = unet.to(torch.bfloat16)                                      # frozen base held in bf16
     if os.environ.get("SDT_UNET_FORMAT", "nhwc") == "nhwc":
         unet = unet.to(memory_format=torch.channels_last)
     else:
         unet.channels_last = False
-    sched = NoiseScheduler(prediction_type="epsilon")
-    tr = LatentDiffusionTrainer(unet, sched, lora_unet_targets(WORKLOAD["rank"], WORKLOAD["alpha"]),
-                                optimizer_params={"lr": 5e-4, "beta1": 0.9, "beta2": 0.999, "weight_decay": 2e-2, "eps": 1e-7},
-                                lr_scale={"enabled": True, "method": "sqrt"}, batch_size=WORKLOAD["batch"],
-                                exchange=exchange, seed=SEED)
+    sched = NoiseScheduler(prediction_type=wl["prediction_type"])
+    opt = ({"lr": 5e-6, "beta1": 0.9, "beta2": 0.999, "weight_decay": 1e-2, "eps": 1e-8} if full else
+           {"lr": 5e-4, "beta1": 0.9, "beta2": 0.999, "weight_decay": 2e-2, "eps": 1e-7})
+    tr = LatentDiffusionTrainer(unet, sched, make_targets(wl), optimizer_params=opt,
+                                lr_scale={"enabled": True, "method": "sqrt"}, batch_size=wl["batch"],
+                                ema={"enabled": wl["ema"] is not None, "decay": wl["ema"] or 0.0},
+                                prior_preservation={"enabled": bool(wl.get("bucketed")),
+                                                    "prior_loss_weight": wl.get("prior_loss_weight", 1.0)},
+                                exchange=exchange, seed=SEED, autocast_dtype=torch.bfloat16 if full else None)
+    if full:
+        tr.enable_overlapped_exchange()
     return tr
 
 
@@ -257,6 +372,33 @@ def elementwise_roofline(device, peaks):
     return out
 
 
+def cupti_step_kernels(step_fn):
+    """(name, start_us, duration_us) of every CUDA kernel of ONE step, in launch order, from CUPTI (torch.profiler)."""
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step_fn()
+        torch.cuda.synchronize()
+    ks = []
+    for e in prof.events():
+        if str(getattr(e, "device_type", "")).endswith("CUDA") and e.time_range.end > e.time_range.start:
+            ks.append((e.name, e.time_range.start, e.time_range.end - e.time_range.start))
+    ks.sort(key=lambda k: k[1])
+    return ks
+
+
+def exclusive_durations(ks):
+    """Per-kernel time ON the step's timeline: ``end_i - max(start_i, latest end of any earlier kernel)``.  With programmatic
+    dependent launch a kernel is resident (prologue, then ``griddepcontrol.wait``) while its predecessor still runs, so its
+    raw CUPTI duration contains the predecessor's tail; the exclusive figure is what the kernel adds to the step."""
+    out, horizon = [], None
+    for name, start, dur in ks:
+        end = start + dur
+        begin = start if horizon is None else max(start, horizon)
+        out.append((name, max(0.0, end - begin), dur))
+        horizon = end if horizon is None else max(horizon, end)
+    return out
+
+
 def ours_main(args):
     # Native libraries (NCCL's version banner, cuDNN warnings) write to fd 1; the contract is ONE JSON line on stdout,
     # so everything else is routed to stderr and the line is written to the saved descriptor at the end.
@@ -265,6 +407,9 @@ def ours_main(args):
     os.dup2(2, 1)
     import torch.distributed as dist
     from scal_sdt_b200 import GradExchange, _lib, build
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -279,12 +424,22 @@ def ours_main(args):
     exchange = GradExchange.from_torch_distributed(device)
     lib = _lib.load()
     peaks = load_peaks()
-    B = WORKLOAD["batch"]
+    B = wl["batch"]
+    bucketed = bool(wl.get("bucketed"))
 
-    tr = build_trainer(device, exchange)
-    n_lora = sum(p.numel() for p, _, _ in tr.arena.slots)
-    host = synthetic_batches(4, B, rank, pin=True)
-    dev = [{k: v.to(device) for k, v in b.items()} for b in host]
+    tr = build_trainer(wl, device, exchange)
+    n_params = sum(p.numel() for p, _, _ in tr.arena.slots)
+    n_steps_total = 2 * args.steps + max(args.warmup, 3) + 8
+    if bucketed:
+        sched = bucketed_schedule(wl, rank, world, n_steps_total)
+        shapes = sorted({s for _, s in sched})
+        host_by_shape = {s: synthetic_batches(wl, 1, B, rank, pin=True, h=s[1] // 8, w=s[0] // 8)[0] for s in shapes}
+        dev_by_shape = {s: {k: v.to(device) for k, v in b.items()} for s, b in host_by_shape.items()}
+        host = [host_by_shape[s] for _, s in sched]
+        dev = [dev_by_shape[s] for _, s in sched]
+    else:
+        host = synthetic_batches(wl, 4, B, rank, pin=True)
+        dev = [{k: v.to(device) for k, v in b.items()} for b in host]
 
     def barrier():
         if world > 1:
@@ -298,41 +453,51 @@ def ours_main(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up (eager), then capture the whole step as one CUDA graph ----
+    # ---- warm-up (eager), then capture the step as CUDA graph(s) ----
+    cursor = 0
     for i in range(max(args.warmup, 3)):
-        tr.step(dev[i % len(dev)])
+        tr.step(dev[cursor % len(dev)])
+        cursor += 1
     barrier()
     use_graph = not args.no_graph and not args.profile_step
-    if use_graph:
+    if use_graph and bucketed:
+        tr.enable_bucketed_cuda_graphs([dev_by_shape[s] for s in shapes])     # one forward/backward graph per bucket shape
+        do_step = tr.bucketed_graphed_step
+    elif use_graph:
         tr.enable_cuda_graph(dev[0])
+        do_step = tr.graphed_step
+    else:
+        do_step = tr.step
+    if use_graph:
         for i in range(2):
-            tr.graphed_step(dev[i % len(dev)])
+            do_step(dev[cursor % len(dev)])
+            cursor += 1
         barrier()
-    do_step = tr.graphed_step if use_graph else tr.step
 
     if args.profile_step:
         torch.cuda.profiler.start()
         tr.step(dev[0])
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        os.write(real_stdout, (json.dumps({"profiled": "one training step", "workload": WORKLOAD["name"]}) + "\n").encode())
+        os.write(real_stdout, (json.dumps({"profiled": "one training step", "workload": wl["name"]}) + "\n").encode())
         exchange.close()
         return 0
 
     # ---- value: device-resident inputs, no host sync inside the region ----
-    launches0 = lib.sdt_launch_count()
+    launches0, replayed0 = lib.sdt_launch_count(), tr.replayed_launches
+    first_timed = cursor
     with ClockSampler(local_rank) as clocks:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            loss = do_step(dev[i % len(dev)])
+            loss = do_step(dev[cursor % len(dev)])
+            cursor += 1
         e1.record()
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = lib.sdt_launch_count() - launches0        # eager launches (noise/timestep refresh are torch ops: not counted)
-    if use_graph:
-        launches += args.steps * tr.graph_launches_per_step     # our kernels inside the captured step, replayed K times
+    # eager launches counted by the library (noise/timestep refresh are torch ops: not counted) + our kernels inside replays
+    launches = (lib.sdt_launch_count() - launches0) + (tr.replayed_launches - replayed0)
     value = world * B * args.steps / (ms_total * 1e-3)
     final_loss = float(loss.item())
 
@@ -345,8 +510,9 @@ def ours_main(args):
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for i in range(args.steps):
-        hb = host[i % len(host)]
-        if use_graph:       # graphed_step copies the pinned host batch straight into the graph's static input buffers
+        hb = host[cursor % len(host)]
+        cursor += 1
+        if use_graph:       # graphed steps copy the pinned host batch straight into the graph's static input buffers
             batch = hb
         else:
             batch = {k: v.to(device, non_blocking=True) for k, v in hb.items()}
@@ -356,58 +522,66 @@ def ours_main(args):
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
     step_loss = float(loss_host[-1])
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    h2d = sum(sum(v.numel() * v.element_size() for v in host[(first_timed + args.steps + i) % len(host)].values())
+              for i in range(args.steps)) / args.steps
 
-    # ---- roofline of the dominant kernel: the fused LoRA GEMM launches of a real training step ----
-    # Pass 1 (eager, every rank: the all-reduce is collective): the ordered list of sites (kind, M, K, N, R) plus CUDA-event
-    # brackets.  Once the step is faster than the host can launch it, event brackets also contain the host's launch gap,
-    # so pass 2 takes the per-kernel durations of one replayed step from CUPTI (torch.profiler) and maps them onto the
-    # site list by launch order (forward sites first, then backward in reverse order; the order is deterministic).
+    # ---- every rank trained the same model: parameters and the last reduced gradient agree bit for bit ----
+    ranks_in_sync = None
+    if world > 1:
+        def checksum(t):
+            return int(t.view(torch.int32).to(torch.int64).sum().item())
+        mine = torch.tensor([checksum(tr.arena.params), checksum(tr.arena.grads)], dtype=torch.int64, device=device)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        ranks_in_sync = all(torch.equal(v, allv[0]) for v in allv)
+
+    # ---- roofline of the dominant kernel ----
+    # Pass 1 (eager, every rank: the all-reduce is collective): the ordered list of sites (kind, M, K, N, R).  Pass 2: the
+    # per-kernel timeline of one replayed step from CUPTI, mapped onto the site list by launch order (forward sites first,
+    # then backward in reverse order; the order is deterministic).
     from scal_sdt_b200 import lora as lora_mod
-    roof = None
+    roof, allreduce_us, step_kernel_us = None, None, None
+    prof_batch = dev[max(range(len(dev)), key=lambda i: dev[i]["latents"].numel())] if bucketed else dev[0]
     lora_mod.PROFILE = [] if rank == 0 else None
-    tr.step(dev[0])
+    tr.step(prof_batch)
     torch.cuda.synchronize()
-    rec = lora_mod.PROFILE
+    rec = lora_mod.PROFILE or []
     lora_mod.PROFILE = None
-    kernel_times = None
-    if rank == 0 or world > 1:
-        try:
-            from torch.profiler import ProfilerActivity, profile
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                do_step(dev[1 % len(dev)])
-                torch.cuda.synchronize()
-            ks = []
-            for e in prof.events():
-                if "lora_gemm" in e.name and str(getattr(e, "device_type", "")).endswith("CUDA"):
-                    ks.append((e.time_range.start, e.time_range.end - e.time_range.start))
-            ks.sort()
-            kernel_times = [d * 1e-6 for _, d in ks]      # seconds
-        except Exception as exc:  # noqa: BLE001
-            print(f"[bench] CUPTI pass unavailable ({exc}); falling back to CUDA-event brackets", file=sys.stderr)
-    if rank == 0:
+    ks = None
+    try:
+        ks = exclusive_durations(cupti_step_kernels(lambda: do_step(prof_batch)))
+    except Exception as exc:  # noqa: BLE001
+        print(f"[bench] CUPTI pass unavailable ({exc})", file=sys.stderr)
+    if ks is not None:
+        nccl = [k for k in ks if "nccl" in k[0].lower()]
+        allreduce_us = {"launches": len(nccl), "raw_us": sum(k[2] for k in nccl), "exclusive_us": sum(k[1] for k in nccl)} if nccl else None
+        step_kernel_us = sum(k[1] for k in ks)
+    if rank == 0 and rec:
         fwd_sites = [r for r in rec if r[0] == "fwd"]
         bwd_sites = [r for r in rec if r[0] == "bwd"]
         n_fwd = len(fwd_sites)
-        timing = "cuda_events"
+        timing = "cuda_events (eager step)"
         fwd_t = [a.elapsed_time(b) * 1e-3 for *_, a, b in fwd_sites]
+        fwd_raw = None
         bwd_gemm_t = None
         t_bwd = sum(a.elapsed_time(b) for *_, a, b in bwd_sites) * 1e-3
-        if kernel_times is not None and len(kernel_times) == n_fwd + len(bwd_sites):
-            timing = "cupti_kernel_durations"
-            fwd_t = kernel_times[:n_fwd]
-            bwd_gemm_t = kernel_times[n_fwd:]
+        gemm_k = [k for k in (ks or []) if "lora_gemm" in k[0]]
+        if len(gemm_k) == n_fwd + len(bwd_sites):
+            timing = "cupti, exclusive time on the replayed step's timeline (end - max(start, previous kernel's end))"
+            fwd_t = [k[1] * 1e-6 for k in gemm_k[:n_fwd]]
+            fwd_raw = sum(k[2] for k in gemm_k[:n_fwd]) * 1e-6
+            bwd_gemm_t = [k[1] * 1e-6 for k in gemm_k[n_fwd:]]
         f_fwd, f_bwd = site_flops(rec)
         t_fwd = sum(fwd_t)
         ach = f_fwd / t_fwd / 1e12
         # per-shape view of the same forward launches: which bound applies to which class of site
-        shapes = {}
+        shapes_acc = {}
         for (kind, M, K, N, R, G, *_), sec in zip(fwd_sites, fwd_t):
-            e = shapes.setdefault((M, K, N, R, G), [0, 0.0])
+            e = shapes_acc.setdefault((M, K, N, R, G), [0, 0.0])
             e[0] += 1
             e[1] += sec
         by_shape = []
-        for (M, K, N, R, G), (cnt, sec) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+        for (M, K, N, R, G), (cnt, sec) in sorted(shapes_acc.items(), key=lambda kv: -kv[1][1]):
             fl = G * (2.0 * M * K * N + 2.0 * M * R * (K + N))
             by = 2.0 * (M * K + G * (K * N + R * (K + N) + M * N + M * R))      # a grouped launch reads its shared X once
             tf, gbs = fl * cnt / sec / 1e12, by * cnt / sec / 1e9
@@ -417,9 +591,9 @@ def ours_main(args):
         # DRAM bytes per GEMM launch from the committed ncu pass over one training step (dram__bytes_read + write summed over
         # the lora_gemm* launches / their count); bench.py cannot run ncu itself
         traffic, traffic_src = None, None
-        for tname in ("r01_v21_kernels_per_step_ncu.json", "r01_v15_kernels_per_step_ncu.json", "r01_v5_lora_kernels_per_step_ncu.json"):
+        for tname in ("r02_kernels_per_step_ncu.json", "r01_v21_kernels_per_step_ncu.json"):
             tpath = os.path.join(ROOT, "profiles", tname)
-            if not os.path.exists(tpath):
+            if args.workload != "cfg2" or not os.path.exists(tpath):
                 continue
             with open(tpath) as f:
                 tj = json.load(f)
@@ -431,24 +605,49 @@ def ours_main(args):
         alg_bytes = sum(2.0 * (M * K + G * (K * N + R * (K + N) + M * N + M * R)) for kind, M, K, N, R, G, *_ in fwd_sites) / max(n_fwd, 1)
         dx_flops = sum(G * (2.0 * M * K * N + 2.0 * M * R * (K + N)) for kind, M, K, N, R, G, dx, *_ in bwd_sites if dx) + \
             sum(G * 2.0 * M * R * N for kind, M, K, N, R, G, dx, *_ in bwd_sites if not dx)
-        backward = {"kernels": "lora_gemm* (dX, G) + lora_wgrad_kernel (dA and dB in one launch)", "timing": "cuda_events",
+        backward = {"kernels": "lora_gemm* (dX, G) + lora_wgrad_kernel (dA and dB in one launch)", "timing": "cuda_events (eager step)",
                     "achieved": f_bwd / t_bwd / 1e12, "frac": f_bwd / t_bwd / 1e12 / peaks["tf_sustained"]}
         if bwd_gemm_t is not None:
             backward["dx_gemm"] = {"timing": timing, "achieved": dx_flops / sum(bwd_gemm_t) / 1e12,
                                    "frac": dx_flops / sum(bwd_gemm_t) / 1e12 / peaks["tf_sustained"],
                                    "seconds_per_step": sum(bwd_gemm_t)}
-        roof = {"kernel": "lora_gemm_kernel / lora_gemm_pair_kernel (K1: fused X W^T + bias + s (X A^T) B^T), every forward launch of a step (192 projections; q/k/v and cross-attention k/v go out as grouped launches)",
+            wg = [k for k in ks if "lora_wgrad" in k[0]]
+            if wg:
+                wg_bytes = sum(G * 2.0 * M * (K + N + 2 * R) for kind, M, K, N, R, G, *_ in bwd_sites)
+                backward["wgrad"] = {"launches": len(wg), "seconds_per_step": sum(k[1] for k in wg) * 1e-6,
+                                     "algorithmic_gbs": wg_bytes / (sum(k[1] for k in wg) * 1e-6) / 1e9,
+                                     "frac_hbm": wg_bytes / (sum(k[1] for k in wg) * 1e-6) / 1e9 / peaks["hbm"]}
+        roof = {"kernel": "lora_gemm_kernel / lora_gemm_pair_kernel (K1: fused X W^T + bias + s (X A^T) B^T), every forward launch of a step "
+                          f"({sum(r[5] for r in fwd_sites)} projections; q/k/v and cross-attention k/v go out as grouped launches)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src, "timing": timing,
+                "raw_cupti_seconds_per_step": fwd_raw,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peaks["source"] + ", sustained bf16",
                 "launches_timed": n_fwd, "avg_launch_us": 1e6 * t_fwd / max(n_fwd, 1),
                 "flops_per_step": f_fwd, "forward_gemm_seconds_per_step": t_fwd,
                 "backward": backward, "by_shape": by_shape, "elementwise": elementwise_roofline(device, peaks)}
+    elif rank == 0 and ks is not None:
+        # native fine-tune: no LoRA GEMMs on the path; the dominant in-scope kernel is the fused AdamW + EMA pass over the arena
+        ad = [k for k in ks if "adamw_flat" in k[0]]
+        if ad:
+            sec = sum(k[1] for k in ad) * 1e-6
+            nbytes = (28.0 + (8.0 if wl["ema"] is not None else 0.0)) * n_params
+            roof = {"kernel": "adamw_flat_kernel (AdamW + EMA lerp over the flat fp32 arena, one pass)", "bound": "hbm",
+                    "achieved": nbytes / sec / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / peaks["hbm"],
+                    "traffic": None, "timing": "cupti, exclusive time on the replayed step's timeline", "launches_timed": len(ad),
+                    "algorithmic_bytes_per_launch": nbytes / len(ad), "peak_source": peaks["source"],
+                    "elementwise": elementwise_roofline(device, peaks)}
 
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----
-    cpu = None
+    # ---- the reference's own torch path on this GPU, and on the host cores (rank 0, N=1 only) ----
+    torch_gpu, cpu = None, None
+    if rank == 0 and world == 1 and not args.no_torch_baseline:
+        tr.release_cuda_graph()
+        try:
+            torch_gpu = run_torch_gpu_reference(wl, device)
+        except Exception as exc:  # noqa: BLE001
+            torch_gpu = {"unavailable": f"{type(exc).__name__}: {exc}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = run_cpu_reference(steps=2, warmup=1)
+        r = run_cpu_reference(wl, steps=2, warmup=1)
         cpu = {"value": r["value"], "unit": "latents/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:
@@ -456,27 +655,46 @@ def ours_main(args):
             "metric": "LoRA train latents/sec SD1.5 512^2", "value": value, "unit": "latents/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD["name"], "global_batch": world * B, "lora_params": n_lora,
-                       "parallelism": f"dp{world}", "optimizer": "fused AdamW over the flat LoRA arena",
-                       "gradient_checkpointing": False, "cuda_graph": bool(use_graph),
+            "config": {"workload": wl["name"], "global_batch": world * B, "trainable_params": n_params,
+                       "parallelism": f"dp{world}", "optimizer": "fused AdamW over the flat parameter arena",
+                       "gradient_checkpointing": False,
+                       "cuda_graph": ("one forward/backward graph per bucket shape" if bucketed else "whole step") if use_graph else False,
+                       "pdl": os.environ.get("SDT_PDL", "1") != "0",
                        "l2": "no flush: a step streams > 10 GB of weights/activations, far beyond the 126 MB L2"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "latents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "final_loss": final_loss, "e2e_last_loss": step_loss,
-            "roofline": roof, "cpu_baseline": cpu,
+            "ranks_in_sync": ranks_in_sync, "allreduce_us": allreduce_us, "step_kernel_us": step_kernel_us,
+            "roofline": roof, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu,
         }
+        if bucketed:
+            line["config"]["bucket_shapes_this_rank"] = [list(s) for s in shapes]
+            line["config"]["first_timed_batches_rank0"] = [{"ids": ids, "size": list(s)} for ids, s in sched[first_timed:first_timed + 4]]
+        if torch_gpu is not None and "value" in torch_gpu:
+            line["vs_torch_gpu"] = {"e2e_ratio": e2e_value / torch_gpu["value"], "ratio": value / torch_gpu["value"]}
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    # teardown: the captured graph references the communicator, so it goes first
+    # teardown: the captured graphs reference the communicator, so they go first; sdt_comm_destroy drains the device,
+    # finalises and destroys.  A watchdog keeps a wedged communicator from holding the job open after the result is out.
     tr.release_cuda_graph()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-        # every rank has its result out; communicator teardown after graph capture has been seen to block, and there is
-        # nothing left to flush but the process itself
-        sys.stderr.flush()
-        os._exit(0)
+        done = threading.Event()
+
+        def _close():
+            try:
+                exchange.close()
+            finally:
+                done.set()
+        threading.Thread(target=_close, daemon=True).start()
+        if not done.wait(timeout=30):
+            print(f"[bench] rank {rank}: sdt_comm_destroy did not return within 30 s; exiting without it", file=sys.stderr)
+            sys.stderr.flush()
+            os._exit(0)
+        dist.destroy_process_group()
+        return 0
     exchange.close()
     return 0
 
@@ -487,8 +705,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="BASELINE.json configs[1..4]; cfg2 (default) is the line the driver records")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph")
+    ap.add_argument("--no-torch-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -60,3 +60,62 @@ class GradExchange:
         if self._native:
             _lib.check(_lib.load().sdt_comm_destroy(), "sdt_comm_destroy")
             self._native = False
+
+
+class OverlappedExchange:
+    """Chunked gradient all-reduce overlapped with backward (DDP's bucketing, ``train.py:98-109``, on the flat arena).
+
+    The arena is cut into contiguous chunks of about ``chunk_bytes`` at parameter boundaries.  Every parameter carries a
+    post-accumulate-grad hook; when the last parameter of a chunk has received its gradient the chunk's ``ncclAllReduce``
+    is issued on a side stream that waits for an event recorded on the compute stream at that moment.  Chunks fill from the
+    END of the arena (backward runs the network in reverse), so the first all-reduces are on the wire while most of backward
+    is still ahead.  ``finish()`` issues whatever is left (parameters that received no gradient) and makes the compute stream
+    wait for the side stream.  Everything is stream-ordered: it can be captured into a CUDA graph."""
+
+    def __init__(self, arena, exchange: GradExchange, chunk_bytes: int = 64 << 20):
+        self.arena, self.exchange = arena, exchange
+        # CPU arenas (the gloo host-logic tests) reduce each chunk synchronously: same partition, same hooks, no streams
+        self.stream = torch.cuda.Stream(device=arena.device) if torch.device(arena.device).type == "cuda" else None
+        target = max(1, chunk_bytes // 4)
+        self.chunks: list[dict] = []
+        cur = None
+        for p, off, n in arena.slots:
+            if cur is None or cur["end"] - cur["begin"] >= target:
+                cur = {"begin": off, "end": off, "params": 0, "pending": 0, "sent": False}
+                self.chunks.append(cur)
+            cur["end"] = off + n
+            cur["params"] += 1
+            p.register_post_accumulate_grad_hook(lambda _p, c=cur: self._arrived(c))
+        for i, c in enumerate(self.chunks):         # a chunk owns the alignment padding up to the next chunk's start
+            c["end"] = self.chunks[i + 1]["begin"] if i + 1 < len(self.chunks) else arena.numel
+        self.launched = 0
+
+    def begin(self) -> None:
+        for c in self.chunks:
+            c["pending"], c["sent"] = c["params"], False
+        self.launched = 0
+
+    def _send(self, c: dict) -> None:
+        c["sent"] = True
+        self.launched += 1
+        if self.stream is None:
+            self.exchange.all_reduce_mean_(self.arena.grads[c["begin"]:c["end"]])
+            return
+        cur = torch.cuda.current_stream(self.arena.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            self.exchange.all_reduce_mean_(self.arena.grads[c["begin"]:c["end"]])
+
+    def _arrived(self, c: dict) -> None:
+        c["pending"] -= 1
+        if c["pending"] == 0 and not c["sent"]:
+            self._send(c)
+
+    def finish(self) -> None:
+        for c in reversed(self.chunks):
+            if not c["sent"]:
+                self._send(c)
+        if self.stream is not None:
+            torch.cuda.current_stream(self.arena.device).wait_stream(self.stream)

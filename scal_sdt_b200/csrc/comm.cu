@@ -24,6 +24,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommFinalize)(ncclComm_t) = nullptr;     // optional (NCCL >= 2.14)
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -48,6 +49,7 @@ static int load_nccl() {
   SDT_SYM(CommDestroy, "ncclCommDestroy");
   SDT_SYM(GetErrorString, "ncclGetErrorString");
 #undef SDT_SYM
+  *(void**)(&g_nccl.CommFinalize) = dlsym(h, "ncclCommFinalize");
   g_nccl.handle = h;
   return SDT_OK;
 }
@@ -103,6 +105,11 @@ extern "C" int sdt_allreduce(void* buf, int64_t count, int dtype, void* stream) 
 
 extern "C" int sdt_comm_destroy(void) {
   if (g_comm == nullptr) return SDT_OK;
+  // Order matters after the collective has been part of a captured graph: the caller destroys the graph exec first
+  // (LatentDiffusionTrainer.release_cuda_graph), then every stream is drained here, the communicator is finalised (flushes
+  // its proxy / outstanding work) and only then destroyed.  Destroying with captured work still referenced blocks forever.
+  SDT_CUDA_OK(cudaDeviceSynchronize());
+  if (g_nccl.CommFinalize != nullptr) SDT_NCCL_OK(g_nccl.CommFinalize(g_comm));
   SDT_NCCL_OK(g_nccl.CommDestroy(g_comm));
   g_comm = nullptr;
   g_world = 0;

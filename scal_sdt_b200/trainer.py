@@ -48,8 +48,13 @@ class LatentDiffusionTrainer:
     def __init__(self, unet: nn.Module, scheduler: NoiseScheduler, unet_targets: Optional[list] = None, *,
                  optimizer_params: Optional[dict] = None, lr_scale: Optional[dict] = None, batch_size: int = 1,
                  prior_preservation: Optional[dict] = None, ema: Optional[dict] = None,
-                 exchange: Optional[GradExchange] = None, seed: Optional[int] = None):
+                 exchange: Optional[GradExchange] = None, seed: Optional[int] = None,
+                 autocast_dtype: Optional[torch.dtype] = None):
         self.unet = unet
+        # native fine-tune: fp32 master weights ARE the module's parameters and the host model runs under torch.autocast, the
+        # reference's own mode (Lightning ``precision: 16 | bf16``, configs/__reserved_default__.yaml:44)
+        self.autocast_dtype = autocast_dtype
+        self.replayed_launches = 0           # libsdt_b200 kernels launched through graph replays so far
         self.scheduler = scheduler
         self.exchange = exchange or GradExchange(0, 1)
         self.device = next(unet.parameters()).device
@@ -93,7 +98,11 @@ class LatentDiffusionTrainer:
             timesteps = torch.randint(0, self.scheduler.config.num_train_timesteps, (latents.shape[0],), dtype=torch.int64,
                                       device=latents.device, generator=self.generator)
         noisy, target = self.scheduler.noise_and_target(latents, noise, timesteps)
-        pred = self.unet(noisy, timesteps, conds).sample
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                pred = self.unet(noisy, timesteps, conds).sample
+        else:
+            pred = self.unet(noisy, timesteps, conds).sample
         return self.criterion(pred.contiguous(), target, want_elementwise=want_elementwise)
 
     # ---- modules/model.py:318-348 ----------------------------------------------------------------------
@@ -102,8 +111,25 @@ class LatentDiffusionTrainer:
             raise NotImplementedError("this path consumes cached latents/conds (the VAE / text encoder are out of scope)")
         return self._denoise_loss(batch["latents"], batch["conds"], noise, timesteps)
 
+    def enable_overlapped_exchange(self, chunk_bytes: int = 64 << 20) -> None:
+        """Reduce the gradient arena in chunks on a side stream WHILE backward is still producing the earlier layers'
+        gradients (``train.py:98-109``: what DDP's bucketed reducer does for the reference).  For a native fine-tune the
+        payload is the whole UNet (3.46 GB fp32 at SD scale) and a serial all-reduce after backward is pure added
+        step time.  Only for arenas whose gradients arrive through autograd (LoRA sites write theirs from the kernels; their
+        27-96 MB go out as one all-reduce)."""
+        from .comm import OverlappedExchange
+        if self.exchange.world > 1 and not isinstance(self.arena, LoraArena):
+            self._overlap = OverlappedExchange(self.arena, self.exchange, chunk_bytes)
+
+    def _exchange_gradients(self) -> None:
+        ov = getattr(self, "_overlap", None)
+        if ov is not None:
+            ov.finish()
+        else:
+            self.exchange.all_reduce_mean_(self.arena.grads)
+
     def optimizer_step(self) -> None:
-        self.exchange.all_reduce_mean_(self.arena.grads)
+        self._exchange_gradients()
         if self.unet_ema is not None and self.unet_ema._shadow_flat is not None:
             ema = self.unet_ema
             if not ema._shadow_flat.is_cuda:        # a caller mirrored the reference's ``unet_ema.to("cpu")`` (model.py:412)
@@ -123,6 +149,8 @@ class LatentDiffusionTrainer:
         (device resident; call ``.item()`` only when logging)."""
         self.optimizer.zero_grad()
         loss = self.training_step(batch, self.global_step, noise, timesteps)
+        if getattr(self, "_overlap", None) is not None:
+            self._overlap.begin()
         loss.backward()
         self.optimizer_step()
         self.global_step += 1
@@ -150,8 +178,10 @@ class LatentDiffusionTrainer:
         def body():
             self.optimizer.zero_grad()
             loss = self._denoise_loss(self._g_lat, self._g_cond, self._g_noise, self._g_t)
+            if getattr(self, "_overlap", None) is not None:
+                self._overlap.begin()
             loss.backward()
-            self.exchange.all_reduce_mean_(self.arena.grads)
+            self._exchange_gradients()
             self.optimizer.step(use_device_hyper=True, ema_shadow=self.unet_ema._shadow_flat if fused_ema else None,
                                 ema_one_minus_decay_dev=self._g_omd if fused_ema else None)
             if isinstance(self.arena, LoraArena):
@@ -203,12 +233,83 @@ class LatentDiffusionTrainer:
         if isinstance(self.arena, LoraArena):
             self.arena.pack()
 
-    def release_cuda_graph(self) -> None:
-        """Drop the captured graph (it pins the NCCL communicator and a private memory pool)."""
-        if getattr(self, "_graph", None) is not None:
+    # ---- one graph per bucket shape (mixed-resolution batches) -----------------------------------------------------
+    def enable_bucketed_cuda_graphs(self, example_batches: list, warmup: int = 2) -> None:
+        """Aspect-ratio-bucketed training (``modules/dataset/bucket.py:154-207``) hands every rank a different latent shape per
+        step, so one captured step does not do.  Per distinct ``(latents.shape, conds.shape)``: ONE graph of zero_grad ->
+        noise/target -> forward -> loss -> backward, all sharing one memory pool (they never run concurrently).  The exchange
+        and the update are shape-independent and stay outside: all-reduce + AdamW(+EMA) + repack are four launches.  No
+        collective is captured or executed while a shape is being prepared, so ranks may meet new shapes at different
+        steps."""
+        dev = self.device
+        if not hasattr(self, "_shape_graphs"):
+            self._shape_graphs = {}
+            self._graph_pool = torch.cuda.graph_pool_handle()
+            self._g_t_shared = {}
+            if not hasattr(self, "_g_omd"):
+                from ._lib import PinnedRing
+                self._g_omd = torch.zeros(1, dtype=torch.float32, device=dev)
+                self._g_omd_host = PinnedRing(self._g_omd)
+        for ex in example_batches:
+            key = (tuple(ex["latents"].shape), tuple(ex["conds"].shape))
+            if key in self._shape_graphs:
+                continue
+            ent = {"lat": ex["latents"].to(dev).clone(), "cond": ex["conds"].to(dev).clone()}
+            ent["noise"] = torch.empty_like(ent["lat"])
+            ent["t"] = torch.zeros(ent["lat"].shape[0], dtype=torch.int64, device=dev)
+
+            def body(e=ent):
+                self.optimizer.zero_grad()
+                loss = self._denoise_loss(e["lat"], e["cond"], e["noise"], e["t"])
+                loss.backward()
+                return loss.detach()
+
+            saved = self._snapshot_train_state()
+            ent["noise"].normal_(generator=self.generator)
+            ent["t"].random_(0, self.scheduler.config.num_train_timesteps, generator=self.generator)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            from . import _lib
+            before = _lib.load().sdt_launch_count()
+            ent["graph"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ent["graph"], pool=self._graph_pool):
+                ent["loss"] = body()
+            ent["launches"] = int(_lib.load().sdt_launch_count() - before)
+            self._restore_train_state(saved)
+            self._shape_graphs[key] = ent
+
+    def bucketed_graphed_step(self, batch: dict) -> torch.Tensor:
+        """``step`` for a batch whose shape was prepared by ``enable_bucketed_cuda_graphs``: replay that shape's forward /
+        backward graph, then exchange + update eagerly."""
+        key = (tuple(batch["latents"].shape), tuple(batch["conds"].shape))
+        ent = self._shape_graphs.get(key)
+        if ent is None:
+            raise KeyError(f"no captured graph for batch shape {key}: pass an example to enable_bucketed_cuda_graphs first")
+        ent["lat"].copy_(batch["latents"], non_blocking=True)
+        ent["cond"].copy_(batch["conds"], non_blocking=True)
+        ent["noise"].normal_(generator=self.generator)
+        ent["t"].random_(0, self.scheduler.config.num_train_timesteps, generator=self.generator)
+        ent["graph"].replay()
+        self.replayed_launches += ent["launches"]
+        self.optimizer_step()
+        self.global_step += 1
+        return ent["loss"]
+
+    def release_cuda_graph(self) -> None:
+        """Drop the captured graphs (they pin the NCCL communicator and a private memory pool)."""
+        if getattr(self, "_graph", None) is not None or getattr(self, "_shape_graphs", None):
+            torch.cuda.synchronize()
+        if getattr(self, "_graph", None) is not None:
             self._graph.reset()
             self._graph = None
+        for ent in getattr(self, "_shape_graphs", {}).values():
+            ent["graph"].reset()
+        self._shape_graphs = {}
 
     def _refresh_step_inputs(self) -> None:
         """Eager, tiny: new noise / timesteps (modules/model.py:294,297-298) and the step-dependent optimizer scalars."""
@@ -234,6 +335,7 @@ class LatentDiffusionTrainer:
             slot["_event"] = ev
         self._refresh_step_inputs()
         self._graph.replay()
+        self.replayed_launches += self.graph_launches_per_step
         self.global_step += 1
         return self._g_loss
 

@@ -38,6 +38,32 @@ def _worker(rank, world, port, q):
         ex.all_reduce_mean_(arena.grads)
         expect = (1 + world) / 2.0
         ok_grad = all(torch.allclose(p.grad, torch.full_like(p.grad, expect * (i + 1))) for i, p in enumerate(net.parameters()))
+        # chunked exchange driven by autograd hooks (the overlapped all-reduce of a native fine-tune): same means as one
+        # all-reduce of the arena, every chunk sent exactly once, chunks cover the arena without gaps
+        from scal_sdt_b200.comm import OverlappedExchange
+        torch.manual_seed(1)
+        net2 = nn.Sequential(nn.Linear(5, 7), nn.Tanh(), nn.Linear(7, 7), nn.Tanh(), nn.Linear(7, 2), nn.Linear(2, 2))
+        for p in net2[5].parameters():
+            p.requires_grad_(False)                           # a frozen tail: never in the arena
+        arena2 = ParamArena([{"params": [p for p in net2.parameters() if p.requires_grad]}])
+        ov = OverlappedExchange(arena2, ex, chunk_bytes=160)
+        cover = [(c["begin"], c["end"]) for c in ov.chunks]
+        ok_cover = cover[0][0] == 0 and cover[-1][1] == arena2.numel and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+        x = torch.full((3, 5), float(rank + 1))
+        arena2.zero_grad()
+        ov.begin()
+        net2(x).sum().backward()
+        sent_in_backward = ov.launched
+        local = None
+        ov.finish()
+        got = arena2.grads.clone()
+        # reference: the same local gradients reduced in one piece
+        arena2.zero_grad()
+        net2(x).sum().backward()
+        ex.all_reduce_mean_(arena2.grads)
+        ok_overlap = (ok_cover and len(ov.chunks) >= 3 and sent_in_backward == len(ov.chunks) and ov.launched == len(ov.chunks)
+                      and torch.allclose(got, arena2.grads, rtol=0, atol=0))
+        ok_grad = ok_grad and ok_overlap
         # sharded sampler
         sizes = [(512, 512), (768, 512), (512, 768), (640, 448)]
         rs = np.random.RandomState(0)
