@@ -80,14 +80,20 @@ int sdt_lora_linear_fwd_group(const sdt_lora_problem* problems /* host */, int n
  *     dB (+)= dY^T Ts                   [N,r_true] f32
  * SDT_BF16: dy[M,N], x[M,K], t_save[M,r], g_ws[M,r] bf16; wt = W^T [K,N] bf16 (cached copy of the
  *           frozen weight); At = A^T [K,r] bf16; Bt = B^T [r,N] bf16 (from sdt_lora_pack).
- *           dA/dB are f32 and are ACCUMULATED into (split-M partial sums use red.global.add):
- *           zero them first unless accumulating across micro-batches.  r_true <= r is the
- *           un-padded rank: only dA[:r_true,:] and dB[:, :r_true] (row stride r_true) are written.
- * SDT_F32 : wt = W [N,K] (no transposed copy needed), At = A [r,K], Bt = B [N,r], r_true == r.
+ *           dA/dB are f32 and are ACCUMULATED into: zero them first unless accumulating across
+ *           micro-batches.  r_true <= r is the un-padded rank: only dA[:r_true,:] and
+ *           dB[:, :r_true] (row stride r_true) are written.
+ *           `ws`: device workspace of sdt_lora_wgrad_workspace_bytes() bytes, 16-byte aligned, ZEROED ONCE by the
+ *           caller (the kernels leave it zeroed where it matters), used by one stream at a time.  With it the
+ *           token-slice partial sums of dA / dB are combined in a fixed order (two stages inside the one launch):
+ *           gradients are bit-identical from run to run, like the reference's torch path.  ws == NULL: the partials
+ *           leave through red.global.add (same values up to f32 summation order, not reproducible).
+ * SDT_F32 : wt = W [N,K] (no transposed copy needed), At = A [r,K], Bt = B [N,r], r_true == r; ws unused.
  */
+size_t sdt_lora_wgrad_workspace_bytes(void);
 int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt, const void* At, const void* Bt,
                         const void* t_save, float scaling, void* dx, void* g_ws, float* dA, float* dB,
-                        int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* stream);
+                        int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* ws, void* stream);
 
 /* ---- K2 (grouped): backward of projections that read ONE input (to_q / to_k / to_v) ----------------------
  * The reference's autograd runs three backward GEMMs and two adds for dX = sum_q (dY_q W_q + s (dY_q B_q) A_q).  Here the sum
@@ -104,7 +110,8 @@ typedef struct {
 } sdt_lora_bwd_problem;
 int sdt_lora_linear_bwd_group_supported(int n_problems, int need_dx, int64_t M, int64_t K, int64_t N, int r);
 int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems /* host */, int n_problems, float scaling, void* dx,
-                              int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* stream);
+                              int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* ws /* as above */,
+                              void* stream);
 
 /* ---- LoRA operand packing (multi-tensor, one launch for all sites) ---------------------------
  * For every site i: from the f32 master lora_A[r_true,K], lora_B[N,r_true] write the four bf16

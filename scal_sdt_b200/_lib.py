@@ -52,10 +52,11 @@ SIGNATURES = {
     "sdt_lora_linear_fwd_group": (c_int, [c_void_p, c_int, c_float, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sdt_lora_linear_bwd_group_supported": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int]),
     "sdt_lora_linear_bwd_group": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
-                                          c_void_p]),
+                                          c_void_p, c_void_p]),
+    "sdt_lora_wgrad_workspace_bytes": (c_size_t, []),
     "sdt_lora_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
-                                    c_void_p]),
+                                    c_void_p, c_void_p]),
     "sdt_lora_pack": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     "sdt_noise_target": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64,
                                  c_int64, c_int, c_void_p, c_void_p]),
@@ -128,6 +129,27 @@ def dtype_code(dtype) -> int:
 def stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+_wgrad_ws = {}
+
+
+def wgrad_workspace() -> int:
+    """Device pointer of the deterministic dA / dB reduction workspace of the CURRENT (device, stream): allocated and zeroed
+    once, then reused by every backward launch on that stream (the kernels leave its counters at zero).  SDT_WGRAD_ATOMIC=1
+    selects the atomic accumulation instead (A/B measurements; not reproducible run to run)."""
+    import os
+
+    import torch
+    if os.environ.get("SDT_WGRAD_ATOMIC", "0") == "1":
+        return 0
+    st = torch.cuda.current_stream()
+    key = (st.device.index, st.cuda_stream)
+    ws = _wgrad_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(load().sdt_lora_wgrad_workspace_bytes(), dtype=torch.uint8, device=st.device)
+        _wgrad_ws[key] = ws
+    return ws.data_ptr()
 
 
 def ptr(t) -> int:

@@ -8,14 +8,16 @@ namespace sdt {
 int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
                    void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, cudaStream_t st);
 int lora_wgrad_pair_bf16(const void* x, const void* g, float* dA, int64_t K, const void* dy, const void* ts, float* dB,
-                         int64_t N, int64_t M, int r, int r_true, cudaStream_t st);
+                         int64_t N, int64_t M, int r, int r_true, void* ws, cudaStream_t st);
+size_t lora_wgrad_workspace_bytes();
 int lora_fwd_f32(const float* x, const float* w, const float* bias, const float* A, const float* B, float scaling,
                  float* y, float* t_save, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st);
 int lora_bwd_f32(const float* dy, const float* x, const float* w, const float* A, const float* B, const float* t_save,
                  float scaling, float* dx, float* g_ws, float* dA, float* dB, int64_t M, int64_t K, int64_t N, int r,
                  cudaStream_t st);
 struct WgradSite { const void* x; const void* g; float* dA; const void* dy; const void* ts; float* dB; };
-int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, cudaStream_t st);
+int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, void* ws,
+                          cudaStream_t st);
 void debug_set(int key, uint64_t value);
 }  // namespace sdt
 
@@ -61,7 +63,7 @@ extern "C" int sdt_lora_linear_fwd_group(const sdt_lora_problem* problems, int n
 
 extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt, const void* At, const void* Bt,
                                    const void* t_save, float scaling, void* dx, void* g_ws, float* dA, float* dB,
-                                   int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* stream) {
+                                   int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* ws, void* stream) {
   SDT_REQUIRE(dy, SDT_ERR_ARG, "sdt_lora_linear_bwd: null dy");
   SDT_REQUIRE(M > 0 && K > 0 && N > 0 && r >= 0, SDT_ERR_ARG, "sdt_lora_linear_bwd: bad sizes");
   SDT_REQUIRE(dx != nullptr || r > 0, SDT_ERR_ARG, "sdt_lora_linear_bwd: nothing to compute");
@@ -78,7 +80,7 @@ extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt
                             dx != nullptr, st);
     if (rc != SDT_OK || r == 0) return rc;
     // dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]: one launch for both reductions
-    return lora_wgrad_pair_bf16(x, g_ws, dA, K, dy, t_save, dB, N, M, r, r_true, st);
+    return lora_wgrad_pair_bf16(x, g_ws, dA, K, dy, t_save, dB, N, M, r, r_true, ws, st);
   }
   if (dtype == SDT_F32) {
     SDT_REQUIRE(r_true == r, SDT_ERR_ARG, "sdt_lora_linear_bwd(f32): r_true must equal r");
@@ -97,7 +99,7 @@ extern "C" int sdt_lora_linear_bwd_group_supported(int n_problems, int need_dx, 
 }
 
 extern "C" int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems, int n_problems, float scaling, void* dx, int64_t M,
-                                         int64_t K, int64_t N, int r, int r_true, int dtype, void* stream) {
+                                         int64_t K, int64_t N, int r, int r_true, int dtype, void* ws, void* stream) {
   SDT_REQUIRE(problems != nullptr, SDT_ERR_ARG, "sdt_lora_linear_bwd_group: null pointer");
   SDT_REQUIRE(dtype == SDT_BF16, SDT_ERR_UNSUPPORTED, "sdt_lora_linear_bwd_group: bf16 only (there is no fallback)");
   SDT_REQUIRE(M > 0 && K > 0 && N > 0, SDT_ERR_ARG, "sdt_lora_linear_bwd_group: bad sizes");
@@ -122,8 +124,10 @@ extern "C" int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems, i
     const sdt_lora_bwd_problem& b = problems[q];
     sites[q] = WgradSite{b.x, b.g_ws, b.dA, b.dy, b.t_save, b.dB};
   }
-  return lora_wgrad_multi_bf16(sites, n_problems, K, N, M, r, r_true, st);
+  return lora_wgrad_multi_bf16(sites, n_problems, K, N, M, r, r_true, ws, st);
 }
+
+extern "C" size_t sdt_lora_wgrad_workspace_bytes(void) { return lora_wgrad_workspace_bytes(); }
 
 extern "C" int sdt_debug_set(int key, uint64_t value) {
   debug_set(key, value);

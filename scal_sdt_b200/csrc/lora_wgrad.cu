@@ -7,7 +7,10 @@
 // V = G or Ts ([M,R]).  The contraction runs over rows, so both operands are "MN-major" for UMMA: the
 // TMA boxes are taken from U and V exactly as stored (no transposes anywhere) and the MMA reads them
 // through MN-major shared-memory descriptors.  A CTA owns a 128-feature block and one slice of the
-// token range; partial sums leave through f32 red.global.add (the outputs are tiny: F x r_true).
+// token range.  The partial sums of the token slices are combined DETERMINISTICALLY: every CTA writes its [128 x R] partial to
+// a caller-provided workspace, and the CTA that arrives last on its feature block (a counter per block) adds all slices in
+// slice order and accumulates the total into dA / dB -- one launch, run-to-run bit-identical gradients, like the
+// reference's torch path.  Without a workspace the partials leave through f32 red.global.add (order not fixed).
 //
 // HBM-bound by construction: every element of U is read once for R multiply-adds.
 #include "sdt_common.cuh"
@@ -42,9 +45,15 @@ struct WgradGroup {
   int f_begin[kWgradSubs + 1];     // first blockIdx.x of every sub-problem (prefix sums of its 128-feature blocks)
   int n_subs;
 };
+// deterministic mode workspace: [kWgradMaxBlocks counters][partials: one [R x 128] f32 slab per CTA]
+constexpr int kWgradMaxBlocks = 4096, kWgradMaxCtas = 1024;
+constexpr size_t kWgradWorkspaceBytes = (size_t)kWgradMaxBlocks * 4 + (size_t)kWgradMaxCtas * 64 * 128 * 4;
+
 struct WgradParams {
   int M, r_true;
   int rows_per_split;     // multiple of 64
+  unsigned int* counters; // deterministic mode: arrivals per feature block (left at zero); null = atomics
+  float* partial;         // deterministic mode: [gridDim.x][gridDim.y][R][128]
   // descriptors are host-built so that the layout constants live in one place (and can be probed)
   uint64_t a_desc_base, b_desc_base;
   uint32_t a_step, b_step, idesc;
@@ -123,26 +132,79 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
   }
 
   // ---- epilogue: all four warps, thread = feature row ----
-  if (nk > 0) {
-    mbar_wait(done, 0);
-    tc_fence_after();
-    const int f = f0 + warp * 32 + lane;
+  const int tid = warp * 32 + lane;
+  const int f = f0 + tid;
+  if (p.partial == nullptr) {
+    if (nk > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < R / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + c * 16, v);
+        tmem_ld_wait();
+        if (f < F) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int jj = c * 16 + j;
+            if (jj < p.r_true) {
+              float* dst = transposed ? out + (size_t)jj * F + f : out + (size_t)f * p.r_true + jj;
+              atomicAdd(dst, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // stage 1: this CTA's partial [R][128 features] (features contiguous: coalesced both ways)
+    float* mine = p.partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * (R * 128);
+    if (nk > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+    }
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
     for (int c = 0; c < R / 16; ++c) {
       uint32_t v[16];
-      tmem_ld_x16(taddr + c * 16, v);
-      tmem_ld_wait();
+      if (nk > 0) {
+        tmem_ld_x16(taddr + c * 16, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c * 16 + j < p.r_true) mine[(c * 16 + j) * 128 + tid] = __uint_as_float(v[j]);
+    }
+    // stage 2: the last CTA to arrive on this feature block sums the slices in slice order and accumulates into dA / dB
+    __shared__ unsigned int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&p.counters[blockIdx.x], 1u) == gridDim.y - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last != 0u) {
+      __threadfence();
+      const float* base = p.partial + (size_t)blockIdx.x * gridDim.y * (R * 128);
+      float acc[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) acc[j] = 0.f;
+      for (unsigned int sl = 0; sl < gridDim.y; ++sl) {
+        const float* src = base + (size_t)sl * (R * 128) + tid;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (j < p.r_true) acc[j] += __ldcg(src + j * 128);
+      }
       if (f < F) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int jj = c * 16 + j;
-          if (jj < p.r_true) {
-            float* dst = transposed ? out + (size_t)jj * F + f : out + (size_t)f * p.r_true + jj;
-            atomicAdd(dst, __uint_as_float(v[j]));
+        for (int j = 0; j < R; ++j)
+          if (j < p.r_true) {
+            float* dst = transposed ? out + (size_t)j * F + f : out + (size_t)f * p.r_true + j;
+            *dst += acc[j];
           }
-        }
       }
+      if (threadIdx.x == 0) p.counters[blockIdx.x] = 0u;     // ready for the next launch on this workspace
     }
   }
   tc_fence_before();
@@ -164,7 +226,7 @@ struct WgradSite {       // one LoRA site: dA[j,k] += sum_m G[m,j] X[m,k]  and  
 };
 
 template <int R>
-static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r_true, cudaStream_t st) {
+static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r_true, void* ws, cudaStream_t st) {
   using C = WgradCfg<R>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -219,13 +281,25 @@ static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t 
   if (g_dbg[4]) p.a_step = (uint32_t)g_dbg[5];
   if (g_dbg[6]) p.b_step = (uint32_t)g_dbg[7];
   if (g_dbg[8]) p.idesc = (uint32_t)g_dbg[9];
+  p.counters = nullptr;
+  p.partial = nullptr;
+  if (ws != nullptr) {
+    SDT_REQUIRE(f_blocks <= kWgradMaxBlocks && (long)f_blocks * splits <= kWgradMaxCtas, SDT_ERR_UNSUPPORTED,
+                "lora_wgrad: %d feature blocks x %d token slices exceed the deterministic workspace (%d CTAs)", f_blocks, splits,
+                kWgradMaxCtas);
+    p.counters = reinterpret_cast<unsigned int*>(ws);
+    p.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + (size_t)kWgradMaxBlocks * 4);
+  }
   SDT_CUDA_OK(launch_kernel(lora_wgrad_kernel<R>, dim3(f_blocks, splits), dim3(128), C::SMEM_BYTES, st, true, gw, p));
   SDT_LAUNCH_OK("lora_wgrad");
   return SDT_OK;
 }
 
 // dA / dB of n_sites same-shape sites (1..kWgradSites) in ONE launch
-int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, cudaStream_t st) {
+size_t lora_wgrad_workspace_bytes() { return kWgradWorkspaceBytes; }
+
+int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, void* ws,
+                          cudaStream_t st) {
   SDT_REQUIRE(sites != nullptr && n_sites >= 1 && n_sites <= kWgradSites, SDT_ERR_ARG, "lora_wgrad: 1..%d sites per launch (got %d)",
               kWgradSites, n_sites);
   for (int q = 0; q < n_sites; ++q)
@@ -234,10 +308,11 @@ int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_
   SDT_REQUIRE(M > 0 && K > 0 && N > 0 && K % 8 == 0 && N % 8 == 0, SDT_ERR_ARG, "lora_wgrad: bad sizes M=%lld K=%lld N=%lld",
               (long long)M, (long long)K, (long long)N);
   SDT_REQUIRE(r_true >= 1 && r_true <= r, SDT_ERR_ARG, "lora_wgrad: r_true=%d outside [1,%d]", r_true, r);
+  SDT_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15u) == 0, SDT_ERR_ARG, "lora_wgrad: workspace must be 16-byte aligned");
   switch (r) {
-    case 16: return launch_wgrad<16>(sites, n_sites, K, N, M, r_true, st);
-    case 32: return launch_wgrad<32>(sites, n_sites, K, N, M, r_true, st);
-    case 64: return launch_wgrad<64>(sites, n_sites, K, N, M, r_true, st);
+    case 16: return launch_wgrad<16>(sites, n_sites, K, N, M, r_true, ws, st);
+    case 32: return launch_wgrad<32>(sites, n_sites, K, N, M, r_true, ws, st);
+    case 64: return launch_wgrad<64>(sites, n_sites, K, N, M, r_true, ws, st);
   }
   set_error("lora_wgrad: padded rank must be 16, 32 or 64 (got %d)", r);
   return SDT_ERR_UNSUPPORTED;
@@ -245,9 +320,9 @@ int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_
 
 // dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]  in ONE launch
 int lora_wgrad_pair_bf16(const void* x, const void* g, float* dA, int64_t K, const void* dy, const void* ts, float* dB,
-                         int64_t N, int64_t M, int r, int r_true, cudaStream_t st) {
+                         int64_t N, int64_t M, int r, int r_true, void* ws, cudaStream_t st) {
   const WgradSite site{x, g, dA, dy, ts, dB};
-  return lora_wgrad_multi_bf16(&site, 1, K, N, M, r, r_true, st);
+  return lora_wgrad_multi_bf16(&site, 1, K, N, M, r, r_true, ws, st);
 }
 
 }  // namespace sdt

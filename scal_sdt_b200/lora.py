@@ -151,7 +151,7 @@ def _site_backward(mod, code, x2, t_save, lora_A, lora_B, dy, need_dx):
         _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), _lib.ptr(wt), ops.At_p.data_ptr(),
                                            ops.Bt_p.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
                                            g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, ops.R, mod.r,
-                                           code, st), "sdt_lora_linear_bwd")
+                                           code, _lib.wgrad_workspace(), st), "sdt_lora_linear_bwd")
         if ev0 is not None:
             PROFILE.append(("bwd", M, K, N, ops.R, 1, need_dx, ev0, _ev()))
     else:
@@ -159,7 +159,7 @@ def _site_backward(mod, code, x2, t_save, lora_A, lora_B, dy, need_dx):
         _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), mod.weight.data_ptr(), lora_A.data_ptr(),
                                            lora_B.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
                                            g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, mod.r, mod.r,
-                                           code, st), "sdt_lora_linear_bwd")
+                                           code, None, st), "sdt_lora_linear_bwd")
     if direct:
         return dx, None, None
     return dx, dA, dB
@@ -229,7 +229,8 @@ class _LoRAProjectionGroup(torch.autograd.Function):
                 for dy, m, o, t, g, dA, dB in zip(dys, mods, ops, ts, gws, dAs, dBs)])
             ev0 = _ev() if PROFILE is not None else None
             _lib.check(lib.sdt_lora_linear_bwd_group(ctypes.addressof(probs), G, mods[0].scaling, _lib.ptr(dx), M, K, N, R,
-                                                     mods[0].r, _lib.SDT_BF16, st), "sdt_lora_linear_bwd_group")
+                                                     mods[0].r, _lib.SDT_BF16, _lib.wgrad_workspace(), st),
+                       "sdt_lora_linear_bwd_group")
             if ev0 is not None:
                 PROFILE.append(("bwd", M, K, N, R, G, ctx.need_dx, ev0, _ev()))
             return (dx, None, *grads)

@@ -86,7 +86,7 @@ def test_summed_backward_outputs_stay_inside_their_buffers(sdt_lib, M, K, N, R, 
     probs = (_lib.LoraBwdProblem * G)(*[_lib.LoraBwdProblem(dys[q].data_ptr(), x.data_ptr(), wts[q].data_ptr(), Ats[q].data_ptr(),
                                                             Bts[q].data_ptr(), tss[q].data_ptr(), gws[q].view.data_ptr(),
                                                             dAs[q].view.data_ptr(), dBs[q].view.data_ptr()) for q in range(G)])
-    _lib.check(lib.sdt_lora_linear_bwd_group(ctypes.addressof(probs), G, 0.5, dx.view.data_ptr(), M, K, N, R, R, 1, st()))
+    _lib.check(lib.sdt_lora_linear_bwd_group(ctypes.addressof(probs), G, 0.5, dx.view.data_ptr(), M, K, N, R, R, 1, _lib.wgrad_workspace(), st()))
     torch.cuda.synchronize()
     assert dx.intact() and all(t.intact() for t in gws + dAs + dBs)
     ref = sum(dys[q].float() @ wts[q].float().t() + (0.5 * (dys[q].float() @ Bts[q].float().t())).bfloat16().float() @ Ats[q].float().t()

@@ -254,3 +254,29 @@ def test_grouped_projection_backward_without_input_gradient(sdt_lib, G, cout, ra
         assert rel(yos[g], yrs[g]) <= 2e-2
         assert rel(mods[g].lora_A.grad, pairs[g][0].lora_A.grad) <= 2e-2, ("dA", g, rel(mods[g].lora_A.grad, pairs[g][0].lora_A.grad))
         assert rel(mods[g].lora_B.grad, pairs[g][0].lora_B.grad) <= 2e-2, ("dB", g)
+
+
+@pytest.mark.parametrize("M,K,N,rank", [(32768, 320, 320, 16), (2048, 1280, 5120, 64), (1000, 640, 640, 4), (616, 768, 320, 16)])
+def test_lora_gradients_are_bit_reproducible(sdt_lib, M, K, N, rank):
+    """dA / dB are reductions over tens of thousands of token rows split over ~148 CTAs.  The partial sums are combined in a
+    fixed order (per-slice partials + last-arriver reduction inside the one launch), so repeated backward passes give
+    bit-identical gradients -- as the reference's torch path does; and accumulation into an existing gradient still works."""
+    ref, ours = make_pair("linear", K, N, rank, 2 * rank, True, 3, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(M + K + N)
+    x = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    dy = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    runs = []
+    for _ in range(4):
+        ours.lora_A.grad = ours.lora_B.grad = None
+        xo = x.clone().requires_grad_(True)
+        ours(xo).backward(dy)
+        runs.append((ours.lora_A.grad.clone(), ours.lora_B.grad.clone(), xo.grad.clone()))
+    for dA, dB, dx in runs[1:]:
+        assert torch.equal(dA, runs[0][0]) and torch.equal(dB, runs[0][1]) and torch.equal(dx, runs[0][2])
+    # second backward without clearing: the kernels accumulate (+=) into the existing gradient
+    xo = x.clone().requires_grad_(True)
+    ours(xo).backward(dy)
+    assert rel(ours.lora_A.grad, 2 * runs[0][0]) <= 1e-6 and rel(ours.lora_B.grad, 2 * runs[0][1]) <= 1e-6
+    # and the values are still the oracle's
+    dA_ref, dB_ref = lora_ref.ref_lora_weight_grads_chunked(x, ref.lora_A, ref.lora_B, ref.scaling, dy)
+    assert rel(runs[0][0], dA_ref) <= 2e-2 and rel(runs[0][1], dB_ref) <= 2e-2

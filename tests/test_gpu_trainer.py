@@ -94,8 +94,9 @@ def test_cuda_graph_step_matches_eager(sdt_lib):
     tr.optimizer.zero_grad()
     loss_e = tr.training_step(batch, 0, tr._g_noise, tr._g_t)
     loss_e.backward()
-    assert abs(loss_g.item() - loss_e.item()) <= 1e-3 * abs(loss_e.item())
-    assert (grads_g - tr.arena.grads).norm() <= 2e-2 * tr.arena.grads.norm()       # atomics: summation order differs
+    assert loss_g.item() == loss_e.item()
+    # the dA / dB reductions are combined in a fixed order (two-stage, csrc/lora_wgrad.cu): replay == eager, bit for bit
+    assert torch.equal(grads_g, tr.arena.grads)
     tr2 = make(2e-3)
     tr2.enable_cuda_graph(batch)
     first = tr2.graphed_step(batch).item()
@@ -151,7 +152,7 @@ def test_enabling_the_graph_does_not_train(sdt_lib):
     assert tr.unet_ema.num_updates == eager.unet_ema.num_updates == 3
     # Adam's first steps move every element by ~lr * sign(g): compare the trajectories by the moments, not by sign flips
     assert (tr.optimizer.exp_avg - eager.optimizer.exp_avg).norm() <= 2e-2 * eager.optimizer.exp_avg.norm()
-    assert (tr.unet_ema._shadow_flat - eager.unet_ema._shadow_flat).norm() <= 1e-3 * eager.unet_ema._shadow_flat.norm()
+    assert (tr.unet_ema._shadow_flat - eager.unet_ema._shadow_flat).norm() <= 1e-2 * eager.unet_ema._shadow_flat.norm()
 
 
 def test_bf16_forward_under_ema_weights_uses_the_ema_weights(sdt_lib):

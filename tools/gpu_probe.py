@@ -117,7 +117,7 @@ def bwd_case(M, K, N, r_true, R, need_dx=True, timing=False):
         dA.zero_(); dB.zero_()
         rc = lib.sdt_lora_linear_bwd(dy.data_ptr(), x.data_ptr(), wt.data_ptr() if need_dx else 0, At.data_ptr(), Bt.data_ptr(),
                                      tsave.data_ptr(), s, _lib.ptr(dx), g.data_ptr(), dA.data_ptr(), dB.data_ptr(),
-                                     M, K, N, R, r_true, _lib.SDT_BF16, st())
+                                     M, K, N, R, r_true, _lib.SDT_BF16, _lib.wgrad_workspace(), st())
         _lib.check(rc, "bwd")
     run()
     torch.cuda.synchronize()

@@ -40,10 +40,11 @@ for (M, K, N, R) in [(32768, 320, 320, 16), (8192, 640, 640, 16), (2048, 1280, 1
     dA = torch.zeros(R, K, device=dev)
     dB = torch.zeros(N, R, device=dev)
     st = torch.cuda.current_stream().cuda_stream
+    WS = 0 if os.environ.get('SDT_WGRAD_ATOMIC') == '1' else _lib.wgrad_workspace()
 
     def run():
         _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x.data_ptr(), None, At.data_ptr(), Bt.data_ptr(), ts.data_ptr(), 0.5, None,
-                                           g.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, R, R, 1, st))
+                                           g.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, R, R, 1, WS, st))
     mb = 2.0 * M * (K + N + 2 * R) / 1e6
     res = []
     for mc, ps in [(8, 2), (16, 2), (32, 2), (8, 1), (16, 1), (4, 2), (8, 3)]:
