@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 /* element types */
-enum { SDT_F32 = 0, SDT_BF16 = 1 };
+enum { SDT_F32 = 0, SDT_BF16 = 1, SDT_F16 = 2 };   /* SDT_F16 (IEEE half): the LoRA projection entry points and sdt_lora_pack */
 /* prediction target, modules/model.py:306-314 */
 enum { SDT_TARGET_EPSILON = 0, SDT_TARGET_SAMPLE = 1, SDT_TARGET_V = 2 };
 /* error codes */
@@ -50,6 +50,8 @@ long long   sdt_launch_count(void);
  * SDT_BF16: x[M,K], w[N,K], A[r,K], B[N,r], y[M,N], t_save[M,r] bf16, bias[N] f32 or NULL;
  *           r in {16,32,64} (host layer zero-pads smaller ranks); K%8==0, N%8==0.
  *           One tcgen05/TMEM/TMA kernel launch.
+ * SDT_F16 : as SDT_BF16 with every 16-bit tensor in IEEE half (the same kernels; the format is an instruction-descriptor
+ *           field plus the conversions in the epilogues).
  * SDT_F32 : all f32, any r >= 1; FFMA kernels (parity path for the reference's fp32 CPU config).
  * A == NULL (r == 0) gives the plain frozen projection Y = X W^T + bias.
  */
@@ -63,7 +65,7 @@ int sdt_lora_linear_fwd(const void* x, const void* w, const float* bias, const v
  * (two) launches of 6.7 GFLOP each.  This entry runs up to SDT_MAX_GROUP such projections -- identical (M, K, N, r,
  * scaling), own W / A / B / bias / y / t_save, x may be shared -- as the work items of ONE persistent kernel, so launch,
  * prologue and pipeline-drain costs are paid once and the wave quantisation is that of the combined tile count.
- * `problems` is a HOST array; bf16 only; every problem has a bias or none has.
+ * `problems` is a HOST array; SDT_BF16 or SDT_F16; every problem has a bias or none has.
  */
 #define SDT_MAX_GROUP 4
 typedef struct {
@@ -117,14 +119,16 @@ int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems /* host */, i
  * For every site i: from the f32 master lora_A[r_true,K], lora_B[N,r_true] write the four bf16
  * operand layouts the tensor-core kernels read, zero-padded to rank r:
  *     A_p[r,K]  At_p[K,r]  B_p[N,r]  Bt_p[r,N]
- * `sites` is a DEVICE array of n_sites sdt_pack_site records (built once by the host layer).
+ * `sites` is a DEVICE array of n_sites sdt_pack_site records (built once by the host layer).  With dtype SDT_F16 the
+ * outputs are IEEE half instead of bf16 (the reference's stock `trainer.precision: 16`, configs/lora.yaml:50).
  */
 typedef struct {
   const float* A;  const float* B;          /* f32 masters */
   void* A_p; void* At_p; void* B_p; void* Bt_p;   /* bf16 outputs */
   int32_t K, N, r_true, r;
 } sdt_pack_site;
-int sdt_lora_pack(const sdt_pack_site* sites, int n_sites, int64_t max_site_elems, void* stream);
+int sdt_lora_pack(const sdt_pack_site* sites, int n_sites, int64_t max_site_elems, int dtype /* SDT_BF16 | SDT_F16 */,
+                  void* stream);
 
 /* ---- K3: DDPM noising + prediction target --------------------------------------------------
  * Replaces scheduler.add_noise / get_velocity (modules/model.py:302,312):

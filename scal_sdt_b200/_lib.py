@@ -11,7 +11,7 @@ from pathlib import Path
 
 from .build import LIB_PATH
 
-SDT_F32, SDT_BF16 = 0, 1
+SDT_F32, SDT_BF16, SDT_F16 = 0, 1, 2
 TARGET_EPSILON, TARGET_SAMPLE, TARGET_V = 0, 1, 2
 
 
@@ -57,7 +57,7 @@ SIGNATURES = {
     "sdt_lora_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
-    "sdt_lora_pack": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
+    "sdt_lora_pack": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p]),
     "sdt_noise_target": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64,
                                  c_int64, c_int, c_void_p, c_void_p]),
     "sdt_mse_loss_workspace_bytes": (c_size_t, []),
@@ -122,8 +122,9 @@ def dtype_code(dtype) -> int:
         return SDT_F32
     if dtype == torch.bfloat16:
         return SDT_BF16
-    raise SdtError(f"unsupported dtype {dtype}: libsdt_b200 computes in float32 or bfloat16 (fp16 is not implemented, "
-                   "and there is no fallback path)")
+    if dtype == torch.float16:
+        return SDT_F16
+    raise SdtError(f"unsupported dtype {dtype}: libsdt_b200 computes in float32, bfloat16 or float16 (there is no fallback path)")
 
 
 def stream_ptr() -> int:

@@ -91,13 +91,22 @@ class LoraArena(ParamArena):
     their tensor-core operands from one bf16 arena that ``pack()`` refreshes with a single launch.
     """
 
-    def __init__(self, module: nn.Module, param_groups: list[dict]):
+    def __init__(self, module: nn.Module, param_groups: list[dict], compute_dtype: Optional[torch.dtype] = None):
         super().__init__(param_groups)
         self.sites: list[tuple[str, _LoRABase]] = [(n, m) for n, m in lora_modules(module) if m.lora_A.requires_grad]
         in_arena = {id(p) for p, _, _ in self.slots}
         self.sites = [(n, m) for n, m in self.sites if id(m.lora_A) in in_arena and id(m.lora_B) in in_arena]
+        if compute_dtype is None:
+            # the 16-bit format of the frozen base decides (unet.to(float16) -> fp16, the reference's `precision: 16`); fp32
+            # bases are driven through autocast and switch the arena on their first launch (set_compute_dtype)
+            wd = self.sites[0][1].weight.dtype if self.sites else torch.bfloat16
+            compute_dtype = wd if wd in (torch.bfloat16, torch.float16) else torch.bfloat16
+        self._build_operands(compute_dtype)
+
+    def _build_operands(self, dtype: torch.dtype) -> None:
+        self.compute_dtype = dtype
         total = sum(PackedOperands.numel(m.in_features, m.out_features, m.r) for _, m in self.sites)
-        self.packed = torch.zeros(max(total, 8), dtype=torch.bfloat16, device=self.device)
+        self.packed = torch.zeros(max(total, 8), dtype=dtype, device=self.device)
         off = 0
         recs = []
         self._max_elems = 1
@@ -115,12 +124,19 @@ class LoraArena(ParamArena):
         if recs:
             self.pack()
 
+    def set_compute_dtype(self, dtype: torch.dtype) -> None:
+        """Switch the packed operands between bf16 and fp16 (re-packs every site; not meant for the inner loop)."""
+        if dtype not in (torch.bfloat16, torch.float16):
+            raise _lib.SdtError(f"tensor-core operands are bfloat16 or float16, not {dtype}")
+        if dtype != self.compute_dtype:
+            self._build_operands(dtype)
+
     def pack(self) -> None:
         """fp32 masters -> bf16 A_p / At_p / B_p / Bt_p of every site, one launch (call after optimizer.step)."""
         if not self._recs:
             return
         if self._sites_dev is None:
-            self._sites_dev = _pack_sites(self._recs, self._max_elems, self.device)
+            self._sites_dev = _pack_sites(self._recs, self._max_elems, self.device, self.compute_dtype)
         else:
             _lib.check(_lib.load().sdt_lora_pack(self._sites_dev.data_ptr(), len(self._recs), self._max_elems,
-                                                 _lib.stream_ptr()), "sdt_lora_pack")
+                                                 _lib.dtype_code(self.compute_dtype), _lib.stream_ptr()), "sdt_lora_pack")

@@ -182,6 +182,21 @@ template <> struct Load8<__nv_bfloat16> {
   }
 };
 
+template <> struct Load8<__half> {      // fp16 predictions (the reference's stock `trainer.precision: 16`)
+  static __device__ __forceinline__ void ld(const void* base, int64_t i, float* out) {
+    uint4 a = ld_stream(reinterpret_cast<const uint4*>(base) + i);
+    const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); out[2 * j] = f.x; out[2 * j + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void st(void* base, int64_t i, const float* v) {
+    st_stream(reinterpret_cast<uint4*>(base) + i,
+              make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7])));
+  }
+  static __device__ __forceinline__ float ld1(const void* base, int64_t i) { return __half2float(reinterpret_cast<const __half*>(base)[i]); }
+  static __device__ __forceinline__ void st1(void* base, int64_t i, float v) { reinterpret_cast<__half*>(base)[i] = __float2half_rn(v); }
+};
+
 // VEC = 8 (128-bit path) or 1 (odd shapes).  One block-level partial per segment, the last block to
 // finish adds the partials in index order: the result does not depend on scheduling.
 template <typename PT, typename TT, int VEC>
@@ -402,8 +417,11 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
 // =============================================================================================
 // LoRA operand packing
 // =============================================================================================
+__device__ __forceinline__ uint16_t f32_to_act_bits(float f, bool f16) {
+  return f16 ? __half_as_ushort(__float2half_rn(f)) : (uint16_t)f32_to_bf16_bits(f);
+}
 __global__ void __launch_bounds__(kThreads)
-lora_pack_kernel(const sdt_pack_site* __restrict__ sites) {
+lora_pack_kernel(const sdt_pack_site* __restrict__ sites, int f16) {
   const sdt_pack_site s = sites[blockIdx.y];
   const int K = s.K, N = s.N, r = s.r, rt = s.r_true;
   const int64_t nA = (int64_t)r * K, nB = (int64_t)N * r;
@@ -414,13 +432,13 @@ lora_pack_kernel(const sdt_pack_site* __restrict__ sites) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nA + nB; e += (int64_t)gridDim.x * blockDim.x) {
     if (e < nA) {                         // (j,k) in A_p order
       const int j = (int)(e / K), k = (int)(e - (int64_t)j * K);
-      const uint16_t b = j < rt ? (uint16_t)f32_to_bf16_bits(__ldg(s.A + (int64_t)j * K + k)) : (uint16_t)0;
+      const uint16_t b = j < rt ? f32_to_act_bits(__ldg(s.A + (int64_t)j * K + k), f16 != 0) : (uint16_t)0;
       A_p[e] = b;
       At_p[(int64_t)k * r + j] = b;
     } else {                              // (n,j) in B_p order
       const int64_t f = e - nA;
       const int n = (int)(f / r), j = (int)(f - (int64_t)n * r);
-      const uint16_t b = j < rt ? (uint16_t)f32_to_bf16_bits(__ldg(s.B + (int64_t)n * rt + j)) : (uint16_t)0;
+      const uint16_t b = j < rt ? f32_to_act_bits(__ldg(s.B + (int64_t)n * rt + j), f16 != 0) : (uint16_t)0;
       B_p[f] = b;
       Bt_p[(int64_t)j * N + n] = b;
     }
@@ -604,6 +622,8 @@ extern "C" int sdt_mse_loss(const void* pred, int pred_dtype, const void* target
   if (pred_dtype == SDT_BF16 && target_dtype == SDT_F32) SDT_MSE(__nv_bfloat16, float);
   if (pred_dtype == SDT_BF16 && target_dtype == SDT_BF16) SDT_MSE(__nv_bfloat16, __nv_bfloat16);
   if (pred_dtype == SDT_F32 && target_dtype == SDT_BF16) SDT_MSE(float, __nv_bfloat16);
+  if (pred_dtype == SDT_F16 && target_dtype == SDT_F32) SDT_MSE(__half, float);
+  if (pred_dtype == SDT_F16 && target_dtype == SDT_F16) SDT_MSE(__half, __half);
 #undef SDT_MSE
   set_error("sdt_mse_loss: unsupported dtypes pred=%d target=%d", pred_dtype, target_dtype);
   return SDT_ERR_UNSUPPORTED;
@@ -653,14 +673,15 @@ extern "C" int sdt_adamw_flat(float* p, const float* g, float* m, float* v, int6
   return SDT_OK;
 }
 
-extern "C" int sdt_lora_pack(const sdt_pack_site* sites, int n_sites, int64_t max_site_elems, void* stream) {
+extern "C" int sdt_lora_pack(const sdt_pack_site* sites, int n_sites, int64_t max_site_elems, int dtype, void* stream) {
   SDT_REQUIRE(sites, SDT_ERR_ARG, "sdt_lora_pack: null pointer");
+  SDT_REQUIRE(dtype == SDT_BF16 || dtype == SDT_F16, SDT_ERR_UNSUPPORTED, "sdt_lora_pack: operands are bf16 or fp16 (got dtype %d)", dtype);
   if (n_sites <= 0) return SDT_OK;
   SDT_REQUIRE(n_sites <= 65535, SDT_ERR_ARG, "sdt_lora_pack: too many sites");
   int gx = (int)((max_site_elems + kThreads * 4 - 1) / (kThreads * 4));
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
-  lora_pack_kernel<<<dim3(gx, n_sites), kThreads, 0, (cudaStream_t)stream>>>(sites);
+  lora_pack_kernel<<<dim3(gx, n_sites), kThreads, 0, (cudaStream_t)stream>>>(sites, dtype == SDT_F16 ? 1 : 0);
   SDT_LAUNCH_OK("lora_pack");
   return SDT_OK;
 }
@@ -701,6 +722,8 @@ namespace sdt {
 __global__ void __launch_bounds__(kThreads)
 residual_bias_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const float4* __restrict__ bias,
                          uint4* __restrict__ out, int64_t n_vec, int C8) {
+  pdl_wait();                 // PDL (sdt_common.cuh)
+  pdl_launch_dependents();
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   constexpr int U = 4;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_vec; i += U * stride) {
@@ -737,8 +760,8 @@ extern "C" int sdt_residual_bias_add(const void* a, const void* b, const float* 
               "sdt_residual_bias_add: pointers must be 16-byte aligned");
   const int64_t n_vec = rows * (C / 8);
   const int grid = grid_for(n_vec, kThreads, 8);
-  sdt::residual_bias_add_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (const float4*)bias,
-                                                                         (uint4*)out, n_vec, C / 8);
+  SDT_CUDA_OK(sdt::launch_kernel(sdt::residual_bias_add_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, true,
+                                 (const uint4*)a, (const uint4*)b, (const float4*)bias, (uint4*)out, n_vec, C / 8));
   SDT_LAUNCH_OK("residual_bias_add");
   return SDT_OK;
 }

@@ -118,6 +118,8 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* 
   __shared__ float acc[2 * 128];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) acc[i] = 0.f;
+  pdl_wait();                 // PDL (sdt_common.cuh): x / dout come from the kernel in front of us
+  pdl_launch_dependents();
   if (BWD) build_table<true, false, SILU>(tab, gamma, beta, fstats, nullptr, cbias, b, s, eps);
   __syncthreads();
   const int v = threadIdx.x % s.vecs, rp = threadIdx.x / s.vecs;
@@ -207,6 +209,8 @@ __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* 
                                 uint16_t* __restrict__ out, const uint16_t* __restrict__ cbias, GnShape s, float eps) {
   extern __shared__ float tab[];                 // forward [2][C] (A, Bc); backward [4][C] (A, Bc, D, E); A, Bc halved for SiLU
   const int b = blockIdx.y;
+  pdl_wait();                 // PDL: the statistics (and x) come from the kernels in front of us
+  pdl_launch_dependents();
   build_table<false, BWD, SILU>(tab, gamma, beta, fstats, bstats, cbias, b, s, eps);
   __syncthreads();
   const int r_begin = blockIdx.x * s.rows_per_cta;
@@ -313,7 +317,7 @@ using namespace sdt;
     GnShape sk = s;                                                          \
     dim3 grid;                                                               \
     if ((rc = gn_grid(KERNEL, &sk, B, SMEM, &grid)) != SDT_OK) return rc;    \
-    KERNEL<<<grid, sk.threads, SMEM, st>>>(__VA_ARGS__, cb, sk, eps);        \
+    SDT_CUDA_OK(launch_kernel(KERNEL, grid, dim3(sk.threads), SMEM, st, true, __VA_ARGS__, cb, sk, eps)); \
     SDT_LAUNCH_OK(WHAT);                                                     \
   } while (0)
 

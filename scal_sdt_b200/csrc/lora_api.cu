@@ -1,14 +1,15 @@
 // C ABI of the LoRA projection (K1 forward, K2 backward): argument checks + dtype dispatch.
-//   SDT_BF16 -> tcgen05 / TMEM / TMA kernels (lora_gemm.cu, lora_wgrad.cu)
+//   SDT_BF16 / SDT_F16 -> tcgen05 / TMEM / TMA kernels (lora_gemm.cu, lora_gemm2.cu, lora_wgrad.cu); the 16-bit format is an
+//                         instruction-descriptor field and a conversion in the epilogues, the kernels are the same
 //   SDT_F32  -> FFMA kernels (simt_gemm.cu): parity path of the reference's fp32 configuration
 #include "sdt_common.cuh"
 #include "lora_gemm.cuh"
 
 namespace sdt {
 int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
-                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, cudaStream_t st);
+                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, bool f16, cudaStream_t st);
 int lora_wgrad_pair_bf16(const void* x, const void* g, float* dA, int64_t K, const void* dy, const void* ts, float* dB,
-                         int64_t N, int64_t M, int r, int r_true, void* ws, cudaStream_t st);
+                         int64_t N, int64_t M, int r, int r_true, void* ws, bool f16, cudaStream_t st);
 size_t lora_wgrad_workspace_bytes();
 int lora_fwd_f32(const float* x, const float* w, const float* bias, const float* A, const float* B, float scaling,
                  float* y, float* t_save, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st);
@@ -17,7 +18,7 @@ int lora_bwd_f32(const float* dy, const float* x, const float* w, const float* A
                  cudaStream_t st);
 struct WgradSite { const void* x; const void* g; float* dA; const void* dy; const void* ts; float* dB; };
 int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, void* ws,
-                          cudaStream_t st);
+                          bool f16, cudaStream_t st);
 void debug_set(int key, uint64_t value);
 }  // namespace sdt
 
@@ -34,9 +35,9 @@ extern "C" int sdt_lora_linear_fwd(const void* x, const void* w, const float* bi
   SDT_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(A) && aligned16(B) && aligned16(t_save),
               SDT_ERR_ARG, "sdt_lora_linear_fwd: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == SDT_BF16) {
+  if (dtype == SDT_BF16 || dtype == SDT_F16) {
     SDT_REQUIRE(r == 0 || t_save != nullptr, SDT_ERR_ARG, "sdt_lora_linear_fwd: t_save is required when r > 0");
-    return lora_gemm_bf16(x, w, bias, A, B, scaling, y, t_save, M, K, N, r, true, st);
+    return lora_gemm_bf16(x, w, bias, A, B, scaling, y, t_save, M, K, N, r, true, dtype == SDT_F16, st);
   }
   if (dtype == SDT_F32)
     return lora_fwd_f32((const float*)x, (const float*)w, bias, (const float*)A, (const float*)B, scaling, (float*)y,
@@ -51,14 +52,14 @@ extern "C" int sdt_lora_linear_fwd_group(const sdt_lora_problem* problems, int n
                                          int64_t N, int r, int dtype, void* stream) {
   SDT_REQUIRE(problems != nullptr && n_problems >= 1 && n_problems <= SDT_MAX_GROUP, SDT_ERR_ARG,
               "sdt_lora_linear_fwd_group: 1..%d problems per launch (got %d)", SDT_MAX_GROUP, n_problems);
-  SDT_REQUIRE(dtype == SDT_BF16, SDT_ERR_UNSUPPORTED,
-              "sdt_lora_linear_fwd_group: bf16 only (fp32 sites go through sdt_lora_linear_fwd one by one; there is no fallback)");
+  SDT_REQUIRE(dtype == SDT_BF16 || dtype == SDT_F16, SDT_ERR_UNSUPPORTED,
+              "sdt_lora_linear_fwd_group: bf16 / fp16 only (fp32 sites go through sdt_lora_linear_fwd one by one; there is no fallback)");
   SDT_REQUIRE(r == 16 || r == 32 || r == 64, SDT_ERR_UNSUPPORTED, "sdt_lora_linear_fwd_group: padded rank must be 16, 32 or 64 (got %d)", r);
   for (int q = 0; q < n_problems; ++q)
     SDT_REQUIRE(problems[q].x && problems[q].w && problems[q].A && problems[q].B && problems[q].y && problems[q].t_save, SDT_ERR_ARG,
                 "sdt_lora_linear_fwd_group: null pointer in problem %d", q);
   return lora_gemm_group_bf16(reinterpret_cast<const LoraProblem*>(problems), n_problems, scaling, M, K, N, r, true,
-                              (cudaStream_t)stream);
+                              dtype == SDT_F16, (cudaStream_t)stream);
 }
 
 extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt, const void* At, const void* Bt,
@@ -70,17 +71,18 @@ extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt
   SDT_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(wt) && aligned16(At) && aligned16(Bt) && aligned16(t_save) &&
                   aligned16(dx) && aligned16(g_ws), SDT_ERR_ARG, "sdt_lora_linear_bwd: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == SDT_BF16) {
+  if (dtype == SDT_BF16 || dtype == SDT_F16) {
+    const bool f16 = dtype == SDT_F16;
     if (r > 0)
       SDT_REQUIRE(x && At && Bt && t_save && g_ws && dA && dB, SDT_ERR_ARG,
                   "sdt_lora_linear_bwd: x, At, Bt, t_save, g_ws, dA, dB are required when r > 0");
     SDT_REQUIRE(dx == nullptr || wt != nullptr, SDT_ERR_ARG, "sdt_lora_linear_bwd: wt is required for dX");
     // G = s dY B ; dX = dY W + G A   -- the forward kernel with (dY, W^T, B^T, A^T)
     int rc = lora_gemm_bf16(dy, wt, nullptr, Bt, At, scaling, dx, g_ws, M, /*contraction*/ N, /*outputs*/ K, r,
-                            dx != nullptr, st);
+                            dx != nullptr, f16, st);
     if (rc != SDT_OK || r == 0) return rc;
     // dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]: one launch for both reductions
-    return lora_wgrad_pair_bf16(x, g_ws, dA, K, dy, t_save, dB, N, M, r, r_true, ws, st);
+    return lora_wgrad_pair_bf16(x, g_ws, dA, K, dy, t_save, dB, N, M, r, r_true, ws, f16, st);
   }
   if (dtype == SDT_F32) {
     SDT_REQUIRE(r_true == r, SDT_ERR_ARG, "sdt_lora_linear_bwd(f32): r_true must equal r");
@@ -101,7 +103,8 @@ extern "C" int sdt_lora_linear_bwd_group_supported(int n_problems, int need_dx, 
 extern "C" int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems, int n_problems, float scaling, void* dx, int64_t M,
                                          int64_t K, int64_t N, int r, int r_true, int dtype, void* ws, void* stream) {
   SDT_REQUIRE(problems != nullptr, SDT_ERR_ARG, "sdt_lora_linear_bwd_group: null pointer");
-  SDT_REQUIRE(dtype == SDT_BF16, SDT_ERR_UNSUPPORTED, "sdt_lora_linear_bwd_group: bf16 only (there is no fallback)");
+  SDT_REQUIRE(dtype == SDT_BF16 || dtype == SDT_F16, SDT_ERR_UNSUPPORTED, "sdt_lora_linear_bwd_group: bf16 / fp16 only (there is no fallback)");
+  const bool f16 = dtype == SDT_F16;
   SDT_REQUIRE(M > 0 && K > 0 && N > 0, SDT_ERR_ARG, "sdt_lora_linear_bwd_group: bad sizes");
   SDT_REQUIRE(sdt_lora_linear_bwd_group_supported(n_problems, dx != nullptr, M, K, N, r), SDT_ERR_UNSUPPORTED,
               "sdt_lora_linear_bwd_group: unsupported group (%d projections, r=%d, M=%lld, dx %s): use sdt_lora_linear_bwd per site",
@@ -115,8 +118,8 @@ extern "C" int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems, i
     // G_q = s dY_q B_q ; dX += dY_q W_q + G_q A_q   -- the forward kernel's roles with (dY, W^T, B^T, A^T)
     pr[q] = LoraProblem{b.dy, dx ? b.wt : nullptr, nullptr, b.Bt, dx ? b.At : nullptr, dx, b.g_ws};
   }
-  int rc = dx != nullptr ? lora_gemm_pair_sum_bf16(pr, n_problems, scaling, M, /*contraction*/ N, /*outputs*/ K, r, st)
-                         : lora_gemm_group_bf16(pr, n_problems, scaling, M, N, K, r, /*main=*/false, st);
+  int rc = dx != nullptr ? lora_gemm_pair_sum_bf16(pr, n_problems, scaling, M, /*contraction*/ N, /*outputs*/ K, r, f16, st)
+                         : lora_gemm_group_bf16(pr, n_problems, scaling, M, N, K, r, /*main=*/false, f16, st);
   if (rc != SDT_OK) return rc;
   // the dA / dB reductions of the whole group: one launch
   WgradSite sites[SDT_MAX_GROUP];
@@ -124,7 +127,7 @@ extern "C" int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems, i
     const sdt_lora_bwd_problem& b = problems[q];
     sites[q] = WgradSite{b.x, b.g_ws, b.dA, b.dy, b.t_save, b.dB};
   }
-  return lora_wgrad_multi_bf16(sites, n_problems, K, N, M, r, r_true, ws, st);
+  return lora_wgrad_multi_bf16(sites, n_problems, K, N, M, r, r_true, ws, f16, st);
 }
 
 extern "C" size_t sdt_lora_wgrad_workspace_bytes(void) { return lora_wgrad_workspace_bytes(); }

@@ -84,6 +84,7 @@ struct LoraGemmParams {
   int has_bias;           // every problem has a bias (all or none)
   int n_tiles, n_groups, group_size, n_items;
   int main;               // 0: only the rank-R projection is computed (t_out), no base GEMM
+  int f16;                // operands / outputs are IEEE fp16 instead of bf16
   int ws;                 // weight-stationary: every CTA keeps the W k-blocks of ITS n-tile resident (K <= 320), see launch
   int ws_stages;
   long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
@@ -163,7 +164,7 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
     // constant part of the tail's A operand: k-step R/16 is [1, 1, 0, ..., 0] per row (pairs with bias hi/lo)
     const int row = (warp - 2) * 32 + lane;
     uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
-    *reinterpret_cast<uint4*>(trow + (R / 8) * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // bf16 1.0, 1.0
+    *reinterpret_cast<uint4*>(trow + (R / 8) * 128) = make_uint4(p.f16 ? 0x3C003C00u : 0x3F803F80u, 0u, 0u, 0u);   // 1.0, 1.0
     *reinterpret_cast<uint4*>(trow + (R / 8 + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
     // zero the second K chunk of the bias operand once (the first chunk is rewritten per tile)
     for (int n = row; n < BN; n += 128)
@@ -230,9 +231,10 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     constexpr int RR = R > 0 ? R : 16;
-    constexpr uint32_t idesc_main = make_idesc_bf16(128, BN, 0, 0);
-    constexpr uint32_t idesc_both = make_idesc_bf16(128, BN + R, 0, 0);      // [W ; lora-down] as one B operand
-    constexpr uint32_t idesc_t = make_idesc_bf16(128, RR, 0, 0);
+    const bool f16 = p.f16 != 0;
+    const uint32_t idesc_main = idesc_operand_format(make_idesc_bf16(128, BN, 0, 0), f16);
+    const uint32_t idesc_both = idesc_operand_format(make_idesc_bf16(128, BN + R, 0, 0), f16);      // [W ; lora-down] as one B operand
+    const uint32_t idesc_t = idesc_operand_format(make_idesc_bf16(128, RR, 0, 0), f16);
     constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
     // lora-up tile [BN,R], K-major, rows of R*2 bytes written by TMA with the matching swizzle
     constexpr uint32_t lb_layout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
@@ -370,9 +372,9 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
             const int n0 = nt * C::BN;
             for (int n = tid; n < BN; n += 128) {
               const float b = (n0 + n < p.N) ? __ldg(bias + n0 + n) : 0.f;
-              const float hi = round_bf16(b);
+              const float hi = round_act(b, p.f16 != 0);
               *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) =
-                  make_uint4(pack_bf16x2(hi, b - hi), 0u, 0u, 0u);
+                  make_uint4(pack_act2(hi, b - hi, p.f16 != 0), 0u, 0u, 0u);
             }
           }
           if (first) {
@@ -386,7 +388,7 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                packed[c * 8 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling);
+                packed[c * 8 + j] = pack_act2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling, p.f16 != 0);
             }
             if (has_main) {
               uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
@@ -446,8 +448,7 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
               tmem_ld_x32(lane_addr + buf * C::ACC1_COL + (2 * cb + h) * 32, v);
               tmem_ld_wait();
               uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              pack_acc32(v, pk, p.f16 != 0);
               stage_row_chunk(stg, lane, h, pk);
             }
             __syncwarp();
@@ -569,7 +570,7 @@ static void choose_groups(int m_tiles, int n_tiles, int BN, int R, int sms, int*
 
 template <int BN, int R, int G>
 static int launch_lora_gemm(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, bool main,
-                            cudaStream_t st) {
+                            bool f16, cudaStream_t st) {
   using C = LoraGemmCfg<BN, R>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -611,6 +612,7 @@ static int launch_lora_gemm(const LoraProblem* probs, int n_probs, float scaling
   p.n_probs = n_probs;
   p.has_bias = probs[0].bias != nullptr ? 1 : 0;
   p.main = main ? 1 : 0;
+  p.f16 = f16 ? 1 : 0;
   p.trace = reinterpret_cast<long long*>(debug_get(10));
   const int m_tiles = (int)((M + C::BM - 1) / C::BM);
   p.n_tiles = main ? (int)((N + BN - 1) / BN) : 1;
@@ -663,7 +665,7 @@ static int check_group(const LoraProblem* probs, int n_probs, int r, bool main) 
 
 // bf16 entry used by sdt_lora_linear_fwd(_group) / sdt_lora_linear_bwd (lora_api.cu): n_probs problems of one shape
 int lora_gemm_group_bf16(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, int r, bool main,
-                         cudaStream_t st) {
+                         bool f16, cudaStream_t st) {
   SDT_REQUIRE(M > 0 && K > 0 && N > 0, SDT_ERR_ARG, "lora_gemm: bad sizes M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
   SDT_REQUIRE(M < (1ll << 31) && K < (1ll << 31) && N < (1ll << 31), SDT_ERR_UNSUPPORTED, "lora_gemm: dimension exceeds int32");
   SDT_REQUIRE(K % 8 == 0 && N % 8 == 0, SDT_ERR_UNSUPPORTED, "lora_gemm: K and N must be multiples of 8 (K=%lld N=%lld)", (long long)K, (long long)N);
@@ -679,9 +681,9 @@ int lora_gemm_group_bf16(const LoraProblem* probs, int n_probs, float scaling, i
   // sdt_debug_set(11, 1) forces the single-CTA kernel (A/B measurements)
   const int64_t pair_min_k = debug_get(14) ? (int64_t)debug_get(14) : 256;
   if (main && M >= 256 && K >= pair_min_k && debug_get(11) == 0)
-    return lora_gemm_pair_group_bf16(probs, n_probs, scaling, M, K, N, r, st);
+    return lora_gemm_pair_group_bf16(probs, n_probs, scaling, M, K, N, r, f16, st);
   const bool bn160 = !main || (N % 160 == 0) || (N % 128 != 0 && N > 128);
-#define SDT_GEMM(BN, R, G) return launch_lora_gemm<BN, R, G>(probs, n_probs, scaling, M, K, N, main, st)
+#define SDT_GEMM(BN, R, G) return launch_lora_gemm<BN, R, G>(probs, n_probs, scaling, M, K, N, main, f16, st)
 #define SDT_GEMM_R(BN, G)                                                                     \
   switch (r) { case 16: SDT_GEMM(BN, 16, G); case 32: SDT_GEMM(BN, 32, G); default: SDT_GEMM(BN, 64, G); }
   if (n_probs == 1) {
@@ -694,9 +696,9 @@ int lora_gemm_group_bf16(const LoraProblem* probs, int n_probs, float scaling, i
 }
 
 int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
-                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, cudaStream_t st) {
+                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, bool f16, cudaStream_t st) {
   const LoraProblem pr{x, w, bias, la, lb, y, t_out};
-  return lora_gemm_group_bf16(&pr, 1, scaling, M, K, N, r, main, st);
+  return lora_gemm_group_bf16(&pr, 1, scaling, M, K, N, r, main, f16, st);
 }
 
 }  // namespace sdt

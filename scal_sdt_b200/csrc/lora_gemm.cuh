@@ -33,13 +33,15 @@ struct GemmGroup {
 };
 
 // entry points (lora_gemm.cu / lora_gemm2.cu)
+// (the names say bf16 for history: `f16` selects IEEE fp16 operands and outputs on the same kernels)
 int lora_gemm_group_bf16(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, int r, bool main,
-                         cudaStream_t st);
+                         bool f16, cudaStream_t st);
 int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, int r,
-                              cudaStream_t st);
+                              bool f16, cudaStream_t st);
 
 // summed sources (input gradient of q / k / v): see lora_gemm2.cu
 bool lora_gemm_pair_sum_supported(int n_src, int64_t M, int64_t K, int64_t N, int r);
-int lora_gemm_pair_sum_bf16(const LoraProblem* probs, int n_src, float scaling, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st);
+int lora_gemm_pair_sum_bf16(const LoraProblem* probs, int n_src, float scaling, int64_t M, int64_t K, int64_t N, int r, bool f16,
+                            cudaStream_t st);
 
 }  // namespace sdt

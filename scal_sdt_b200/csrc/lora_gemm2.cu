@@ -143,6 +143,7 @@ struct PairParams {
   int n_probs;            // problems of identical shape in this launch (<= G)
   int n_src;              // sources summed into each output (<= S; their operands are entries 0..n_src-1 of the group)
   int has_bias;
+  int f16;                // operands / outputs are IEEE fp16 instead of bf16
   int n_tiles, n_groups, group_size, n_items;   // items are (256-row tile, problem, n-group)
   long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
 };
@@ -197,6 +198,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
   const int nk = (p.K + C::BK - 1) / C::BK;
   const bool has_bias = p.has_bias != 0;
   const bool has_tail = R > 0 || has_bias;
+  const bool f16 = p.f16 != 0;
 
   if (threadIdx.x == 0) SDT_TRACE2(0);
   if (warp == 0) {
@@ -224,7 +226,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
   if (warp >= 2 && warp < 6) {
     const int row = (warp - 2) * 32 + lane;
     uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16;
-    *reinterpret_cast<uint4*>(trow + (S * R / 8) * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // bf16 1.0, 1.0
+    *reinterpret_cast<uint4*>(trow + (S * R / 8) * 128) = make_uint4(f16 ? 0x3C003C00u : 0x3F803F80u, 0u, 0u, 0u);   // 1.0, 1.0
     *reinterpret_cast<uint4*>(trow + (S * R / 8 + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
     for (int n = row; n < C::HN + C::HR; n += 128) {
       *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + 128 + (n & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -292,9 +294,9 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
     // ===================================== MMA issuer (leader CTA only) =================================
     if (leader) {
       constexpr int RR = R > 0 ? R : 16;
-      constexpr uint32_t idesc_main = make_idesc_bf16(256, BN, 0, 0);
-      constexpr uint32_t idesc_both = make_idesc_bf16(256, BN + R, 0, 0);    // first tile of an item: [W ; lora-down]
-      constexpr uint32_t idesc_rank = make_idesc_bf16(256, RR, 0, 0);        // S > 1: the rank projection as its own UMMA
+      const uint32_t idesc_main = idesc_operand_format(make_idesc_bf16(256, BN, 0, 0), f16);
+      const uint32_t idesc_both = idesc_operand_format(make_idesc_bf16(256, BN + R, 0, 0), f16);    // first tile of an item: [W ; lora-down]
+      const uint32_t idesc_rank = idesc_operand_format(make_idesc_bf16(256, RR, 0, 0), f16);        // S > 1: the rank projection as its own UMMA
       constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
       constexpr uint32_t lb_layout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
       constexpr uint64_t d_lb = make_smem_desc_base(16, 8 * RR * 2, lb_layout);
@@ -419,8 +421,8 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             const int n0 = nt * C::BN + (int)rank * C::HN;
             for (int n = tid; n < C::HN; n += 128) {
               const float b = (n0 + n < p.N) ? __ldg(bias + n0 + n) : 0.f;
-              const float hi = round_bf16(b);
-              *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) = make_uint4(pack_bf16x2(hi, b - hi), 0u, 0u, 0u);
+              const float hi = round_act(b, f16);
+              *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) = make_uint4(pack_act2(hi, b - hi, f16), 0u, 0u, 0u);
             }
           }
           if (first) {
@@ -439,7 +441,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  packed[c * 4 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling);
+                  packed[c * 4 + j] = pack_act2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling, f16);
               }
               uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16 + src * (RR / 8) * 128;
 #pragma unroll
@@ -515,8 +517,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             for (int h = 0; h < subs; ++h) {
               load_sub(2 * cb + h);
               uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              pack_acc32(v, pk, f16);
               stage_row_chunk(stg + slot * 4096, lane, h, pk);
             }
           }
@@ -537,8 +538,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             for (int h = 0; h < subs; ++h) {
               load_sub(2 * cb + h);
               uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              pack_acc32(v, pk, f16);
               stage_row_chunk(stg, lane, h, pk);
             }
             __syncwarp();
@@ -584,7 +584,7 @@ static void choose_groups_pair(int m_tiles, int n_tiles, int BN, int R, int pair
 
 // n_probs problems as independent work items (S == 1), or n_probs SOURCES summed into probs[0].y (S > 1)
 template <int BN, int R, int G, int S>
-static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, cudaStream_t st) {
+static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, bool f16, cudaStream_t st) {
   using C = PairCfg<BN, R, S>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -617,6 +617,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
   p.n_probs = S > 1 ? 1 : n_probs;
   p.n_src = S > 1 ? n_probs : 1;
   p.has_bias = probs[0].bias != nullptr ? 1 : 0;
+  p.f16 = f16 ? 1 : 0;
   p.trace = reinterpret_cast<long long*>(debug_get(10));
   const int m_tiles = (int)((M + 2 * C::BM - 1) / (2 * C::BM));
   p.n_tiles = (int)((N + BN - 1) / BN);
@@ -641,9 +642,9 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
 
 // CTA-pair entry; same contract as lora_gemm_group_bf16 with main == true (arguments already validated there)
 int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, int r,
-                              cudaStream_t st) {
+                              bool f16, cudaStream_t st) {
   const bool bn160 = (N % 160 == 0) || (N % 128 != 0 && N > 128);
-#define SDT_PAIR(BN, R, G) return launch_pair<BN, R, G, 1>(probs, n_probs, scaling, M, K, N, st)
+#define SDT_PAIR(BN, R, G) return launch_pair<BN, R, G, 1>(probs, n_probs, scaling, M, K, N, f16, st)
 #define SDT_PAIR_R(BN, G)                                                                     \
   switch (r) { case 16: SDT_PAIR(BN, 16, G); case 32: SDT_PAIR(BN, 32, G); default: SDT_PAIR(BN, 64, G); }
   // wide tiles (more FLOP per byte brought into the SM) when the rank accumulators still fit next to two 224-column
@@ -670,7 +671,8 @@ int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scali
 bool lora_gemm_pair_sum_supported(int n_src, int64_t M, int64_t K, int64_t N, int r) {
   return n_src >= 2 && n_src <= 3 && (r == 16 || r == 32) && M >= 256 && K >= 64 && K % 8 == 0 && N % 8 == 0;
 }
-int lora_gemm_pair_sum_bf16(const LoraProblem* probs, int n_src, float scaling, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st) {
+int lora_gemm_pair_sum_bf16(const LoraProblem* probs, int n_src, float scaling, int64_t M, int64_t K, int64_t N, int r, bool f16,
+                            cudaStream_t st) {
   SDT_REQUIRE(lora_gemm_pair_sum_supported(n_src, M, K, N, r), SDT_ERR_UNSUPPORTED,
               "lora_gemm(sum): needs 2..3 sources, padded rank 16/32, M >= 256 (got %d sources, r=%d, M=%lld)", n_src, r, (long long)M);
   for (int q = 0; q < n_src; ++q) {
@@ -679,8 +681,8 @@ int lora_gemm_pair_sum_bf16(const LoraProblem* probs, int n_src, float scaling, 
     SDT_REQUIRE(aligned16(pr.x) && aligned16(pr.w) && aligned16(pr.la) && aligned16(pr.lb) && aligned16(probs[0].y) && aligned16(pr.t_out),
                 SDT_ERR_ARG, "lora_gemm(sum): pointers must be 16-byte aligned (source %d)", q);
   }
-  if (r == 16) return launch_pair<160, 16, kMaxGroup, 3>(probs, n_src, scaling, M, K, N, st);
-  return launch_pair<160, 32, kMaxGroup, 3>(probs, n_src, scaling, M, K, N, st);
+  if (r == 16) return launch_pair<160, 16, kMaxGroup, 3>(probs, n_src, scaling, M, K, N, f16, st);
+  return launch_pair<160, 32, kMaxGroup, 3>(probs, n_src, scaling, M, K, N, f16, st);
 }
 
 }  // namespace sdt

@@ -186,23 +186,56 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
     __syncthreads();
     if (s_last != 0u) {
       __threadfence();
-      const float* base = p.partial + (size_t)blockIdx.x * gridDim.y * (R * 128);
-      float acc[R];
+      // The slab of one slice is [R][128] f32 = R * 32 float4; thread t owns float4 number t + 128 i (rank row j = i * 4 + t / 32,
+      // features 4 (t % 32) .. + 3).  All of a thread's loads of 4 consecutive slices are issued before the first add (4 / 2 / 1 slices at rank 16 / 32 / 64), so the
+      // ~200 KB of partials stream in at L2 bandwidth instead of one dependent load at a time; the slices are still added in
+      // slice order, which is what makes the result reproducible.
+      constexpr int V = R / 4;                       // float4 per thread per slice
+      constexpr int U = R <= 16 ? 4 : (R == 32 ? 2 : 1);   // slices in flight (register budget: U * V float4)
+      const float4* base = reinterpret_cast<const float4*>(p.partial + (size_t)blockIdx.x * gridDim.y * (R * 128)) + tid;
+      float4 acc[V];
 #pragma unroll
-      for (int j = 0; j < R; ++j) acc[j] = 0.f;
-      for (unsigned int sl = 0; sl < gridDim.y; ++sl) {
-        const float* src = base + (size_t)sl * (R * 128) + tid;
+      for (int i = 0; i < V; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const unsigned int n_sl = gridDim.y;
+      unsigned int sl = 0;
+      for (; sl + U <= n_sl; sl += U) {
+        float4 v[U][V];
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (j < p.r_true) acc[j] += __ldcg(src + j * 128);
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < V; ++i)
+            if (i * 4 < p.r_true) v[u][i] = __ldcg(base + (size_t)(sl + u) * (R * 32) + i * 128);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < V; ++i)
+            if (i * 4 < p.r_true) { acc[i].x += v[u][i].x; acc[i].y += v[u][i].y; acc[i].z += v[u][i].z; acc[i].w += v[u][i].w; }
       }
-      if (f < F) {
+      for (; sl < n_sl; ++sl) {
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (j < p.r_true) {
-            float* dst = transposed ? out + (size_t)j * F + f : out + (size_t)f * p.r_true + j;
-            *dst += acc[j];
+        for (int i = 0; i < V; ++i)
+          if (i * 4 < p.r_true) {
+            const float4 v = __ldcg(base + (size_t)sl * (R * 32) + i * 128);
+            acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
           }
+      }
+      const int fq = f0 + 4 * (tid & 31);            // first of this thread's four features
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int j = i * 4 + (tid >> 5);
+        if (j < p.r_true && fq < F) {                // F % 8 == 0 and fq % 4 == 0: the four features are in range together
+          if (transposed) {
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)j * F + fq);
+            float4 o = *dst;
+            o.x += acc[i].x; o.y += acc[i].y; o.z += acc[i].z; o.w += acc[i].w;
+            *dst = o;
+          } else {
+            out[(size_t)(fq + 0) * p.r_true + j] += acc[i].x;
+            out[(size_t)(fq + 1) * p.r_true + j] += acc[i].y;
+            out[(size_t)(fq + 2) * p.r_true + j] += acc[i].z;
+            out[(size_t)(fq + 3) * p.r_true + j] += acc[i].w;
+          }
+        }
       }
       if (threadIdx.x == 0) p.counters[blockIdx.x] = 0u;     // ready for the next launch on this workspace
     }
@@ -226,7 +259,8 @@ struct WgradSite {       // one LoRA site: dA[j,k] += sum_m G[m,j] X[m,k]  and  
 };
 
 template <int R>
-static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r_true, void* ws, cudaStream_t st) {
+static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r_true, void* ws, bool f16,
+                        cudaStream_t st) {
   using C = WgradCfg<R>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -275,7 +309,7 @@ static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t 
   p.b_desc_base = make_smem_desc_base(8 * R * 2, 8 * R * 2, vlayout);
   p.a_step = 16 * 128;
   p.b_step = 16 * R * 2;
-  p.idesc = make_idesc_bf16(128, R, 1, 1);
+  p.idesc = idesc_operand_format(make_idesc_bf16(128, R, 1, 1), f16);
   if (g_dbg[0]) p.a_desc_base = g_dbg[1];
   if (g_dbg[2]) p.b_desc_base = g_dbg[3];
   if (g_dbg[4]) p.a_step = (uint32_t)g_dbg[5];
@@ -299,7 +333,7 @@ static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t 
 size_t lora_wgrad_workspace_bytes() { return kWgradWorkspaceBytes; }
 
 int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, void* ws,
-                          cudaStream_t st) {
+                          bool f16, cudaStream_t st) {
   SDT_REQUIRE(sites != nullptr && n_sites >= 1 && n_sites <= kWgradSites, SDT_ERR_ARG, "lora_wgrad: 1..%d sites per launch (got %d)",
               kWgradSites, n_sites);
   for (int q = 0; q < n_sites; ++q)
@@ -310,9 +344,9 @@ int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_
   SDT_REQUIRE(r_true >= 1 && r_true <= r, SDT_ERR_ARG, "lora_wgrad: r_true=%d outside [1,%d]", r_true, r);
   SDT_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15u) == 0, SDT_ERR_ARG, "lora_wgrad: workspace must be 16-byte aligned");
   switch (r) {
-    case 16: return launch_wgrad<16>(sites, n_sites, K, N, M, r_true, ws, st);
-    case 32: return launch_wgrad<32>(sites, n_sites, K, N, M, r_true, ws, st);
-    case 64: return launch_wgrad<64>(sites, n_sites, K, N, M, r_true, ws, st);
+    case 16: return launch_wgrad<16>(sites, n_sites, K, N, M, r_true, ws, f16, st);
+    case 32: return launch_wgrad<32>(sites, n_sites, K, N, M, r_true, ws, f16, st);
+    case 64: return launch_wgrad<64>(sites, n_sites, K, N, M, r_true, ws, f16, st);
   }
   set_error("lora_wgrad: padded rank must be 16, 32 or 64 (got %d)", r);
   return SDT_ERR_UNSUPPORTED;
@@ -320,9 +354,9 @@ int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_
 
 // dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]  in ONE launch
 int lora_wgrad_pair_bf16(const void* x, const void* g, float* dA, int64_t K, const void* dy, const void* ts, float* dB,
-                         int64_t N, int64_t M, int r, int r_true, void* ws, cudaStream_t st) {
+                         int64_t N, int64_t M, int r, int r_true, void* ws, bool f16, cudaStream_t st) {
   const WgradSite site{x, g, dA, dy, ts, dB};
-  return lora_wgrad_multi_bf16(&site, 1, K, N, M, r, r_true, ws, st);
+  return lora_wgrad_multi_bf16(&site, 1, K, N, M, r, r_true, ws, f16, st);
 }
 
 }  // namespace sdt

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -113,5 +114,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 // round an f32 to the nearest bf16 value, result as f32 (what torch does after every bf16 op)
 __device__ __forceinline__ float round_bf16(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+
+// ---- 16-bit activation format of the tensor-core path: bf16 (default) or IEEE fp16 (the reference's stock
+// `trainer.precision: 16`).  A launch-uniform flag selects it; the tensor core takes the format from the instruction descriptor.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+__device__ __forceinline__ float round_act(float f, bool f16) { return f16 ? __half2float(__float2half_rn(f)) : round_bf16(f); }
+// 32 f32 accumulator values (as raw bits) -> 16 packed pairs; the branch is outside the unrolled loops
+__device__ __forceinline__ void pack_acc32(const uint32_t (&v)[32], uint32_t (&pk)[16], bool f16) {
+  if (f16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+  }
+}
 
 }  // namespace sdt

@@ -109,6 +109,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same descriptor with IEEE fp16 operands (A fmt = B fmt = 0): clear the two format fields
+constexpr uint32_t kIdescFmtBf16 = (1u << 7) | (1u << 10);
+__host__ __device__ constexpr uint32_t idesc_operand_format(uint32_t idesc_bf16, bool f16) {
+  return f16 ? (idesc_bf16 & ~kIdescFmtBf16) : idesc_bf16;
+}
 
 // shared-memory matrix descriptor
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4

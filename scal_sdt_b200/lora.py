@@ -44,24 +44,26 @@ def padded_rank(rank: int) -> int:
     raise SdtError(f"LoRA rank {rank} > {MAX_TC_RANK} is not supported by the bf16 tensor-core path")
 
 
-def _pack_sites(sites: list[PackSite], max_elems: int, device) -> torch.Tensor:
+def _pack_sites(sites: list[PackSite], max_elems: int, device, dtype=torch.bfloat16) -> torch.Tensor:
     arr = (PackSite * len(sites))(*sites)
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
     dev = host.to(device, non_blocking=False)
-    _lib.check(_lib.load().sdt_lora_pack(dev.data_ptr(), len(sites), max_elems, _lib.stream_ptr()), "sdt_lora_pack")
+    _lib.check(_lib.load().sdt_lora_pack(dev.data_ptr(), len(sites), max_elems, _lib.dtype_code(dtype), _lib.stream_ptr()),
+               "sdt_lora_pack")
     # `dev` must outlive the launch: the caching allocator keeps stream order for us
     return dev
 
 
 class PackedOperands:
-    """bf16 tensor-core operand layouts of one site: A_p [R,K], At_p [K,R], B_p [N,R], Bt_p [R,N]."""
+    """16-bit (bf16 or fp16) tensor-core operand layouts of one site: A_p [R,K], At_p [K,R], B_p [N,R], Bt_p [R,N]."""
 
-    def __init__(self, K: int, N: int, r_true: int, device, storage: Optional[torch.Tensor] = None):
+    def __init__(self, K: int, N: int, r_true: int, device, storage: Optional[torch.Tensor] = None, dtype=torch.bfloat16):
         self.K, self.N, self.r_true, self.R = K, N, r_true, padded_rank(r_true)
         n = self.numel(K, N, r_true)
         if storage is None:
-            storage = torch.zeros(n, dtype=torch.bfloat16, device=device)
-        assert storage.numel() == n and storage.dtype == torch.bfloat16
+            storage = torch.zeros(n, dtype=dtype, device=device)
+        assert storage.numel() == n and storage.dtype in (torch.bfloat16, torch.float16)
+        self.dtype = storage.dtype
         R = self.R
         self.storage = storage
         o = 0
@@ -92,10 +94,10 @@ class _LoRAProjection(torch.autograd.Function):
         st = _lib.stream_ptr()
         y = torch.empty(M, N, dtype=x2.dtype, device=x2.device)
         ev0 = None
-        if code == _lib.SDT_BF16:
-            ops = mod._packed_operands()
-            w = mod._weight_bf16()
-            t_save = torch.empty(M, ops.R, dtype=torch.bfloat16, device=x2.device)
+        if code in (_lib.SDT_BF16, _lib.SDT_F16):
+            ops = mod._packed_operands(x2.dtype)
+            w = mod._weight_lp(x2.dtype)
+            t_save = torch.empty(M, ops.R, dtype=x2.dtype, device=x2.device)
             if PROFILE is not None:
                 ev0 = _ev()
             _lib.check(lib.sdt_lora_linear_fwd(x2.data_ptr(), w.data_ptr(), _lib.ptr(mod._bias_f32()), ops.A_p.data_ptr(),
@@ -143,10 +145,10 @@ def _site_backward(mod, code, x2, t_save, lora_A, lora_B, dy, need_dx):
     else:
         dA = torch.zeros(mod.r, K, dtype=torch.float32, device=x2.device)
         dB = torch.zeros(N, mod.r, dtype=torch.float32, device=x2.device)
-    if code == _lib.SDT_BF16:
-        ops = mod._packed_operands()
-        wt = mod._weight_t_bf16() if need_dx else None
-        g_ws = torch.empty(M, ops.R, dtype=torch.bfloat16, device=x2.device)
+    if code in (_lib.SDT_BF16, _lib.SDT_F16):
+        ops = mod._packed_operands(x2.dtype)
+        wt = mod._weight_t_lp(x2.dtype) if need_dx else None
+        g_ws = torch.empty(M, ops.R, dtype=x2.dtype, device=x2.device)
         ev0 = _ev() if PROFILE is not None else None
         _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), _lib.ptr(wt), ops.At_p.data_ptr(),
                                            ops.Bt_p.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
@@ -176,16 +178,17 @@ class _LoRAProjectionGroup(torch.autograd.Function):
         N = mods[0].out_features
         G = len(mods)
         st = _lib.stream_ptr()
-        ops = [m._packed_operands() for m in mods]
+        ops = [m._packed_operands(x2.dtype) for m in mods]
         R = ops[0].R
+        code = _lib.dtype_code(x2.dtype)
         ys = [torch.empty(M, N, dtype=x2.dtype, device=x2.device) for _ in mods]
-        ts = [torch.empty(M, R, dtype=torch.bfloat16, device=x2.device) for _ in mods]
+        ts = [torch.empty(M, R, dtype=x2.dtype, device=x2.device) for _ in mods]
         probs = (_lib.LoraProblem * G)(*[
-            _lib.LoraProblem(x2.data_ptr(), m._weight_bf16().data_ptr(), _lib.ptr(m._bias_f32()), o.A_p.data_ptr(),
+            _lib.LoraProblem(x2.data_ptr(), m._weight_lp(x2.dtype).data_ptr(), _lib.ptr(m._bias_f32()), o.A_p.data_ptr(),
                              o.B_p.data_ptr(), y.data_ptr(), t.data_ptr())
             for m, o, y, t in zip(mods, ops, ys, ts)])
         ev0 = _ev() if PROFILE is not None else None
-        _lib.check(lib.sdt_lora_linear_fwd_group(ctypes.addressof(probs), G, mods[0].scaling, M, K, N, R, _lib.SDT_BF16, st),
+        _lib.check(lib.sdt_lora_linear_fwd_group(ctypes.addressof(probs), G, mods[0].scaling, M, K, N, R, code, st),
                    "sdt_lora_linear_fwd_group")
         if ev0 is not None:
             PROFILE.append(("fwd", M, K, N, R, G, ev0, _ev()))
@@ -203,8 +206,9 @@ class _LoRAProjectionGroup(torch.autograd.Function):
         M, K = x2.shape
         N = mods[0].out_features
         lib = _lib.load()
-        ops = [m._packed_operands() for m in mods]
+        ops = [m._packed_operands(x2.dtype) for m in mods]
         R = ops[0].R
+        code = _lib.dtype_code(x2.dtype)
         # every projection received a gradient and the shape qualifies: dX of all of them in ONE launch (summed sources);
         # without dX (text context) the rank projections G = s dY B of the group are the work items of one launch
         if (all(dy is not None for dy in dys)
@@ -212,7 +216,7 @@ class _LoRAProjectionGroup(torch.autograd.Function):
             st = _lib.stream_ptr()
             dys = [dy.contiguous() if dy.dtype == x2.dtype else dy.to(x2.dtype).contiguous() for dy in dys]
             dx = torch.empty_like(x2) if ctx.need_dx else None
-            gws = [torch.empty(M, R, dtype=torch.bfloat16, device=x2.device) for _ in mods]
+            gws = [torch.empty(M, R, dtype=x2.dtype, device=x2.device) for _ in mods]
             grads, dAs, dBs = [], [], []
             for m in mods:
                 if m._grad_A is not None:
@@ -224,12 +228,12 @@ class _LoRAProjectionGroup(torch.autograd.Function):
                     dAs.append(dA); dBs.append(dB)
                     grads += [dA, dB]
             probs = (_lib.LoraBwdProblem * G)(*[
-                _lib.LoraBwdProblem(dy.data_ptr(), x2.data_ptr(), m._weight_t_bf16().data_ptr() if ctx.need_dx else None,
+                _lib.LoraBwdProblem(dy.data_ptr(), x2.data_ptr(), m._weight_t_lp(x2.dtype).data_ptr() if ctx.need_dx else None,
                                     o.At_p.data_ptr(), o.Bt_p.data_ptr(), t.data_ptr(), g.data_ptr(), dA.data_ptr(), dB.data_ptr())
                 for dy, m, o, t, g, dA, dB in zip(dys, mods, ops, ts, gws, dAs, dBs)])
             ev0 = _ev() if PROFILE is not None else None
             _lib.check(lib.sdt_lora_linear_bwd_group(ctypes.addressof(probs), G, mods[0].scaling, _lib.ptr(dx), M, K, N, R,
-                                                     mods[0].r, _lib.SDT_BF16, _lib.wgrad_workspace(), st),
+                                                     mods[0].r, code, _lib.wgrad_workspace(), st),
                        "sdt_lora_linear_bwd_group")
             if ev0 is not None:
                 PROFILE.append(("bwd", M, K, N, R, G, ctx.need_dx, ev0, _ev()))
@@ -240,7 +244,7 @@ class _LoRAProjectionGroup(torch.autograd.Function):
             if dy is None:                    # this output was not used downstream
                 grads += [None, None]
                 continue
-            dx_g, dA, dB = _site_backward(m, _lib.SDT_BF16, x2, ts[g], lora_params[2 * g], lora_params[2 * g + 1], dy, ctx.need_dx)
+            dx_g, dA, dB = _site_backward(m, code, x2, ts[g], lora_params[2 * g], lora_params[2 * g + 1], dy, ctx.need_dx)
             grads += [dA, dB]
             if dx_g is not None:
                 dx = dx_g if dx is None else dx.add_(dx_g)
@@ -256,7 +260,7 @@ def groupable(mods, x2: torch.Tensor) -> bool:
     if not x2.is_cuda or x2.shape[0] == 0:
         return False
     dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x2.dtype
-    if dt != torch.bfloat16:
+    if dt not in (torch.bfloat16, torch.float16):
         return False
     return all(m.in_features == m0.in_features and m.out_features == m0.out_features and m.r == m0.r
                and m.scaling == m0.scaling and (m.bias is None) == (m0.bias is None) and m.lora_dropout_p == 0.0
@@ -272,8 +276,9 @@ def project_group(mods, x: torch.Tensor):
         return [m(x) for m in mods]
     _lib.require_cuda(x2, *(m.weight for m in mods))
     _lib.device_check()
-    if x2.dtype != torch.bfloat16:
-        x2 = x2.to(torch.bfloat16)
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x2.dtype
+    if x2.dtype != dt:
+        x2 = x2.to(dt)
     params = [p for m in mods for p in (m.lora_A, m.lora_B)]
     ys = _LoRAProjectionGroup.apply(x2.contiguous(), mods, *params)
     return [y.view(*lead, m.out_features) for y, m in zip(ys, mods)]
@@ -306,19 +311,23 @@ class _LoRABase(nn.Module):
     def _weight_2d(self) -> torch.Tensor:
         return self.weight.view(self.out_features, self.in_features)
 
-    def _weight_bf16(self) -> torch.Tensor:
+    def _weight_lp(self, dtype=torch.bfloat16) -> torch.Tensor:
+        """the frozen weight [N,K] in the 16-bit compute format (bf16 or fp16); cached"""
         w = self.weight
-        key = (w.data_ptr(), w._version)
+        key = (w.data_ptr(), w._version, dtype)
         if self._w_cache is None or self._w_cache[0] != key:
-            self._w_cache = (key, self._weight_2d().detach().to(torch.bfloat16).contiguous())
+            self._w_cache = (key, self._weight_2d().detach().to(dtype).contiguous())
         return self._w_cache[1]
 
-    def _weight_t_bf16(self) -> torch.Tensor:
+    def _weight_t_lp(self, dtype=torch.bfloat16) -> torch.Tensor:
+        """its transpose [K,N] (the B-type operand of the input-gradient GEMM); cached"""
         w = self.weight
-        key = (w.data_ptr(), w._version)
+        key = (w.data_ptr(), w._version, dtype)
         if self._wt_cache is None or self._wt_cache[0] != key:
-            self._wt_cache = (key, self._weight_2d().detach().to(torch.bfloat16).t().contiguous())
+            self._wt_cache = (key, self._weight_2d().detach().to(dtype).t().contiguous())
         return self._wt_cache[1]
+
+    _weight_bf16, _weight_t_bf16 = _weight_lp, _weight_t_lp     # older call sites / tools
 
     def _bias_f32(self) -> Optional[torch.Tensor]:
         b = self.bias
@@ -331,15 +340,21 @@ class _LoRABase(nn.Module):
             self._b_cache = (key, b.detach().float())
         return self._b_cache[1]
 
-    def _packed_operands(self) -> PackedOperands:
+    def _packed_operands(self, dtype=torch.bfloat16) -> PackedOperands:
         if self._ops_external:
+            if self._ops.dtype != dtype:      # first launch in the other 16-bit format: the arena re-packs every site once
+                arena = self._arena_ref() if self._arena_ref is not None else None
+                if arena is None:
+                    raise SdtError("packed LoRA operands belong to an arena that no longer exists")
+                arena.set_compute_dtype(dtype)
             return self._ops       # refreshed by LoraArena.pack() after every optimizer step
         A, B = self.lora_A, self.lora_B
-        if self._ops is None or self._ops.storage.device != A.device:
-            self._ops = PackedOperands(self.in_features, self.out_features, self.r, A.device)
+        if self._ops is None or self._ops.storage.device != A.device or self._ops.dtype != dtype:
+            self._ops = PackedOperands(self.in_features, self.out_features, self.r, A.device, dtype=dtype)
         ver = (A._version, B._version)
         if self._ops.versions != ver:
-            _pack_sites([self._ops.site(A.detach(), B.detach())], self._ops.R * (self.in_features + self.out_features), A.device)
+            _pack_sites([self._ops.site(A.detach(), B.detach())], self._ops.R * (self.in_features + self.out_features), A.device,
+                        dtype)
             self._ops.versions = ver
         return self._ops
 
@@ -350,8 +365,6 @@ class _LoRABase(nn.Module):
             raise SdtError("lora dropout > 0 is not implemented in the fused kernel (every shipped optim_target uses 0.)")
         if torch.is_autocast_enabled():
             x2 = x2.to(torch.get_autocast_dtype("cuda"))
-        if x2.dtype == torch.float16:
-            raise SdtError("fp16 is not implemented: use bf16 (trainer.precision=bf16) or fp32")
         if x2.shape[0] == 0:                 # empty batch: nothing to launch (F.linear returns an empty tensor too)
             return x2.new_zeros(0, self.out_features) + 0.0 * (self.lora_A.sum() + self.lora_B.sum()).to(x2.dtype)
         return _LoRAProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self)

@@ -280,3 +280,69 @@ def test_lora_gradients_are_bit_reproducible(sdt_lib, M, K, N, rank):
     # and the values are still the oracle's
     dA_ref, dB_ref = lora_ref.ref_lora_weight_grads_chunked(x, ref.lora_A, ref.lora_B, ref.scaling, dy)
     assert rel(runs[0][0], dA_ref) <= 2e-2 and rel(runs[0][1], dB_ref) <= 2e-2
+
+
+F16_CASES = [
+    ("linear", (2, 77, 768), 768, 320, 4, 1, False),        # single-CTA kernel, rank 4
+    ("linear", (8, 1024, 640), 640, 640, 16, 16, True),     # CTA-pair kernel with bias (bias hi/lo pair in fp16)
+    ("linear", (1, 1000, 640), 640, 5120, 16, 8, True),     # 224-wide tiles, ragged M
+    ("linear", (2, 300, 1280), 1280, 1280, 64, 64, False),  # rank 64
+    ("conv", (2, 320, 16, 16), 320, 320, 16, 1, True),      # proj_in 1x1 conv
+]
+
+
+@pytest.mark.parametrize("case", F16_CASES, ids=[f"{c[0]}-{c[2]}x{c[3]}-r{c[4]}" for c in F16_CASES])
+def test_get_lora_forward_backward_fp16(sdt_lib, case):
+    """The reference's stock configs train with ``trainer.precision: 16`` (configs/lora.yaml:50): IEEE half operands on the same
+    tcgen05 kernels (instruction-descriptor format field + fp16 conversions).  Bound: 2e-2 as for bf16 -- and, half having three
+    more mantissa bits than bf16, the measured error must also be well below the bf16 run's."""
+    kind, xshape, cin, cout, rank, alpha, bias = case
+    errs = {}
+    for dtype in (torch.float16, torch.bfloat16):
+        ref, ours = make_pair(kind, cin, cout, rank, alpha, bias, 7, torch.bfloat16)   # operands exact in both 16-bit formats
+        with torch.no_grad():                          # ... if they also fit fp16's range / precision: round through both
+            for m in (ref, ours):
+                for p in (m.weight, m.lora_A, m.lora_B):
+                    p.copy_(p.float().half().bfloat16().half().float().to(p.dtype))
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(*xshape, generator=g).bfloat16().half().float()
+        xr = x.double().requires_grad_(True)
+        yr = ref(xr)
+        dy = torch.randn(yr.shape, generator=g).bfloat16().half().float()
+        yr.backward(dy.double())
+        xo = x.to(DEV).to(dtype).requires_grad_(True)
+        yo = ours(xo)
+        assert yo.dtype == dtype
+        yo.backward(dy.to(DEV).to(dtype))
+        errs[dtype] = (rel(yo, yr), rel(xo.grad, xr.grad), rel(ours.lora_A.grad, ref.lora_A.grad), rel(ours.lora_B.grad, ref.lora_B.grad))
+    for e in errs[torch.float16]:
+        assert e <= 2e-2, errs
+    assert errs[torch.float16][0] < 0.5 * errs[torch.bfloat16][0], errs        # y: one rounding of the output dominates
+    assert errs[torch.float16][1] < 0.5 * errs[torch.bfloat16][1], errs        # dx likewise
+
+
+def test_fp16_grouped_qkv_and_autocast(sdt_lib):
+    """q / k / v as one fp16 launch (+ summed-source dX), and fp32 masters driven through torch.autocast(float16)."""
+    from scal_sdt_b200.lora import groupable, project_group
+    pairs = [make_pair("linear", 640, 640, 16, 16, False, 100 + g, torch.bfloat16) for g in range(3)]
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 300, 640, generator=gen).bfloat16().float()
+    dys = [torch.randn(2, 300, 640, generator=gen).bfloat16().float() for _ in range(3)]
+    xr = x.double().requires_grad_(True)
+    yrs = [ref(xr) for ref, _ in pairs]
+    torch.autograd.backward(yrs, [d.double() for d in dys])
+    mods = [ours for _, ours in pairs]
+    xo = x.to(DEV).half().requires_grad_(True)
+    assert groupable(mods, xo.reshape(-1, 640))
+    yos = project_group(mods, xo)
+    torch.autograd.backward(yos, [d.to(DEV).half() for d in dys])
+    for g in range(3):
+        assert yos[g].dtype == torch.float16 and rel(yos[g], yrs[g]) <= 2e-2
+        assert rel(mods[g].lora_A.grad, pairs[g][0].lora_A.grad) <= 2e-2 and rel(mods[g].lora_B.grad, pairs[g][0].lora_B.grad) <= 2e-2
+    assert rel(xo.grad, xr.grad) <= 2e-2
+    # autocast: fp32 input and fp32 frozen weight, fp16 compute
+    ref, ours = pairs[0]
+    x32 = x.to(DEV)
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = ours(x32)
+    assert y.dtype == torch.float16 and rel(y, yrs[0]) <= 2e-2

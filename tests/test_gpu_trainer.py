@@ -94,9 +94,11 @@ def test_cuda_graph_step_matches_eager(sdt_lib):
     tr.optimizer.zero_grad()
     loss_e = tr.training_step(batch, 0, tr._g_noise, tr._g_t)
     loss_e.backward()
-    assert loss_g.item() == loss_e.item()
-    # the dA / dB reductions are combined in a fixed order (two-stage, csrc/lora_wgrad.cu): replay == eager, bit for bit
-    assert torch.equal(grads_g, tr.arena.grads)
+    # The LoRA kernels are bit-reproducible (test_gpu_lora.py::test_lora_gradients_are_bit_reproducible); the host model around
+    # them is not: torch's SDPA backward and the GroupNorm statistics accumulate with float atomics (tools/determinism_probe.py),
+    # so two executions of the same step agree to rounding, not to the bit.
+    assert abs(loss_g.item() - loss_e.item()) <= 1e-3 * abs(loss_e.item())
+    assert (grads_g - tr.arena.grads).norm() <= 2e-2 * tr.arena.grads.norm()
     tr2 = make(2e-3)
     tr2.enable_cuda_graph(batch)
     first = tr2.graphed_step(batch).item()
@@ -170,17 +172,22 @@ def test_bf16_forward_under_ema_weights_uses_the_ema_weights(sdt_lib):
     t = torch.tensor([5, 500], device=dev)
     with torch.no_grad():
         tr.unet_ema._shadow_flat.mul_(0.5)                     # shadow != parameters
-        y_train = tr.unet(lat, t, cond).sample.clone()
+        packed_train = tr.arena.packed.clone()
         with tr.unet_ema.average_parameters():
-            y_ema = tr.unet(lat, t, cond).sample.clone()
-        y_back = tr.unet(lat, t, cond).sample.clone()
+            packed_ema = tr.arena.packed.clone()               # what the kernels read inside the context
+            y_ema = tr.unet(lat, t, cond).sample.float()
+        packed_back = tr.arena.packed.clone()
+        y_back = tr.unet(lat, t, cond).sample.float()
         # the same EMA values loaded the "official" way: copy into the masters, repack
         tr.arena.params.copy_(tr.unet_ema._shadow_flat)
         tr.arena.pack()
-        y_loaded = tr.unet(lat, t, cond).sample
-    assert torch.equal(y_back, y_train)
-    assert torch.equal(y_ema, y_loaded)
-    assert not torch.equal(y_ema, y_train)
+        y_loaded = tr.unet(lat, t, cond).sample.float()
+    assert torch.equal(packed_back, packed_train)               # restored on exit
+    assert torch.equal(packed_ema, tr.arena.packed)             # EMA operands inside == EMA values loaded and packed
+    assert not torch.equal(packed_ema, packed_train)
+    # forward outputs (the host model's GroupNorm statistics use float atomics: compare to rounding, not to the bit)
+    assert (y_ema - y_loaded).norm() <= 2e-2 * y_loaded.norm()
+    assert (y_ema - y_back).norm() > 4 * (y_ema - y_loaded).norm()
     # module without an arena: the per-module operand cache is keyed on Parameter versions, which .data writes do not bump
     torch.manual_seed(0)
     lin = get_lora(nn.Linear(64, 32).to(dev).requires_grad_(False), 4, 4)
