@@ -115,6 +115,17 @@ int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems /* host */, i
                               int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* ws /* as above */,
                               void* stream);
 
+/* ---- LoRA dropout on the rank path (modules/lora.py:12; loralib 0.1: (dropout(x) A^T) B^T * scaling) --------------------
+ * Compatibility path (every shipped optim_target has dropout 0): the projection runs on the concatenated contraction
+ * X' = [x | xd], W' = [W | 0], A' = [0 | A] with xd = x * keep / (1 - p), through the same fused kernels.
+ *   backward == 0: in = x [M,K] -> out = X' [M,2K]
+ *   backward == 1: in = dX' [M,2K] -> out = dx [M,K] = dX'[:, :K] + dX'[:, K:] * keep / (1 - p)
+ * keep is regenerated from Philox4x32-10 keyed by *seed_dev (device int64: a captured graph draws fresh masks per replay
+ * when the caller refreshes it) and `salt` (distinct per site and call).  p is realised on a 1/65536 grid.  bf16 / fp16.
+ */
+int sdt_lora_dropout(const void* in, void* out, int64_t M, int64_t K, float p, const int64_t* seed_dev, uint64_t salt,
+                     int backward, int dtype, void* stream);
+
 /* ---- LoRA operand packing (multi-tensor, one launch for all sites) ---------------------------
  * For every site i: from the f32 master lora_A[r_true,K], lora_B[N,r_true] write the four bf16
  * operand layouts the tensor-core kernels read, zero-padded to rank r:

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sdt_lora_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
+    "sdt_lora_dropout": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_uint64, c_int, c_int, c_void_p]),
     "sdt_lora_pack": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p]),
     "sdt_noise_target": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64,
                                  c_int64, c_int, c_void_p, c_void_p]),

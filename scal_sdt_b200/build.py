@@ -16,7 +16,7 @@ BUILD_DIR = PKG_DIR / "_build"
 LIB_PATH = BUILD_DIR / "libsdt_b200.so"
 INCLUDE_DIR = PKG_DIR.parent / "include"
 
-SOURCES = ["api.cu", "elementwise.cu", "groupnorm.cu", "layernorm.cu", "comm.cu", "simt_gemm.cu", "lora_gemm.cu", "lora_gemm2.cu", "lora_wgrad.cu", "lora_api.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "groupnorm.cu", "layernorm.cu", "comm.cu", "simt_gemm.cu", "lora_gemm.cu", "lora_gemm2.cu", "lora_wgrad.cu", "lora_api.cu", "dropout.cu"]
 
 COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -220,20 +220,42 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
           }
       }
       const int fq = f0 + 4 * (tid & 31);            // first of this thread's four features
+      // accumulate into dA / dB: ALL old values are loaded before the first store (written as `+=` per element the compiler
+      // must keep every load behind the previous store -- 16 dependent L2 round trips, ~15 us per launch, measured)
+      if (fq < F) {                                  // F % 8 == 0 and fq % 4 == 0: the four features are in range together
+        if (transposed) {
+          float4 o[V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const int j = i * 4 + (tid >> 5);
-        if (j < p.r_true && fq < F) {                // F % 8 == 0 and fq % 4 == 0: the four features are in range together
-          if (transposed) {
-            float4* dst = reinterpret_cast<float4*>(out + (size_t)j * F + fq);
-            float4 o = *dst;
-            o.x += acc[i].x; o.y += acc[i].y; o.z += acc[i].z; o.w += acc[i].w;
-            *dst = o;
-          } else {
-            out[(size_t)(fq + 0) * p.r_true + j] += acc[i].x;
-            out[(size_t)(fq + 1) * p.r_true + j] += acc[i].y;
-            out[(size_t)(fq + 2) * p.r_true + j] += acc[i].z;
-            out[(size_t)(fq + 3) * p.r_true + j] += acc[i].w;
+          for (int i = 0; i < V; ++i) {
+            const int j = i * 4 + (tid >> 5);
+            if (j < p.r_true) o[i] = __ldcg(reinterpret_cast<const float4*>(out + (size_t)j * F + fq));
+          }
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const int j = i * 4 + (tid >> 5);
+            if (j < p.r_true)
+              *reinterpret_cast<float4*>(out + (size_t)j * F + fq) =
+                  make_float4(o[i].x + acc[i].x, o[i].y + acc[i].y, o[i].z + acc[i].z, o[i].w + acc[i].w);
+          }
+        } else {
+          float o[V][4];
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const int j = i * 4 + (tid >> 5);
+            if (j < p.r_true) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) o[i][q] = __ldcg(out + (size_t)(fq + q) * p.r_true + j);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const int j = i * 4 + (tid >> 5);
+            if (j < p.r_true) {
+              out[(size_t)(fq + 0) * p.r_true + j] = o[i][0] + acc[i].x;
+              out[(size_t)(fq + 1) * p.r_true + j] = o[i][1] + acc[i].y;
+              out[(size_t)(fq + 2) * p.r_true + j] = o[i][2] + acc[i].z;
+              out[(size_t)(fq + 3) * p.r_true + j] = o[i][3] + acc[i].w;
+            }
           }
         }
       }

@@ -167,6 +167,97 @@ def _site_backward(mod, code, x2, t_save, lora_A, lora_B, dy, need_dx):
     return dx, dA, dB
 
 
+# ---- dropout on the rank path (loralib: ``(dropout(x) @ A.T @ B.T) * scaling``) -------------------------------------------------
+_dropout_seed: dict = {}
+_dropout_sites = 0
+
+
+def dropout_seed(device) -> torch.Tensor:
+    """The device-resident int64 seed of the LoRA dropout masks on ``device`` (one per device).  Kernels read it from memory, so a
+    captured CUDA graph draws new masks on every replay as long as ``advance_dropout_seed`` runs between replays."""
+    key = torch.device(device).index
+    t = _dropout_seed.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64, device=device)
+        t.random_()                                           # from torch's default CUDA generator: follows torch.manual_seed
+        _dropout_seed[key] = t
+    return t
+
+
+def advance_dropout_seed(device, generator=None) -> None:
+    """New masks for the next step (called once per optimisation step by the trainer, outside any captured graph)."""
+    dropout_seed(device).random_(generator=generator)
+
+
+class _LoRADropoutProjection(torch.autograd.Function):
+    """Training-mode projection of a site with ``lora_dropout > 0``: the fused kernels on the concatenated contraction
+    ``[x | dropout(x)]`` (see ``csrc/dropout.cu``).  Twice the GEMM work of the plain path -- no shipped optim_target uses
+    dropout, this exists so that a reference config that sets it runs instead of raising."""
+
+    @staticmethod
+    def forward(ctx, x2, lora_A, lora_B, mod):
+        lib = _lib.load()
+        M, K = x2.shape
+        N = mod.out_features
+        code = _lib.dtype_code(x2.dtype)
+        st = _lib.stream_ptr()
+        dev = x2.device
+        mod._drop_calls += 1
+        salt = (mod._drop_site << 32) | (mod._drop_calls & 0xFFFFFFFF)
+        seed = dropout_seed(dev).clone()                      # the value this forward used, for the backward
+        xcat = torch.empty(M, 2 * K, dtype=x2.dtype, device=dev)
+        _lib.check(lib.sdt_lora_dropout(x2.data_ptr(), xcat.data_ptr(), M, K, mod.lora_dropout_p, seed.data_ptr(), salt, 0, code, st),
+                   "sdt_lora_dropout")
+        ops = mod._packed_operands(x2.dtype)
+        a_cat = torch.zeros(ops.R, 2 * K, dtype=x2.dtype, device=dev)
+        a_cat[:, K:] = ops.A_p                                # A' = [0 | A]: the rank path sees only the dropped-out half
+        y = torch.empty(M, N, dtype=x2.dtype, device=dev)
+        t_save = torch.empty(M, ops.R, dtype=x2.dtype, device=dev)
+        _lib.check(lib.sdt_lora_linear_fwd(xcat.data_ptr(), mod._weight_cat_lp(x2.dtype).data_ptr(), _lib.ptr(mod._bias_f32()),
+                                           a_cat.data_ptr(), ops.B_p.data_ptr(), mod.scaling, y.data_ptr(), t_save.data_ptr(),
+                                           M, 2 * K, N, ops.R, code, st), "sdt_lora_linear_fwd")
+        ctx.mod, ctx.code, ctx.salt = mod, code, salt
+        ctx.need_dx = x2.requires_grad
+        ctx.save_for_backward(xcat, t_save, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xcat, t_save, seed = ctx.saved_tensors
+        mod, code = ctx.mod, ctx.code
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        M, K2 = xcat.shape
+        K, N = K2 // 2, mod.out_features
+        dev = xcat.device
+        dy = dy.contiguous()
+        if dy.dtype != xcat.dtype:
+            dy = dy.to(xcat.dtype)
+        ops = mod._packed_operands(xcat.dtype)
+        at_cat = torch.zeros(K2, ops.R, dtype=xcat.dtype, device=dev)
+        at_cat[K:] = ops.At_p
+        dxcat = torch.empty(M, K2, dtype=xcat.dtype, device=dev) if ctx.need_dx else None
+        g_ws = torch.empty(M, ops.R, dtype=xcat.dtype, device=dev)
+        dA_cat = torch.zeros(mod.r, K2, dtype=torch.float32, device=dev)
+        direct = mod._grad_A is not None
+        dB = mod._grad_B if direct else torch.zeros(N, mod.r, dtype=torch.float32, device=dev)
+        wt = mod._weight_cat_t_lp(xcat.dtype) if ctx.need_dx else None
+        _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), xcat.data_ptr(), _lib.ptr(wt), at_cat.data_ptr(), ops.Bt_p.data_ptr(),
+                                           t_save.data_ptr(), mod.scaling, _lib.ptr(dxcat), g_ws.data_ptr(), dA_cat.data_ptr(),
+                                           dB.data_ptr(), M, K2, N, ops.R, mod.r, code, _lib.wgrad_workspace(), st),
+                   "sdt_lora_linear_bwd")
+        dx = None
+        if ctx.need_dx:
+            dx = torch.empty(M, K, dtype=xcat.dtype, device=dev)
+            _lib.check(lib.sdt_lora_dropout(dxcat.data_ptr(), dx.data_ptr(), M, K, mod.lora_dropout_p, seed.data_ptr(), ctx.salt, 1,
+                                            code, st), "sdt_lora_dropout")
+        dA = dA_cat[:, K:]                                     # the gradient of A' = [0 | A] restricted to A
+        if direct:
+            mod._grad_A.add_(dA)
+            return dx, None, None, None
+        return dx, dA.contiguous(), dB, None
+
+
 class _LoRAProjectionGroup(torch.autograd.Function):
     """G same-shape projections of ONE input (to_q / to_k / to_v on the normalised hidden states; to_k / to_v of one or two
     cross-attentions on the text context) as the work items of one ``sdt_lora_linear_fwd_group`` launch."""
@@ -306,6 +397,12 @@ class _LoRABase(nn.Module):
         self._arena_ref = None               # weakref to that arena (refresh_packed_operands)
         self._grad_A = None
         self._grad_B = None
+        global _dropout_sites
+        _dropout_sites += 1
+        self._drop_site = _dropout_sites      # salt of this site's dropout masks
+        self._drop_calls = 0
+        self._wcat_cache = None
+        self._wcat_t_cache = None
 
     # ---- frozen operand caches ------------------------------------------------------------------
     def _weight_2d(self) -> torch.Tensor:
@@ -328,6 +425,24 @@ class _LoRABase(nn.Module):
         return self._wt_cache[1]
 
     _weight_bf16, _weight_t_bf16 = _weight_lp, _weight_t_lp     # older call sites / tools
+
+    def _weight_cat_lp(self, dtype) -> torch.Tensor:
+        """[W | 0] [N, 2K]: the base weight on the concatenated contraction of the dropout path; cached"""
+        w = self.weight
+        key = (w.data_ptr(), w._version, dtype)
+        if self._wcat_cache is None or self._wcat_cache[0] != key:
+            wl = self._weight_lp(dtype)
+            self._wcat_cache = (key, torch.cat([wl, torch.zeros_like(wl)], dim=1).contiguous())
+        return self._wcat_cache[1]
+
+    def _weight_cat_t_lp(self, dtype) -> torch.Tensor:
+        """its transpose [2K, N] = [W^T ; 0]; cached"""
+        w = self.weight
+        key = (w.data_ptr(), w._version, dtype)
+        if self._wcat_t_cache is None or self._wcat_t_cache[0] != key:
+            wt = self._weight_t_lp(dtype)
+            self._wcat_t_cache = (key, torch.cat([wt, torch.zeros_like(wt)], dim=0).contiguous())
+        return self._wcat_t_cache[1]
 
     def _bias_f32(self) -> Optional[torch.Tensor]:
         b = self.bias
@@ -361,12 +476,14 @@ class _LoRABase(nn.Module):
     def _project(self, x2: torch.Tensor) -> torch.Tensor:
         _lib.require_cuda(x2, self.weight, self.lora_A)
         _lib.device_check()
-        if self.training and self.lora_dropout_p > 0.0:
-            raise SdtError("lora dropout > 0 is not implemented in the fused kernel (every shipped optim_target uses 0.)")
         if torch.is_autocast_enabled():
             x2 = x2.to(torch.get_autocast_dtype("cuda"))
         if x2.shape[0] == 0:                 # empty batch: nothing to launch (F.linear returns an empty tensor too)
             return x2.new_zeros(0, self.out_features) + 0.0 * (self.lora_A.sum() + self.lora_B.sum()).to(x2.dtype)
+        if self.training and self.lora_dropout_p > 0.0:       # loralib: dropout acts on the rank path's input, training mode only
+            if x2.dtype == torch.float32:
+                raise SdtError("lora dropout > 0 runs on the bf16 / fp16 tensor-core path only (fp32 is the parity path)")
+            return _LoRADropoutProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self)
         return _LoRAProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self)
 
     def extra_repr(self) -> str:

@@ -85,12 +85,18 @@ class LatentDiffusionTrainer:
             # the reference keeps EMA on global rank 0 only (model.py:399-401); parameters are identical on every rank
             # after the step, so computing it everywhere is equivalent and keeps ranks symmetric
             self.unet_ema = ExponentialMovingAverage(unet, float(ema.get("decay", 0.995)))
+        self._has_dropout = any(m.lora_dropout_p > 0.0 for _, m in lora_modules(unet))
         self.generator = torch.Generator(device=self.device)
         if seed is not None:
             self.generator.manual_seed(seed + self.exchange.rank)
         self.global_step = 0
 
     # ---- modules/model.py:289-316 ----------------------------------------------------------------------
+    def _new_dropout_masks(self) -> None:
+        if self._has_dropout:
+            from .lora import advance_dropout_seed
+            advance_dropout_seed(self.device, self.generator)
+
     def _denoise_loss(self, latents, conds, noise=None, timesteps=None, want_elementwise=False):
         if noise is None:
             noise = torch.randn(latents.shape, dtype=latents.dtype, device=latents.device, generator=self.generator)
@@ -148,6 +154,7 @@ class LatentDiffusionTrainer:
         """zero_grad -> training_step -> backward -> exchange -> optimizer (+EMA) -> repack.  Returns the loss tensor
         (device resident; call ``.item()`` only when logging)."""
         self.optimizer.zero_grad()
+        self._new_dropout_masks()
         loss = self.training_step(batch, self.global_step, noise, timesteps)
         if getattr(self, "_overlap", None) is not None:
             self._overlap.begin()
@@ -294,6 +301,7 @@ class LatentDiffusionTrainer:
         ent["cond"].copy_(batch["conds"], non_blocking=True)
         ent["noise"].normal_(generator=self.generator)
         ent["t"].random_(0, self.scheduler.config.num_train_timesteps, generator=self.generator)
+        self._new_dropout_masks()
         ent["graph"].replay()
         self.replayed_launches += ent["launches"]
         self.optimizer_step()
@@ -315,6 +323,7 @@ class LatentDiffusionTrainer:
         """Eager, tiny: new noise / timesteps (modules/model.py:294,297-298) and the step-dependent optimizer scalars."""
         self._g_noise.normal_(generator=self.generator)
         self._g_t.random_(0, self.scheduler.config.num_train_timesteps, generator=self.generator)
+        self._new_dropout_masks()
         self.optimizer.step_count += 1
         self.optimizer.refresh_device_hyper(self.optimizer.step_count)
         if self.unet_ema is not None:
