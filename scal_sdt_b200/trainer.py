@@ -161,14 +161,18 @@ class LatentDiffusionTrainer:
         loss.backward()
         self.optimizer_step()
         self.global_step += 1
-        return loss
+        # detached: a caller that keeps the returned loss must not keep the step's autograd graph alive with it (its
+        # AccumulateGrad nodes carry the eager stream and would poison a later CUDA-graph capture of the same parameters)
+        return loss.detach()
 
     # ---- whole-step CUDA graph -------------------------------------------------------------------------------
     def enable_cuda_graph(self, example_batch: dict, warmup: int = 3) -> None:
         """Capture zero_grad -> forward -> loss -> backward -> all-reduce -> AdamW(+EMA) -> repack as ONE CUDA graph.
 
         The step launches ~3,000 kernels; once the GPU work per step drops towards the host's launch rate the Python /
-        driver overhead shows.  Replays read the batch, the noise and the timesteps from static buffers (filled by a few
+        driver overhead shows.  (Drop references to losses of earlier ``training_step`` calls first: a live autograd graph keeps
+        the parameters' AccumulateGrad nodes of the eager stream alive, and torch refuses to capture a backward that must
+        synchronise with an uncaptured stream -- cudaErrorStreamCaptureIsolation.)  Replays read the batch, the noise and the timesteps from static buffers (filled by a few
         eager launches before each replay) and the optimizer's step-dependent scalars from a device table."""
         dev = self.device
         self._g_lat = example_batch["latents"].to(dev).clone()
