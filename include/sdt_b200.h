@@ -115,6 +115,21 @@ int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems /* host */, i
                               int64_t M, int64_t K, int64_t N, int r, int r_true, int dtype, void* ws /* as above */,
                               void* stream);
 
+/* ---- K2 (batched reductions): dA / dB of up to sdt_lora_wgrad_max_sites() sites of ANY shapes in ONE launch -----------
+ * sdt_lora_linear_bwd(_group) called with dA == NULL and dB == NULL computes only dX and G = s dY B (g_ws) and leaves the two
+ * token reductions to the caller, who collects the sites of a transformer block (q / k / v / out of both attentions, the
+ * feed-forward projections, proj_in / proj_out: different M, K, N, one padded rank r) and reduces them here:
+ *     dA_i (+)= G_i^T X_i        dB_i (+)= dY_i^T Ts_i
+ * One launch instead of one per site: prologue, ramp-up and the tail of the deterministic second stage are paid once.  The
+ * operands must stay alive and unchanged until the launch has run.  `sites` is a HOST array.  ws as for sdt_lora_linear_bwd.
+ */
+typedef struct {
+  const void* x; const void* g_ws; float* dA; const void* dy; const void* t_save; float* dB;
+  int64_t M, K, N;
+} sdt_wgrad_site;
+int sdt_lora_wgrad_max_sites(void);
+int sdt_lora_wgrad_batch(const sdt_wgrad_site* sites /* host */, int n_sites, int r, int r_true, int dtype, void* ws, void* stream);
+
 /* ---- LoRA dropout on the rank path (modules/lora.py:12; loralib 0.1: (dropout(x) A^T) B^T * scaling) --------------------
  * Compatibility path (every shipped optim_target has dropout 0): the projection runs on the concatenated contraction
  * X' = [x | xd], W' = [W | 0], A' = [0 | A] with xd = x * keep / (1 - p), through the same fused kernels.

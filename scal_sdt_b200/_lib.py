@@ -34,6 +34,11 @@ class LoraBwdProblem(ctypes.Structure):
                 ("g_ws", c_void_p), ("dA", c_void_p), ("dB", c_void_p)]
 
 
+class WgradSite(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("g_ws", c_void_p), ("dA", c_void_p), ("dy", c_void_p), ("t_save", c_void_p), ("dB", c_void_p),
+                ("M", c_int64), ("K", c_int64), ("N", c_int64)]
+
+
 MAX_GROUP = 4
 
 
@@ -54,6 +59,8 @@ SIGNATURES = {
     "sdt_lora_linear_bwd_group": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                           c_void_p, c_void_p]),
     "sdt_lora_wgrad_workspace_bytes": (c_size_t, []),
+    "sdt_lora_wgrad_max_sites": (c_int, []),
+    "sdt_lora_wgrad_batch": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sdt_lora_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),

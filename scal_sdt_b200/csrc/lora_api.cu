@@ -8,17 +8,15 @@
 namespace sdt {
 int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
                    void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, bool f16, cudaStream_t st);
-int lora_wgrad_pair_bf16(const void* x, const void* g, float* dA, int64_t K, const void* dy, const void* ts, float* dB,
-                         int64_t N, int64_t M, int r, int r_true, void* ws, bool f16, cudaStream_t st);
 size_t lora_wgrad_workspace_bytes();
+int lora_wgrad_max_sites();
 int lora_fwd_f32(const float* x, const float* w, const float* bias, const float* A, const float* B, float scaling,
                  float* y, float* t_save, int64_t M, int64_t K, int64_t N, int r, cudaStream_t st);
 int lora_bwd_f32(const float* dy, const float* x, const float* w, const float* A, const float* B, const float* t_save,
                  float scaling, float* dx, float* g_ws, float* dA, float* dB, int64_t M, int64_t K, int64_t N, int r,
                  cudaStream_t st);
-struct WgradSite { const void* x; const void* g; float* dA; const void* dy; const void* ts; float* dB; };
-int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, void* ws,
-                          bool f16, cudaStream_t st);
+struct WgradSite { const void* x; const void* g; float* dA; const void* dy; const void* ts; float* dB; int64_t M, K, N; };
+int lora_wgrad_batch_bf16(const WgradSite* sites, int n_sites, int r, int r_true, void* ws, bool f16, cudaStream_t st);
 void debug_set(int key, uint64_t value);
 }  // namespace sdt
 
@@ -73,16 +71,20 @@ extern "C" int sdt_lora_linear_bwd(const void* dy, const void* x, const void* wt
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SDT_BF16 || dtype == SDT_F16) {
     const bool f16 = dtype == SDT_F16;
+    // dA == NULL and dB == NULL: only dX and G are computed; the caller batches the two reductions of several sites into one
+    // sdt_lora_wgrad_batch launch (a transformer block's worth) instead of one small launch per site
+    const bool defer = (dA == nullptr && dB == nullptr);
     if (r > 0)
-      SDT_REQUIRE(x && At && Bt && t_save && g_ws && dA && dB, SDT_ERR_ARG,
-                  "sdt_lora_linear_bwd: x, At, Bt, t_save, g_ws, dA, dB are required when r > 0");
+      SDT_REQUIRE(Bt && g_ws && (dx == nullptr || At) && (defer || (x && t_save && dA && dB)), SDT_ERR_ARG,
+                  "sdt_lora_linear_bwd: Bt, g_ws (and At for dX; x, t_save, dA, dB unless deferred) are required when r > 0");
     SDT_REQUIRE(dx == nullptr || wt != nullptr, SDT_ERR_ARG, "sdt_lora_linear_bwd: wt is required for dX");
     // G = s dY B ; dX = dY W + G A   -- the forward kernel with (dY, W^T, B^T, A^T)
     int rc = lora_gemm_bf16(dy, wt, nullptr, Bt, At, scaling, dx, g_ws, M, /*contraction*/ N, /*outputs*/ K, r,
                             dx != nullptr, f16, st);
-    if (rc != SDT_OK || r == 0) return rc;
+    if (rc != SDT_OK || r == 0 || defer) return rc;
     // dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]: one launch for both reductions
-    return lora_wgrad_pair_bf16(x, g_ws, dA, K, dy, t_save, dB, N, M, r, r_true, ws, f16, st);
+    const WgradSite site{x, g_ws, dA, dy, t_save, dB, M, K, N};
+    return lora_wgrad_batch_bf16(&site, 1, r, r_true, ws, f16, st);
   }
   if (dtype == SDT_F32) {
     SDT_REQUIRE(r_true == r, SDT_ERR_ARG, "sdt_lora_linear_bwd(f32): r_true must equal r");
@@ -113,24 +115,36 @@ extern "C" int sdt_lora_linear_bwd_group(const sdt_lora_bwd_problem* problems, i
   LoraProblem pr[SDT_MAX_GROUP];
   for (int q = 0; q < n_problems; ++q) {
     const sdt_lora_bwd_problem& b = problems[q];
-    SDT_REQUIRE(b.dy && b.x && b.At && b.Bt && b.t_save && b.g_ws && b.dA && b.dB && (dx == nullptr || b.wt), SDT_ERR_ARG,
+    SDT_REQUIRE(b.dy && b.x && b.At && b.Bt && b.t_save && b.g_ws && (dx == nullptr || b.wt), SDT_ERR_ARG,
                 "sdt_lora_linear_bwd_group: null pointer in problem %d", q);
+    SDT_REQUIRE((b.dA == nullptr) == (b.dB == nullptr) && (b.dA == nullptr) == (problems[0].dA == nullptr), SDT_ERR_ARG,
+                "sdt_lora_linear_bwd_group: dA / dB must be given for every problem or for none (deferred reductions)");
     // G_q = s dY_q B_q ; dX += dY_q W_q + G_q A_q   -- the forward kernel's roles with (dY, W^T, B^T, A^T)
     pr[q] = LoraProblem{b.dy, dx ? b.wt : nullptr, nullptr, b.Bt, dx ? b.At : nullptr, dx, b.g_ws};
   }
   int rc = dx != nullptr ? lora_gemm_pair_sum_bf16(pr, n_problems, scaling, M, /*contraction*/ N, /*outputs*/ K, r, f16, st)
                          : lora_gemm_group_bf16(pr, n_problems, scaling, M, N, K, r, /*main=*/false, f16, st);
-  if (rc != SDT_OK) return rc;
+  if (rc != SDT_OK || problems[0].dA == nullptr) return rc;
   // the dA / dB reductions of the whole group: one launch
   WgradSite sites[SDT_MAX_GROUP];
   for (int q = 0; q < n_problems; ++q) {
     const sdt_lora_bwd_problem& b = problems[q];
-    sites[q] = WgradSite{b.x, b.g_ws, b.dA, b.dy, b.t_save, b.dB};
+    sites[q] = WgradSite{b.x, b.g_ws, b.dA, b.dy, b.t_save, b.dB, M, K, N};
   }
-  return lora_wgrad_multi_bf16(sites, n_problems, K, N, M, r, r_true, ws, f16, st);
+  return lora_wgrad_batch_bf16(sites, n_problems, r, r_true, ws, f16, st);
 }
 
 extern "C" size_t sdt_lora_wgrad_workspace_bytes(void) { return lora_wgrad_workspace_bytes(); }
+
+static_assert(sizeof(sdt_wgrad_site) == sizeof(WgradSite), "sdt_wgrad_site mirrors sdt::WgradSite");
+
+extern "C" int sdt_lora_wgrad_max_sites(void) { return lora_wgrad_max_sites(); }
+
+extern "C" int sdt_lora_wgrad_batch(const sdt_wgrad_site* sites, int n_sites, int r, int r_true, int dtype, void* ws, void* stream) {
+  SDT_REQUIRE(dtype == SDT_BF16 || dtype == SDT_F16, SDT_ERR_UNSUPPORTED, "sdt_lora_wgrad_batch: bf16 / fp16 only (there is no fallback)");
+  return lora_wgrad_batch_bf16(reinterpret_cast<const WgradSite*>(sites), n_sites, r, r_true, ws, dtype == SDT_F16,
+                               (cudaStream_t)stream);
+}
 
 extern "C" int sdt_debug_set(int key, uint64_t value) {
   debug_set(key, value);

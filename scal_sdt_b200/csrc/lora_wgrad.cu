@@ -34,15 +34,25 @@ struct WgradCfg {
   static constexpr int TMEM_COLS = R < 32 ? 32 : R;
 };
 
-// One launch covers the dA and dB reductions of up to kWgradSites sites (q / k / v of a self-attention, k / v of two
-// cross-attentions): 2 sub-problems per site, each a range of blockIdx.x.  The tensor maps and pointers sit in one
-// __grid_constant__ block that is indexed in parameter space.
-constexpr int kWgradSites = 4, kWgradSubs = 2 * kWgradSites;
-struct WgradGroup {
-  CUtensorMap u[kWgradSubs], v[kWgradSubs];
-  float* out[kWgradSubs];          // dA [r_true,F] (transposed = 1) or dB [F,r_true] (transposed = 0)
-  int F[kWgradSubs], transposed[kWgradSubs];
-  int f_begin[kWgradSubs + 1];     // first blockIdx.x of every sub-problem (prefix sums of its 128-feature blocks)
+// One launch covers the dA and dB reductions of up to kWgradSites sites OF ANY SHAPES (a whole transformer block: q / k / v /
+// out of both attentions, the two feed-forward projections, proj_in / proj_out -- or just one site): 2 sub-problems per
+// site, each with its own token count, feature width, tensor maps and split of the token range.  The grid is 1-D; a CTA finds
+// its sub-problem by scanning the prefix table, then (feature block, token slice) = (local / n_splits, local % n_splits).  The
+// descriptors sit in one __grid_constant__ block (about 9 KB; kernel parameters may be 32 KB since CUDA 12.1).
+constexpr int kWgradSites = 16, kWgradSubs = 2 * kWgradSites;
+struct alignas(64) WgradSub {
+  CUtensorMap u, v;
+  float* out;              // dA [r_true,F] (transposed = 1) or dB [F,r_true] (transposed = 0)
+  int F, transposed;
+  int M;                   // token rows of this sub-problem
+  int rows_per_split;      // multiple of 64
+  int n_splits;
+  int cta_begin;           // first blockIdx.x of this sub-problem
+  int blk_begin;           // index of its first feature block in the per-launch counter array
+  int pad;
+};
+struct WgradBatch {
+  WgradSub sub[kWgradSubs];
   int n_subs;
 };
 // deterministic mode workspace: [kWgradMaxBlocks counters][partials: one [R x 128] f32 slab per CTA]
@@ -50,10 +60,9 @@ constexpr int kWgradMaxBlocks = 4096, kWgradMaxCtas = 1024;
 constexpr size_t kWgradWorkspaceBytes = (size_t)kWgradMaxBlocks * 4 + (size_t)kWgradMaxCtas * 64 * 128 * 4;
 
 struct WgradParams {
-  int M, r_true;
-  int rows_per_split;     // multiple of 64
+  int r_true;
   unsigned int* counters; // deterministic mode: arrivals per feature block (left at zero); null = atomics
-  float* partial;         // deterministic mode: [gridDim.x][gridDim.y][R][128]
+  float* partial;         // deterministic mode: [CTA][R][128]
   // descriptors are host-built so that the layout constants live in one place (and can be probed)
   uint64_t a_desc_base, b_desc_base;
   uint32_t a_step, b_step, idesc;
@@ -61,7 +70,7 @@ struct WgradParams {
 
 template <int R>
 __global__ void __launch_bounds__(128, 1)
-lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
+lora_wgrad_kernel(const __grid_constant__ WgradBatch gw, const WgradParams p) {
   using C = WgradCfg<R>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,15 +82,21 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int which = 0;
-  while (which + 1 < gw.n_subs && (int)blockIdx.x >= gw.f_begin[which + 1]) ++which;
-  float* const out = gw.out[which];
-  const int F = gw.F[which], transposed = gw.transposed[which];
-  const CUtensorMap* tm_u = &gw.u[which];
-  const CUtensorMap* tm_v = &gw.v[which];
-  const int f0 = ((int)blockIdx.x - gw.f_begin[which]) * C::BF;
-  const int m_begin = blockIdx.y * p.rows_per_split;
-  const int m_end = min(m_begin + p.rows_per_split, p.M);
-  const int nk = (m_end - m_begin + C::BMK - 1) / C::BMK;
+  while (which + 1 < gw.n_subs && (int)blockIdx.x >= gw.sub[which + 1].cta_begin) ++which;
+  const WgradSub& sb = gw.sub[which];
+  float* const out = sb.out;
+  const int F = sb.F, transposed = sb.transposed;
+  const CUtensorMap* tm_u = &sb.u;
+  const CUtensorMap* tm_v = &sb.v;
+  const int local = (int)blockIdx.x - sb.cta_begin;
+  const int n_splits = sb.n_splits;
+  const int fb = local / n_splits, split = local - fb * n_splits;     // neighbouring CTAs: the slices of one feature block
+  const int f0 = fb * C::BF;
+  const int m_begin = split * sb.rows_per_split;
+  const int m_end = min(m_begin + sb.rows_per_split, sb.M);
+  const int nk = m_end > m_begin ? (m_end - m_begin + C::BMK - 1) / C::BMK : 0;
+  const int first_cta = sb.cta_begin + fb * n_splits;                  // slab of slice 0 of this feature block
+  unsigned int* const counter = p.counters != nullptr ? p.counters + sb.blk_begin + fb : nullptr;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(tm_u);
@@ -158,7 +173,7 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
     }
   } else {
     // stage 1: this CTA's partial [R][128 features] (features contiguous: coalesced both ways)
-    float* mine = p.partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * (R * 128);
+    float* mine = p.partial + (size_t)blockIdx.x * (R * 128);
     if (nk > 0) {
       mbar_wait(done, 0);
       tc_fence_after();
@@ -182,7 +197,7 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
     __shared__ unsigned int s_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&p.counters[blockIdx.x], 1u) == gridDim.y - 1) ? 1u : 0u;
+    if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == (unsigned int)n_splits - 1u) ? 1u : 0u;
     __syncthreads();
     if (s_last != 0u) {
       __threadfence();
@@ -192,11 +207,11 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
       // slice order, which is what makes the result reproducible.
       constexpr int V = R / 4;                       // float4 per thread per slice
       constexpr int U = R <= 16 ? 4 : (R == 32 ? 2 : 1);   // slices in flight (register budget: U * V float4)
-      const float4* base = reinterpret_cast<const float4*>(p.partial + (size_t)blockIdx.x * gridDim.y * (R * 128)) + tid;
+      const float4* base = reinterpret_cast<const float4*>(p.partial + (size_t)first_cta * (R * 128)) + tid;
       float4 acc[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const unsigned int n_sl = gridDim.y;
+      const unsigned int n_sl = (unsigned int)n_splits;
       unsigned int sl = 0;
       for (; sl + U <= n_sl; sl += U) {
         float4 v[U][V];
@@ -259,7 +274,7 @@ lora_wgrad_kernel(const __grid_constant__ WgradGroup gw, const WgradParams p) {
           }
         }
       }
-      if (threadIdx.x == 0) p.counters[blockIdx.x] = 0u;     // ready for the next launch on this workspace
+      if (threadIdx.x == 0) *counter = 0u;           // ready for the next launch on this workspace
     }
   }
   tc_fence_before();
@@ -278,11 +293,11 @@ uint64_t debug_get(int key) { return (key >= 0 && key < 32) ? g_dbg[key] : 0; }
 struct WgradSite {       // one LoRA site: dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]
   const void* x; const void* g; float* dA;
   const void* dy; const void* ts; float* dB;
+  int64_t M, K, N;
 };
 
 template <int R>
-static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r_true, void* ws, bool f16,
-                        cudaStream_t st) {
+static int launch_wgrad(const WgradSite* sites, int n_sites, int r_true, void* ws, bool f16, cudaStream_t st) {
   using C = WgradCfg<R>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -290,39 +305,55 @@ static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t 
     attr_set = true;
   }
   const TmapSwizzle vsw = R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32);
-  WgradGroup gw;
+  static thread_local WgradBatch gw;            // ~9 KB: keep it off the stack of the caller's thread
   gw.n_subs = 2 * n_sites;
-  int f_blocks = 0;
+  // work units (128 features x 64 tokens) of every sub-problem
+  long total_units = 0;
+  for (int q = 0; q < gw.n_subs; ++q) {
+    const WgradSite& site = sites[q / 2];
+    const int64_t F = (q & 1) == 0 ? site.K : site.N;
+    total_units += ((F + C::BF - 1) / C::BF) * ((site.M + C::BMK - 1) / C::BMK);
+  }
+  // A CTA streams at most `cpc` 64-token chunks of its feature block: enough CTAs for `per_sm` per SM over the whole launch, at
+  // least `min_chunks` stages of work each (tools/wgrad_ab.py: one CTA per SM beats two on the 22-190 MB shapes -- fewer
+  // partials -- and ties on the small ones).  sdt_debug_set(15, min | per_sm << 8) overrides.
+  const int min_chunks = (g_dbg[15] & 0xff) ? (int)(g_dbg[15] & 0xff) : 8;
+  const int per_sm = (g_dbg[15] >> 8) ? (int)(g_dbg[15] >> 8) : 1;
+  long cpc = (total_units + (long)per_sm * num_sms() - 1) / ((long)per_sm * num_sms());
+  if (cpc < min_chunks) cpc = min_chunks;
+  int ctas = 0, blocks = 0;
   for (int q = 0; q < kWgradSubs; ++q) {
-    const WgradSite& site = sites[q / 2 < n_sites ? q / 2 : 0];       // unused slots repeat site 0 (never selected)
+    WgradSub& sb = gw.sub[q];
+    const WgradSite& site = sites[q < gw.n_subs ? q / 2 : 0];          // unused slots repeat site 0 (never selected)
     const bool is_dA = (q & 1) == 0;
     const void* u = is_dA ? site.x : site.dy;
     const void* v = is_dA ? site.g : site.ts;
-    const int64_t F = is_dA ? K : N;
-    int rc = make_tmap_2d_bf16(&gw.u[q], u, M, F, F * 2, C::BMK, 64, TMAP_SW_128);
+    const int64_t F = is_dA ? site.K : site.N;
+    int rc = make_tmap_2d_bf16(&sb.u, u, site.M, F, F * 2, C::BMK, 64, TMAP_SW_128);
     if (rc != SDT_OK) return rc;
-    rc = make_tmap_2d_bf16(&gw.v[q], v, M, R, (uint64_t)R * 2, C::BMK, R, vsw);
+    rc = make_tmap_2d_bf16(&sb.v, v, site.M, R, (uint64_t)R * 2, C::BMK, R, vsw);
     if (rc != SDT_OK) return rc;
-    gw.out[q] = is_dA ? site.dA : site.dB;
-    gw.F[q] = (int)F;
-    gw.transposed[q] = is_dA ? 1 : 0;
-    gw.f_begin[q] = f_blocks;
-    if (q < gw.n_subs) f_blocks += (int)((F + C::BF - 1) / C::BF);
+    sb.out = is_dA ? site.dA : site.dB;
+    sb.F = (int)F;
+    sb.transposed = is_dA ? 1 : 0;
+    sb.M = (int)site.M;
+    const int m_chunks = (int)((site.M + C::BMK - 1) / C::BMK);
+    int splits = (int)((m_chunks + cpc - 1) / cpc);
+    const int chunks_per_split = (m_chunks + splits - 1) / splits;
+    splits = (m_chunks + chunks_per_split - 1) / chunks_per_split;      // no empty slices
+    sb.rows_per_split = chunks_per_split * C::BMK;
+    sb.n_splits = splits;
+    sb.cta_begin = ctas;
+    sb.blk_begin = blocks;
+    sb.pad = 0;
+    if (q < gw.n_subs) {
+      const int f_blocks = (int)((F + C::BF - 1) / C::BF);
+      ctas += f_blocks * splits;
+      blocks += f_blocks;
+    }
   }
-  gw.f_begin[kWgradSubs] = f_blocks;
   WgradParams p;
-  p.M = (int)M; p.r_true = r_true;
-  const int m_chunks = (int)((M + C::BMK - 1) / C::BMK);
-  // enough CTAs for one per SM, at least 8 stages of work each (tools/wgrad_ab.py: one CTA per SM beats two by ~10 % on the
-  // 22-190 MB shapes -- fewer red.global.add partials -- and ties on the small ones).  sdt_debug_set(15, min | per_sm << 8) overrides.
-  const int min_chunks = (g_dbg[15] & 0xff) ? (int)(g_dbg[15] & 0xff) : 8;
-  const int per_sm = (g_dbg[15] >> 8) ? (int)(g_dbg[15] >> 8) : 1;
-  int splits = (per_sm * num_sms() + f_blocks - 1) / f_blocks;
-  if (splits > (m_chunks + min_chunks - 1) / min_chunks) splits = (m_chunks + min_chunks - 1) / min_chunks;
-  if (splits < 1) splits = 1;
-  const int chunks_per_split = (m_chunks + splits - 1) / splits;
-  p.rows_per_split = chunks_per_split * C::BMK;
-  splits = (m_chunks + chunks_per_split - 1) / chunks_per_split;
+  p.r_true = r_true;
   // A = U tile, MN-major, 128B swizzle: 64-feature blocks 8 KiB apart (LBO), 8-token groups 1 KiB apart (SBO),
   //     16 tokens per MMA -> 2 KiB per k-step
   // B = V tile, MN-major, rows of R*2 bytes with the matching swizzle: 8-token groups 8*R*2 B apart (SBO)
@@ -340,45 +371,41 @@ static int launch_wgrad(const WgradSite* sites, int n_sites, int64_t K, int64_t 
   p.counters = nullptr;
   p.partial = nullptr;
   if (ws != nullptr) {
-    SDT_REQUIRE(f_blocks <= kWgradMaxBlocks && (long)f_blocks * splits <= kWgradMaxCtas, SDT_ERR_UNSUPPORTED,
-                "lora_wgrad: %d feature blocks x %d token slices exceed the deterministic workspace (%d CTAs)", f_blocks, splits,
-                kWgradMaxCtas);
+    SDT_REQUIRE(blocks <= kWgradMaxBlocks && ctas <= kWgradMaxCtas, SDT_ERR_UNSUPPORTED,
+                "lora_wgrad: %d feature blocks / %d CTAs exceed the deterministic workspace (%d / %d): launch fewer sites at once",
+                blocks, ctas, kWgradMaxBlocks, kWgradMaxCtas);
     p.counters = reinterpret_cast<unsigned int*>(ws);
     p.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + (size_t)kWgradMaxBlocks * 4);
   }
-  SDT_CUDA_OK(launch_kernel(lora_wgrad_kernel<R>, dim3(f_blocks, splits), dim3(128), C::SMEM_BYTES, st, true, gw, p));
+  SDT_CUDA_OK(launch_kernel(lora_wgrad_kernel<R>, dim3(ctas), dim3(128), C::SMEM_BYTES, st, true, gw, p));
   SDT_LAUNCH_OK("lora_wgrad");
   return SDT_OK;
 }
 
-// dA / dB of n_sites same-shape sites (1..kWgradSites) in ONE launch
 size_t lora_wgrad_workspace_bytes() { return kWgradWorkspaceBytes; }
+int lora_wgrad_max_sites() { return kWgradSites; }
 
-int lora_wgrad_multi_bf16(const WgradSite* sites, int n_sites, int64_t K, int64_t N, int64_t M, int r, int r_true, void* ws,
-                          bool f16, cudaStream_t st) {
+// dA / dB of n_sites sites (1..kWgradSites) of ANY shapes, one padded rank, in ONE launch
+int lora_wgrad_batch_bf16(const WgradSite* sites, int n_sites, int r, int r_true, void* ws, bool f16, cudaStream_t st) {
   SDT_REQUIRE(sites != nullptr && n_sites >= 1 && n_sites <= kWgradSites, SDT_ERR_ARG, "lora_wgrad: 1..%d sites per launch (got %d)",
               kWgradSites, n_sites);
-  for (int q = 0; q < n_sites; ++q)
-    SDT_REQUIRE(sites[q].x && sites[q].g && sites[q].dA && sites[q].dy && sites[q].ts && sites[q].dB, SDT_ERR_ARG,
-                "lora_wgrad: null pointer (site %d)", q);
-  SDT_REQUIRE(M > 0 && K > 0 && N > 0 && K % 8 == 0 && N % 8 == 0, SDT_ERR_ARG, "lora_wgrad: bad sizes M=%lld K=%lld N=%lld",
-              (long long)M, (long long)K, (long long)N);
+  for (int q = 0; q < n_sites; ++q) {
+    const WgradSite& t = sites[q];
+    SDT_REQUIRE(t.x && t.g && t.dA && t.dy && t.ts && t.dB, SDT_ERR_ARG, "lora_wgrad: null pointer (site %d)", q);
+    SDT_REQUIRE(t.M > 0 && t.K > 0 && t.N > 0 && t.K % 8 == 0 && t.N % 8 == 0 && t.M < (1ll << 31), SDT_ERR_ARG,
+                "lora_wgrad: bad sizes M=%lld K=%lld N=%lld (site %d)", (long long)t.M, (long long)t.K, (long long)t.N, q);
+    SDT_REQUIRE(aligned16(t.x) && aligned16(t.g) && aligned16(t.dy) && aligned16(t.ts), SDT_ERR_ARG,
+                "lora_wgrad: operands must be 16-byte aligned (site %d)", q);
+  }
   SDT_REQUIRE(r_true >= 1 && r_true <= r, SDT_ERR_ARG, "lora_wgrad: r_true=%d outside [1,%d]", r_true, r);
   SDT_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15u) == 0, SDT_ERR_ARG, "lora_wgrad: workspace must be 16-byte aligned");
   switch (r) {
-    case 16: return launch_wgrad<16>(sites, n_sites, K, N, M, r_true, ws, f16, st);
-    case 32: return launch_wgrad<32>(sites, n_sites, K, N, M, r_true, ws, f16, st);
-    case 64: return launch_wgrad<64>(sites, n_sites, K, N, M, r_true, ws, f16, st);
+    case 16: return launch_wgrad<16>(sites, n_sites, r_true, ws, f16, st);
+    case 32: return launch_wgrad<32>(sites, n_sites, r_true, ws, f16, st);
+    case 64: return launch_wgrad<64>(sites, n_sites, r_true, ws, f16, st);
   }
   set_error("lora_wgrad: padded rank must be 16, 32 or 64 (got %d)", r);
   return SDT_ERR_UNSUPPORTED;
-}
-
-// dA[j,k] += sum_m G[m,j] X[m,k]  and  dB[n,j] += sum_m dY[m,n] Ts[m,j]  in ONE launch
-int lora_wgrad_pair_bf16(const void* x, const void* g, float* dA, int64_t K, const void* dy, const void* ts, float* dB,
-                         int64_t N, int64_t M, int r, int r_true, void* ws, bool f16, cudaStream_t st) {
-  const WgradSite site{x, g, dA, dy, ts, dB};
-  return lora_wgrad_multi_bf16(&site, 1, K, N, M, r, r_true, ws, f16, st);
 }
 
 }  // namespace sdt

@@ -127,6 +127,65 @@ class _LoRAProjection(torch.autograd.Function):
         return dx, dA, dB, None
 
 
+# ---- deferred weight-gradient reductions --------------------------------------------------------------------------------------
+class _WgradQueue:
+    """dA / dB reductions waiting to go out as ONE ``sdt_lora_wgrad_batch`` launch.  Inside ``deferred_wgrad()`` the backward
+    of a bf16 / fp16 site computes dX and G = s dY B at once (the gradient chain needs dX) but only *queues* its two token
+    reductions; a full queue -- about a transformer block's sites -- or the end of the context flushes them.  Nothing reads
+    dA / dB before the optimizer, so the only effect is fewer, larger launches.  The queue keeps every operand alive."""
+
+    def __init__(self, max_sites: int):
+        self.max_sites = max_sites
+        self.items: list = []
+
+    def add(self, x2, g_ws, dA, dy, t_save, dB, M, K, N, R, r_true, code) -> None:
+        if self.items and (self.items[0][9:] != (R, r_true, code)):
+            self.flush()                                # one launch = one padded rank / dtype
+        self.items.append((x2, g_ws, dA, dy, t_save, dB, M, K, N, R, r_true, code))
+        if len(self.items) >= self.max_sites:
+            self.flush()
+
+    def flush(self) -> None:
+        if not self.items:
+            return
+        items, self.items = self.items, []
+        R, r_true, code = items[0][9:]
+        arr = (_lib.WgradSite * len(items))(*[
+            _lib.WgradSite(x.data_ptr(), g.data_ptr(), dA.data_ptr(), dy.data_ptr(), ts.data_ptr(), dB.data_ptr(), M, K, N)
+            for x, g, dA, dy, ts, dB, M, K, N, *_ in items])
+        ev0 = _ev() if PROFILE is not None else None
+        _lib.check(_lib.load().sdt_lora_wgrad_batch(ctypes.addressof(arr), len(items), R, r_true, code, _lib.wgrad_workspace(),
+                                                    _lib.stream_ptr()), "sdt_lora_wgrad_batch")
+        if ev0 is not None:
+            PROFILE.append(("wgrad", 0, 0, 0, R, len(items), [(M, K, N) for *_, M, K, N, _R, _rt, _c in items], ev0, _ev()))
+
+
+_wgrad_queue: Optional[_WgradQueue] = None
+
+
+class deferred_wgrad:
+    """``with deferred_wgrad(): loss.backward()`` -- batch the LoRA weight-gradient reductions of the backward pass (see
+    ``_WgradQueue``).  Gradients are complete when the context exits.  Not re-entrant, one backward at a time."""
+
+    def __init__(self, max_sites: Optional[int] = None):
+        self.max_sites = max_sites
+
+    def __enter__(self):
+        global _wgrad_queue
+        if _wgrad_queue is not None:
+            raise SdtError("deferred_wgrad() is not re-entrant")
+        n = self.max_sites or int(_lib.load().sdt_lora_wgrad_max_sites())
+        _wgrad_queue = _WgradQueue(min(n, int(_lib.load().sdt_lora_wgrad_max_sites())))
+        return _wgrad_queue
+
+    def __exit__(self, exc_type, exc, tb):
+        global _wgrad_queue
+        q, _wgrad_queue = _wgrad_queue, None
+        if exc_type is None:
+            q.flush()
+        return False
+
+
 def _site_backward(mod, code, x2, t_save, lora_A, lora_B, dy, need_dx):
     """dX (optional), dA, dB of one site through ``sdt_lora_linear_bwd``.  Returns (dx, dA, dB); dA / dB are None when the
     kernels accumulated straight into the flat gradient arena."""
@@ -150,12 +209,16 @@ def _site_backward(mod, code, x2, t_save, lora_A, lora_B, dy, need_dx):
         wt = mod._weight_t_lp(x2.dtype) if need_dx else None
         g_ws = torch.empty(M, ops.R, dtype=x2.dtype, device=x2.device)
         ev0 = _ev() if PROFILE is not None else None
+        q = _wgrad_queue if direct else None        # only arena gradients may be written after this backward has returned
         _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), _lib.ptr(wt), ops.At_p.data_ptr(),
                                            ops.Bt_p.data_ptr(), t_save.data_ptr(), mod.scaling, _lib.ptr(dx),
-                                           g_ws.data_ptr(), dA.data_ptr(), dB.data_ptr(), M, K, N, ops.R, mod.r,
+                                           g_ws.data_ptr(), None if q is not None else dA.data_ptr(),
+                                           None if q is not None else dB.data_ptr(), M, K, N, ops.R, mod.r,
                                            code, _lib.wgrad_workspace(), st), "sdt_lora_linear_bwd")
         if ev0 is not None:
             PROFILE.append(("bwd", M, K, N, ops.R, 1, need_dx, ev0, _ev()))
+        if q is not None:
+            q.add(x2, g_ws, dA, dy, t_save, dB, M, K, N, ops.R, mod.r, code)
     else:
         g_ws = torch.empty(M, mod.r, dtype=torch.float32, device=x2.device)
         _lib.check(lib.sdt_lora_linear_bwd(dy.data_ptr(), x2.data_ptr(), mod.weight.data_ptr(), lora_A.data_ptr(),
@@ -318,9 +381,11 @@ class _LoRAProjectionGroup(torch.autograd.Function):
                     dB = torch.zeros(N, m.r, dtype=torch.float32, device=x2.device)
                     dAs.append(dA); dBs.append(dB)
                     grads += [dA, dB]
+            q = _wgrad_queue if all(m._grad_A is not None for m in mods) else None
             probs = (_lib.LoraBwdProblem * G)(*[
                 _lib.LoraBwdProblem(dy.data_ptr(), x2.data_ptr(), m._weight_t_lp(x2.dtype).data_ptr() if ctx.need_dx else None,
-                                    o.At_p.data_ptr(), o.Bt_p.data_ptr(), t.data_ptr(), g.data_ptr(), dA.data_ptr(), dB.data_ptr())
+                                    o.At_p.data_ptr(), o.Bt_p.data_ptr(), t.data_ptr(), g.data_ptr(),
+                                    None if q is not None else dA.data_ptr(), None if q is not None else dB.data_ptr())
                 for dy, m, o, t, g, dA, dB in zip(dys, mods, ops, ts, gws, dAs, dBs)])
             ev0 = _ev() if PROFILE is not None else None
             _lib.check(lib.sdt_lora_linear_bwd_group(ctypes.addressof(probs), G, mods[0].scaling, _lib.ptr(dx), M, K, N, R,
@@ -328,6 +393,9 @@ class _LoRAProjectionGroup(torch.autograd.Function):
                        "sdt_lora_linear_bwd_group")
             if ev0 is not None:
                 PROFILE.append(("bwd", M, K, N, R, G, ctx.need_dx, ev0, _ev()))
+            if q is not None:
+                for dy, m, t, g, dA, dB in zip(dys, mods, ts, gws, dAs, dBs):
+                    q.add(x2, g, dA, dy, t, dB, M, K, N, R, m.r, code)
             return (dx, None, *grads)
         dx = None
         grads = []

@@ -22,7 +22,7 @@ from .arena import LoraArena, ParamArena
 from .comm import GradExchange
 from .diffusion import DenoiseLoss, NoiseScheduler
 from .ema import ExponentialMovingAverage
-from .lora import lora_modules
+from .lora import deferred_wgrad, lora_modules
 from .module_config import config_module, freeze_permanently
 from .optim import FlatAdamW
 
@@ -134,6 +134,15 @@ class LatentDiffusionTrainer:
         else:
             self.exchange.all_reduce_mean_(self.arena.grads)
 
+    def _backward(self, loss: torch.Tensor) -> None:
+        """``loss.backward()`` with the LoRA weight-gradient reductions batched: a transformer block's dA / dB go out as one
+        launch instead of one per site (``lora.deferred_wgrad``)."""
+        if isinstance(self.arena, LoraArena):
+            with deferred_wgrad():
+                loss.backward()
+        else:
+            loss.backward()
+
     def optimizer_step(self) -> None:
         self._exchange_gradients()
         if self.unet_ema is not None and self.unet_ema._shadow_flat is not None:
@@ -158,7 +167,7 @@ class LatentDiffusionTrainer:
         loss = self.training_step(batch, self.global_step, noise, timesteps)
         if getattr(self, "_overlap", None) is not None:
             self._overlap.begin()
-        loss.backward()
+        self._backward(loss)
         self.optimizer_step()
         self.global_step += 1
         # detached: a caller that keeps the returned loss must not keep the step's autograd graph alive with it (its
@@ -191,7 +200,7 @@ class LatentDiffusionTrainer:
             loss = self._denoise_loss(self._g_lat, self._g_cond, self._g_noise, self._g_t)
             if getattr(self, "_overlap", None) is not None:
                 self._overlap.begin()
-            loss.backward()
+            self._backward(loss)
             self._exchange_gradients()
             self.optimizer.step(use_device_hyper=True, ema_shadow=self.unet_ema._shadow_flat if fused_ema else None,
                                 ema_one_minus_decay_dev=self._g_omd if fused_ema else None)
@@ -272,7 +281,7 @@ class LatentDiffusionTrainer:
             def body(e=ent):
                 self.optimizer.zero_grad()
                 loss = self._denoise_loss(e["lat"], e["cond"], e["noise"], e["t"])
-                loss.backward()
+                self._backward(loss)
                 return loss.detach()
 
             saved = self._snapshot_train_state()
