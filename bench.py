@@ -224,7 +224,7 @@ def run_cpu_reference(wl: dict, steps: int, warmup: int, sample_batch: int = 1):
                        f"torch CPU (oracle port: loralib/diffusers/lightning are not installable offline)")
 
 
-def run_torch_gpu_reference(wl: dict, device, steps: int = 5, warmup: int = 3):
+def run_torch_gpu_reference(wl: dict, device, steps: int = 5, warmup: int = 3, batches=None):
     """The comparator SURVEY 2.1 / BASELINE.md 5 name: the oracle trainer (fp32 modules, restated loralib layers =
     F.linear + two matmuls + mul + add per site, torch AdamW, per-tensor EMA) as EAGER torch under autocast(bf16) on this
     GPU, same batch as our arm.  None of this repo's kernels run on it (``fused.torch_only``)."""
@@ -237,7 +237,8 @@ def run_torch_gpu_reference(wl: dict, device, steps: int = 5, warmup: int = 3):
     tr = RefTrainer(unet, make_targets(wl), prediction_type=wl["prediction_type"], ema_decay=wl["ema"],
                     prior_preservation=bool(wl.get("bucketed")), prior_loss_weight=wl.get("prior_loss_weight", 1.0))
     B = wl["batch"]
-    batches = [{k: v.to(device) for k, v in b.items()} for b in synthetic_batches(wl, 2, B, 0, pin=False)]
+    if batches is None:
+        batches = [{k: v.to(device) for k, v in b.items()} for b in synthetic_batches(wl, 2, B, 0, pin=False)]
     g = torch.Generator(device=device).manual_seed(SEED)
 
     def one(i):
@@ -267,7 +268,7 @@ def run_torch_gpu_reference(wl: dict, device, steps: int = 5, warmup: int = 3):
     out = {"value": B / (ms * 1e-3), "unit": "latents/s", "ms_per_step": ms, "steps": steps, "loss": float(loss),
            "what": "oracle trainer (restated loralib layers, torch AdamW, per-tensor EMA) as eager torch 2.11 / cuBLAS / cuDNN "
                    "under torch.autocast(bfloat16) on this GPU, fp32 master weights, same batch; no kernel of this repo"}
-    del tr, unet, batches
+    del tr, unet
     torch.cuda.empty_cache()
     return out
 
@@ -643,7 +644,9 @@ def ours_main(args):
     if rank == 0 and world == 1 and not args.no_torch_baseline:
         tr.release_cuda_graph()
         try:
-            torch_gpu = run_torch_gpu_reference(wl, device)
+            # bucketed workload: the same sequence of bucket shapes our timed region saw
+            torch_gpu = run_torch_gpu_reference(wl, device, batches=dev[first_timed:first_timed + 8] if bucketed else None,
+                                                steps=8 if bucketed else 5)
         except Exception as exc:  # noqa: BLE001
             torch_gpu = {"unavailable": f"{type(exc).__name__}: {exc}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

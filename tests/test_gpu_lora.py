@@ -350,8 +350,9 @@ def test_fp16_grouped_qkv_and_autocast(sdt_lib):
 
 def test_batched_weight_gradients_of_mixed_shapes_match_per_site_launches(sdt_lib):
     """``sdt_lora_wgrad_batch``: the dA / dB reductions of a transformer block's worth of sites -- different token counts
-    (32768 image tokens, 616 text tokens), widths and bias-ness, one padded rank -- in ONE launch, bit-identical to the
-    per-site launches (same slices, same order) and equal to the oracle."""
+    (8192 image tokens, 616 text tokens), widths and bias-ness, one padded rank -- in ONE launch: equal to the per-site
+    launches up to f32 summation order (the token range is cut into different slices), bit-reproducible itself, and equal to
+    the oracle."""
     from scal_sdt_b200 import LoraArena, config_module
     from scal_sdt_b200.lora import deferred_wgrad
 
@@ -391,7 +392,12 @@ def test_batched_weight_gradients_of_mixed_shapes_match_per_site_launches(sdt_li
         torch.autograd.backward(ys, [dys[n] for n in xs])
         assert len(q.items) == 5 and float(arena.grads.abs().sum()) == 0.0       # nothing reduced yet
     batched = arena.grads.clone()
-    assert torch.equal(batched, per_site)
+    assert (batched - per_site).norm() <= 1e-5 * per_site.norm()
+    with deferred_wgrad():
+        arena.zero_grad()
+        ys = [getattr(net, n)(xs[n]) for n in xs]
+        torch.autograd.backward(ys, [dys[n] for n in xs])
+    assert torch.equal(arena.grads, batched)                                      # run to run: bit-identical
     for n in xs:
         m = getattr(net, n)
         dA_ref, dB_ref = lora_ref.ref_lora_weight_grads_chunked(xs[n].detach(), m.lora_A, m.lora_B, m.scaling, dys[n])
