@@ -428,6 +428,14 @@ def ours_main(args):
     B = wl["batch"]
     bucketed = bool(wl.get("bucketed"))
 
+    # the NCCL branch computes what DDP computes: the mean over ranks (checked on a known pattern before anything is timed)
+    allreduce_mean_ok = None
+    if world > 1:
+        probe = torch.arange(1 << 16, device=device, dtype=torch.float32) * 0.5 + float(rank + 1)
+        expect = torch.arange(1 << 16, device=device, dtype=torch.float32) * 0.5 + (world + 1) / 2.0
+        exchange.all_reduce_mean_(probe)
+        torch.cuda.synchronize()
+        allreduce_mean_ok = bool(torch.allclose(probe, expect, rtol=1e-6, atol=1e-6))
     tr = build_trainer(wl, device, exchange)
     n_params = sum(p.numel() for p, _, _ in tr.arena.slots)
     n_steps_total = 2 * args.steps + max(args.warmup, 3) + 8
@@ -668,7 +676,7 @@ def ours_main(args):
             "e2e": {"value": e2e_value, "unit": "latents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "final_loss": final_loss, "e2e_last_loss": step_loss,
-            "ranks_in_sync": ranks_in_sync, "allreduce_us": allreduce_us, "step_kernel_us": step_kernel_us,
+            "ranks_in_sync": ranks_in_sync, "allreduce_mean_ok": allreduce_mean_ok, "allreduce_us": allreduce_us, "step_kernel_us": step_kernel_us,
             "roofline": roof, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu,
         }
         if bucketed:
