@@ -54,6 +54,9 @@ SIGNATURES = {
     "sdt_launch_count": (ctypes.c_longlong, []),
     "sdt_lora_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "sdt_lora_linear_geglu_supported": (c_int, [c_int64, c_int64, c_int64, c_int]),
+    "sdt_lora_linear_geglu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                          c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sdt_lora_linear_fwd_group": (c_int, [c_void_p, c_int, c_float, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sdt_lora_linear_bwd_group_supported": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int]),
     "sdt_lora_linear_bwd_group": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,

@@ -448,12 +448,7 @@ lora_pack_kernel(const sdt_pack_site* __restrict__ sites, int f16) {
 // =============================================================================================
 // f2: GEGLU (the activation that follows ff.net.0.proj): out = h * gelu(gate), proj = [h | gate]
 // =============================================================================================
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
+// gelu_erf / gelu_erf_grad: sdt_common.cuh (shared with the GEGLU epilogue of the fused projection)
 
 // proj [M, 2I] bf16 -> out [M, I] bf16; one 16-byte vector (8 elements) of h and of gate per thread per iteration
 __global__ void __launch_bounds__(kThreads)

@@ -44,6 +44,18 @@ extern "C" int sdt_lora_linear_fwd(const void* x, const void* w, const float* bi
   return SDT_ERR_UNSUPPORTED;
 }
 
+extern "C" int sdt_lora_linear_geglu_supported(int64_t M, int64_t K, int64_t I, int r) {
+  return lora_gemm_pair_geglu_supported(M, K, I, r) ? 1 : 0;
+}
+
+extern "C" int sdt_lora_linear_geglu_fwd(const void* x, const void* w, const float* bias, const void* A, const void* B, float scaling,
+                                         void* proj, void* act, void* t_save, int64_t M, int64_t K, int64_t I, int r, int dtype,
+                                         void* stream) {
+  SDT_REQUIRE(dtype == SDT_BF16 || dtype == SDT_F16, SDT_ERR_UNSUPPORTED, "sdt_lora_linear_geglu_fwd: bf16 / fp16 only (there is no fallback)");
+  const LoraProblem pr{x, w, bias, A, B, proj, t_save};
+  return lora_gemm_pair_geglu_bf16(pr, act, scaling, M, K, I, r, dtype == SDT_F16, (cudaStream_t)stream);
+}
+
 static_assert(sizeof(sdt_lora_problem) == sizeof(LoraProblem), "sdt_lora_problem mirrors sdt::LoraProblem");
 
 extern "C" int sdt_lora_linear_fwd_group(const sdt_lora_problem* problems, int n_problems, float scaling, int64_t M, int64_t K,

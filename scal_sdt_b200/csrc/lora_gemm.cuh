@@ -44,4 +44,9 @@ bool lora_gemm_pair_sum_supported(int n_src, int64_t M, int64_t K, int64_t N, in
 int lora_gemm_pair_sum_bf16(const LoraProblem* probs, int n_src, float scaling, int64_t M, int64_t K, int64_t N, int r, bool f16,
                             cudaStream_t st);
 
+// GEGLU epilogue (ff.net.0.proj): see lora_gemm2.cu
+bool lora_gemm_pair_geglu_supported(int64_t M, int64_t K, int64_t I, int r);
+int lora_gemm_pair_geglu_bf16(const LoraProblem& pr, void* act_out, float scaling, int64_t M, int64_t K, int64_t I, int r, bool f16,
+                              cudaStream_t st);
+
 }  // namespace sdt

@@ -145,6 +145,10 @@ struct PairParams {
   int has_bias;
   int f16;                // operands / outputs are IEEE fp16 instead of bf16
   int n_tiles, n_groups, group_size, n_items;   // items are (256-row tile, problem, n-group)
+  // GEGLU epilogue (ff.net.0.proj): N = 2 I, tile nt holds h columns [nt HN, (nt+1) HN) and the matching gate columns
+  // I + [nt HN, (nt+1) HN); besides proj (y, for the backward) the epilogue writes act = h * gelu(gate) [M, I]
+  int geglu_I;
+  uint8_t* act_out;
   long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
 };
 
@@ -167,11 +171,12 @@ __device__ __forceinline__ PairItem decode_pair_item(int item, const PairParams&
   return c;
 }
 
-template <int BN, int R, int G, int S>
+template <int BN, int R, int G, int S, bool GEGLU = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams p) {
   using C = PairCfg<BN, R, S>;
   static_assert(S == 1 || (G >= S && R > 0), "summed sources live in the entries of the group");
+  static_assert(!GEGLU || (G == 1 && S == 1 && R > 0 && C::STG_BLOCKS >= 2 && C::HN % 8 == 0), "GEGLU epilogue: one merged problem, <= 160-wide tiles");
   constexpr bool kMerged = S == 1;             // first tile of an item: base GEMM and rank projection as one UMMA
   const int n_src = S == 1 ? 1 : p.n_src;
   extern __shared__ uint8_t smem_raw[];
@@ -265,7 +270,9 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
-          const int n0 = nt * C::BN + (int)rank * C::HN;
+          // rows of W / lora-up this CTA contributes to the tile.  cta_group::2 runs the N index over CTA 0's rows, then CTA 1's:
+          // for GEGLU CTA 0 brings the h rows and CTA 1 the gate rows of the same output columns -- no permuted weight copy
+          const int n0 = GEGLU ? nt * C::HN + (int)rank * p.geglu_I : nt * C::BN + (int)rank * C::HN;
           const uint32_t tx = 2u * (C::X_BYTES + C::W_BYTES + (first ? C::HR * C::BK * 2 : 0));
           for (int src = 0; src < n_src; ++src) {
             const int q = S > 1 ? src : ic.prob;          // operand set: the source, or the problem of a grouped launch
@@ -418,7 +425,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           const bool first = (nt == nt0) && R > 0;
           if (has_bias) {
             if (tile_ctr > 0) mbar_wait(lb_empty, (tile_ctr - 1) & 1);
-            const int n0 = nt * C::BN + (int)rank * C::HN;
+            const int n0 = GEGLU ? nt * C::HN + (int)rank * p.geglu_I : nt * C::BN + (int)rank * C::HN;
             for (int n = tid; n < C::HN; n += 128) {
               const float b = (n0 + n < p.N) ? __ldg(bias + n0 + n) : 0.f;
               const float hi = round_act(b, f16);
@@ -491,7 +498,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
         if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(48 + 2 * tile_ctr);
         tc_fence_after();
-        const int n_sub = min(C::BN / 32, (p.N - n0 + 31) / 32);
+        const int n_sub = GEGLU ? C::BN / 32 : min(C::BN / 32, (p.N - n0 + 31) / 32);      // GEGLU: I % HN == 0, tiles are full
         uint32_t v[32];
         // 32 output columns of this tile -> registers: one TMEM load, or two 16-column loads where the block straddles the gap of
         // a merged first tile (HN is a multiple of 16, so a half never straddles it)
@@ -525,10 +532,62 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           __syncwarp();
           if (lane == 0) remote_arrive_relaxed(acc_empty_leader[buf]);
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(49 + 2 * tile_ctr);
-          // Phase 2: stream the staged blocks out (full 128-byte lines); the next tile's phase 1 follows in program order
-          slot = 0;
-          for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot)
-            write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * min(2, n_sub - 2 * cb));
+          if constexpr (GEGLU) {
+            // act = h * gelu(gate) from the STAGED (already rounded) halves of the tile, exactly what the unfused sequence computes
+            // from proj in HBM.  h and gate of one output column sit in different 64-column blocks, i.e. in the staging of both
+            // epilogue warps of this lane quarter: pair barrier, then each warp takes 16 of the quarter's 32 rows.
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+            {
+              const uint32_t stg_q = smem_u32(stg_smem) + (uint32_t)(e & 3) * (C::STG_BLOCKS * 4096);     // half 0's staging of this quarter
+              constexpr int kSlots = C::HN / 8;                                      // 16-byte slots per output row (80 columns: 10)
+              auto staged = [&](int r, int tile_col) -> uint4 {
+                const int cb = tile_col >> 6, sl = (tile_col & 63) >> 3;
+                const uint32_t owner = (uint32_t)((cb + tile_ctr) & 1);               // which half staged block cb of this tile
+                const uint32_t base = stg_q + owner * (4u * C::STG_BLOCKS * 4096u) + (uint32_t)(cb >> 1) * 4096u;
+                return ld_shared_v4(base + r * 128 + ((sl ^ (r & 7)) << 4));
+              };
+              uint8_t* act = p.act_out;
+              for (int task = lane; task < 16 * kSlots; task += 32) {
+                const int r = half * 16 + task / kSlots, so = task % kSlots;
+                const int grow = m0 + q * 32 + r;
+                const uint4 hv = staged(r, 8 * so), gv = staged(r, C::HN + 8 * so);
+                const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float h0, h1, g0, g1;
+                  if (f16) {
+                    const float2 hh = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+                    const float2 gg = __half22float2(*reinterpret_cast<const __half2*>(&gw[j]));
+                    h0 = hh.x; h1 = hh.y; g0 = gg.x; g1 = gg.y;
+                  } else {
+                    h0 = bf16_bits_to_f32(hw[j] & 0xffffu); h1 = bf16_bits_to_f32(hw[j] >> 16);
+                    g0 = bf16_bits_to_f32(gw[j] & 0xffffu); g1 = bf16_bits_to_f32(gw[j] >> 16);
+                  }
+                  ow[j] = pack_act2(h0 * gelu_erf(g0), h1 * gelu_erf(g1), f16);
+                }
+                if (grow < p.M)
+                  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(act + ((size_t)grow * p.geglu_I + nt * C::HN + 8 * so) * 2),
+                               "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3])
+                               : "memory");
+              }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");      // the partner has read my staging: it may be rewritten
+            // proj (kept for the backward) in its reference layout [h | gate]: tile columns >= HN land I - HN columns further right
+            slot = 0;
+            for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot) {
+              const int tc0 = cb * 64;
+              int col0 = nt * C::HN + tc0, split_slot = 8, shift = 0;
+              if (tc0 >= C::HN) col0 += p.geglu_I - C::HN;
+              else if (tc0 + 64 > C::HN) { split_slot = (C::HN - tc0) / 8; shift = p.geglu_I - C::HN; }
+              write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, col0, p.N, 4 * min(2, n_sub - 2 * cb), split_slot, shift);
+            }
+          } else {
+            // Phase 2: stream the staged blocks out (full 128-byte lines); the next tile's phase 1 follows in program order
+            slot = 0;
+            for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot)
+              write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * min(2, n_sub - 2 * cb));
+          }
           __syncwarp();
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(70 + tile_ctr);
         } else {
@@ -583,12 +642,13 @@ static void choose_groups_pair(int m_tiles, int n_tiles, int BN, int R, int pair
 }
 
 // n_probs problems as independent work items (S == 1), or n_probs SOURCES summed into probs[0].y (S > 1)
-template <int BN, int R, int G, int S>
-static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, bool f16, cudaStream_t st) {
+template <int BN, int R, int G, int S, bool GEGLU = false>
+static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, bool f16, cudaStream_t st,
+                       void* act_out = nullptr) {
   using C = PairCfg<BN, R, S>;
   static bool attr_set = false;
   if (!attr_set) {
-    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R, G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R, G, S, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   GemmGroup<G> gm;
@@ -596,7 +656,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
     const LoraProblem& pr = probs[q < n_probs ? q : 0];
     int rc = make_tmap_2d_bf16(&gm.x[q], pr.x, M, K, K * 2, C::BM, C::BK, TMAP_SW_128);
     if (rc != SDT_OK) return rc;
-    rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);
+    rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);     // GEGLU: same map, rows addressed per CTA
     if (rc != SDT_OK) return rc;
     gm.y[q] = reinterpret_cast<uint8_t*>(S > 1 ? probs[0].y : pr.y);
     if (R > 0) {
@@ -618,6 +678,8 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
   p.n_src = S > 1 ? n_probs : 1;
   p.has_bias = probs[0].bias != nullptr ? 1 : 0;
   p.f16 = f16 ? 1 : 0;
+  p.geglu_I = GEGLU ? (int)(N / 2) : 0;
+  p.act_out = reinterpret_cast<uint8_t*>(act_out);
   p.trace = reinterpret_cast<long long*>(debug_get(10));
   const int m_tiles = (int)((M + 2 * C::BM - 1) / (2 * C::BM));
   p.n_tiles = (int)((N + BN - 1) / BN);
@@ -635,7 +697,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
   }
   p.n_items = m_tiles * p.n_probs * p.n_groups;
   const int pairs = p.n_items < pairs_max ? p.n_items : pairs_max;
-  SDT_CUDA_OK(launch_kernel(lora_gemm_pair_kernel<BN, R, G, S>, dim3(2 * pairs), dim3(kPairThreads), C::SMEM_BYTES, st, true, gm, p));
+  SDT_CUDA_OK(launch_kernel(lora_gemm_pair_kernel<BN, R, G, S, GEGLU>, dim3(2 * pairs), dim3(kPairThreads), C::SMEM_BYTES, st, true, gm, p));
   SDT_LAUNCH_OK("lora_gemm_pair");
   return SDT_OK;
 }
@@ -663,6 +725,27 @@ int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scali
   if (bn160) { SDT_PAIR_R(160, kMaxGroup) } else { SDT_PAIR_R(128, kMaxGroup) }
 #undef SDT_PAIR_R
 #undef SDT_PAIR
+}
+
+// GEGLU epilogue (ff.net.0.proj): proj [M, 2I] = X W^T + b + s (X A^T) B^T  AND  act [M, I] = proj[:, :I] * gelu(proj[:, I:]) from ONE
+// launch.  Tile nt holds the h columns [80 nt, 80 nt + 80) and the matching gate columns (CTA 0 of the pair brings the h rows of W /
+// lora-up / bias, CTA 1 the gate rows), so the activation is formed from the staged tile and the separate GEGLU pass over
+// proj -- read 2I, write I per token -- disappears; proj is still written (the backward needs it), in its reference layout.
+bool lora_gemm_pair_geglu_supported(int64_t M, int64_t K, int64_t I, int r) {
+  return (r == 16 || r == 32 || r == 64) && M >= 256 && K >= 64 && K % 8 == 0 && I % 80 == 0 && I >= 80;
+}
+int lora_gemm_pair_geglu_bf16(const LoraProblem& pr, void* act_out, float scaling, int64_t M, int64_t K, int64_t I, int r, bool f16,
+                              cudaStream_t st) {
+  SDT_REQUIRE(lora_gemm_pair_geglu_supported(M, K, I, r), SDT_ERR_UNSUPPORTED,
+              "lora_gemm(geglu): needs padded rank 16/32/64, M >= 256, I %% 80 == 0 (got r=%d M=%lld I=%lld)", r, (long long)M, (long long)I);
+  SDT_REQUIRE(pr.x && pr.w && pr.la && pr.lb && pr.y && pr.t_out && act_out, SDT_ERR_ARG, "lora_gemm(geglu): null pointer");
+  SDT_REQUIRE(aligned16(pr.x) && aligned16(pr.w) && aligned16(pr.la) && aligned16(pr.lb) && aligned16(pr.y) && aligned16(pr.t_out) &&
+                  aligned16(act_out), SDT_ERR_ARG, "lora_gemm(geglu): pointers must be 16-byte aligned");
+  switch (r) {
+    case 16: return launch_pair<160, 16, 1, 1, true>(&pr, 1, scaling, M, K, 2 * I, f16, st, act_out);
+    case 32: return launch_pair<160, 32, 1, 1, true>(&pr, 1, scaling, M, K, 2 * I, f16, st, act_out);
+    default: return launch_pair<160, 64, 1, 1, true>(&pr, 1, scaling, M, K, 2 * I, f16, st, act_out);
+  }
 }
 
 // Summed sources: Y = sum_s X_s W_s^T + (scaling X_s la_s^T) lb_s^T  with T_s = scaling X_s la_s^T written to probs[s].t_out.

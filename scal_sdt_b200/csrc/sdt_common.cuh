@@ -115,6 +115,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // round an f32 to the nearest bf16 value, result as f32 (what torch does after every bf16 op)
 __device__ __forceinline__ float round_bf16(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
+// exact (erf) GELU as torch.nn.functional.gelu evaluates it, and its derivative
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
 // ---- 16-bit activation format of the tensor-core path: bf16 (default) or IEEE fp16 (the reference's stock
 // `trainer.precision: 16`).  A launch-uniform flag selects it; the tensor core takes the format from the instruction descriptor.
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {

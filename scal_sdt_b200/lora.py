@@ -230,6 +230,74 @@ def _site_backward(mod, code, x2, t_save, lora_A, lora_B, dy, need_dx):
     return dx, dA, dB
 
 
+class _LoRAGegluProjection(torch.autograd.Function):
+    """``h, gate = proj(x).chunk(2, -1); h * gelu(gate)`` with ``proj`` a LoRA site (diffusers ``GEGLU`` under
+    ``configs/optim_targets/lora.yaml:23-27``) as ONE launch: the activation is formed in the GEMM's epilogue
+    (``sdt_lora_linear_geglu_fwd``).  ``proj`` is still written -- the backward needs it -- and the backward is the GEGLU
+    gradient kernel followed by the site's usual dX / dA / dB."""
+
+    @staticmethod
+    def forward(ctx, x2, lora_A, lora_B, mod):
+        lib = _lib.load()
+        M, K = x2.shape
+        N = mod.out_features
+        I = N // 2
+        code = _lib.dtype_code(x2.dtype)
+        ops = mod._packed_operands(x2.dtype)
+        proj = torch.empty(M, N, dtype=x2.dtype, device=x2.device)
+        act = torch.empty(M, I, dtype=x2.dtype, device=x2.device)
+        t_save = torch.empty(M, ops.R, dtype=x2.dtype, device=x2.device)
+        ev0 = _ev() if PROFILE is not None else None
+        _lib.check(lib.sdt_lora_linear_geglu_fwd(x2.data_ptr(), mod._weight_lp(x2.dtype).data_ptr(), _lib.ptr(mod._bias_f32()),
+                                                 ops.A_p.data_ptr(), ops.B_p.data_ptr(), mod.scaling, proj.data_ptr(), act.data_ptr(),
+                                                 t_save.data_ptr(), M, K, I, ops.R, code, _lib.stream_ptr()),
+                   "sdt_lora_linear_geglu_fwd")
+        if ev0 is not None:
+            PROFILE.append(("fwd", M, K, N, ops.R, 1, ev0, _ev()))
+        ctx.mod, ctx.code = mod, code
+        ctx.need_dx = x2.requires_grad
+        ctx.save_for_backward(x2, t_save, proj, lora_A, lora_B)
+        return act
+
+    @staticmethod
+    def backward(ctx, dact):
+        x2, t_save, proj, lora_A, lora_B = ctx.saved_tensors
+        M, N = proj.shape
+        d2 = dact.contiguous()
+        if d2.dtype != proj.dtype:
+            d2 = d2.to(proj.dtype)
+        dproj = torch.empty_like(proj)
+        _lib.check(_lib.load().sdt_geglu(proj.data_ptr(), d2.data_ptr(), dproj.data_ptr(), M, N // 2, 1, ctx.code, _lib.stream_ptr()),
+                   "sdt_geglu")
+        dx, dA, dB = _site_backward(ctx.mod, ctx.code, x2, t_save, lora_A, lora_B, dproj, ctx.need_dx)
+        return dx, dA, dB, None
+
+
+def geglu_projection_supported(mod, x: torch.Tensor) -> bool:
+    """True when ``h * gelu(gate)`` of ``mod(x)`` can come out of the projection's own epilogue."""
+    if not isinstance(mod, LoRALinear) or not x.is_cuda or x.numel() == 0 or mod.out_features % 2 != 0:
+        return False
+    if mod.training and mod.lora_dropout_p > 0.0:
+        return False
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+    if dt != torch.bfloat16:                   # the GEGLU gradient kernel is bf16 / fp32
+        return False
+    M = x.numel() // x.shape[-1]
+    return bool(_lib.load().sdt_lora_linear_geglu_supported(M, mod.in_features, mod.out_features // 2, padded_rank(mod.r)))
+
+
+def geglu_projection(mod, x: torch.Tensor) -> torch.Tensor:
+    """``h * gelu(gate)`` for ``[h | gate] = mod(x)`` -- one fused launch (``geglu_projection_supported`` says when)."""
+    _lib.require_cuda(x, mod.weight, mod.lora_A)
+    _lib.device_check()
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, mod.in_features)
+    if x2.dtype != torch.bfloat16:
+        x2 = x2.to(torch.bfloat16)
+    act = _LoRAGegluProjection.apply(x2.contiguous(), mod.lora_A, mod.lora_B, mod)
+    return act.view(*lead, mod.out_features // 2)
+
+
 # ---- dropout on the rank path (loralib: ``(dropout(x) @ A.T @ B.T) * scaling``) -------------------------------------------------
 _dropout_seed: dict = {}
 _dropout_sites = 0

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .fused import add_layer_norm, fused_enabled, geglu, geglu_supported, group_norm_act, residual_bias_add
-from .lora import project_group
+from .lora import geglu_projection, geglu_projection_supported, project_group
 
 
 @dataclass
@@ -154,8 +154,10 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim, inner * 2)
 
     def forward(self, x):
+        if fused_enabled() and geglu_projection_supported(self.proj, x):
+            return geglu_projection(self.proj, x)      # the activation comes out of the projection's epilogue
         y = self.proj(x)
-        if geglu_supported(y):                 # one vectorised pass per direction (SURVEY 8 f2)
+        if geglu_supported(y):                 # one vectorised pass per direction
             return geglu(y)
         h, gate = y.chunk(2, dim=-1)           # host model on the CPU (oracle / reference arm)
         return h * F.gelu(gate)

@@ -402,3 +402,37 @@ def test_batched_weight_gradients_of_mixed_shapes_match_per_site_launches(sdt_li
         m = getattr(net, n)
         dA_ref, dB_ref = lora_ref.ref_lora_weight_grads_chunked(xs[n].detach(), m.lora_A, m.lora_B, m.scaling, dys[n])
         assert rel(m.lora_A.grad, dA_ref) <= 2e-2 and rel(m.lora_B.grad, dB_ref) <= 2e-2, n
+
+
+GEGLU_CASES = [(32768, 320, 1280, 16), (8192, 640, 2560, 16), (2048, 1280, 5120, 16), (1000, 640, 2560, 64), (300, 320, 1280, 4)]
+
+
+@pytest.mark.parametrize("M,K,I,rank", GEGLU_CASES, ids=[f"{m}x{k}x2*{i}-r{r}" for m, k, i, r in GEGLU_CASES])
+def test_geglu_epilogue_equals_projection_then_geglu(sdt_lib, M, K, I, rank):
+    """ff.net.0.proj with the GEGLU activation formed in the GEMM's epilogue: bit-identical to the projection
+    launch followed by the GEGLU kernel (same rounded proj values go into the same arithmetic), equal to the fp64 oracle
+    ``h * gelu(gate)`` of the reference expression within the bf16 bound, same gradients."""
+    from scal_sdt_b200.fused import geglu
+    from scal_sdt_b200.lora import geglu_projection, geglu_projection_supported
+    ref, ours = make_pair("linear", K, 2 * I, rank, rank, True, 5, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(M + I)
+    x = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    dact = torch.randn(M, I, device=DEV, generator=g).bfloat16()
+    assert geglu_projection_supported(ours, x)
+    xa = x.clone().requires_grad_(True)
+    act = geglu_projection(ours, xa)
+    act.backward(dact)
+    gA, gB, gx = ours.lora_A.grad.clone(), ours.lora_B.grad.clone(), xa.grad.clone()
+    ours.lora_A.grad = ours.lora_B.grad = None
+    xb = x.clone().requires_grad_(True)
+    act2 = geglu(ours(xb))
+    act2.backward(dact)
+    assert torch.equal(act, act2)                                            # fused epilogue == two launches, to the bit
+    assert torch.equal(gx, xb.grad) and torch.equal(gA, ours.lora_A.grad) and torch.equal(gB, ours.lora_B.grad)
+    # oracle on a row sample (all columns): the reference expression in fp64
+    rows = torch.randperm(M, generator=torch.Generator().manual_seed(1))[:384]
+    xr = x[rows.to(DEV)].double().cpu()
+    proj = ref(xr)
+    h, gate = proj.chunk(2, dim=-1)
+    act_ref = h * torch.nn.functional.gelu(gate)
+    assert rel(act[rows.to(DEV)], act_ref) <= 2e-2, rel(act[rows.to(DEV)], act_ref)
