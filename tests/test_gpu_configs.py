@@ -12,6 +12,7 @@ from oracle.ref_trainer import RefTrainer
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
+_LAST_FROZEN = None
 
 
 def _pair(cfg, targets, dtype, **kw):
@@ -24,6 +25,8 @@ def _pair(cfg, targets, dtype, **kw):
         with torch.no_grad():
             for p in unet_cpu.parameters():
                 p.copy_(p.bfloat16().float())
+    global _LAST_FROZEN
+    _LAST_FROZEN = copy.deepcopy(unet_cpu)
     unet_gpu = copy.deepcopy(unet_cpu).to(DEV).to(dtype)
     if dtype == torch.bfloat16:
         unet_gpu = unet_gpu.to(memory_format=torch.channels_last)
@@ -53,6 +56,35 @@ def _sync_lora(ref, ours, seed=5):
     return refm
 
 
+def _torch_autocast_grad_rel(unet_frozen, targets, refm, sites, batch, noise, t, **ref_kw):
+    """The reference's own mode on this GPU (fp32 modules under autocast(bf16), eager torch, oracle LoRA layers, none of this
+    repo's kernels) against the same fp32 CPU oracle gradients: the yardstick for the whole-network bf16 error."""
+    from scal_sdt_b200 import fused
+    tg = RefTrainer(copy.deepcopy(unet_frozen).to(DEV), copy.deepcopy(targets), **ref_kw)
+    tm = dict(tg.unet.named_modules())
+    with torch.no_grad():
+        for name, _m in sites:
+            tm[name].lora_A.copy_(refm[name].lora_A); tm[name].lora_B.copy_(refm[name].lora_B)
+    with fused.torch_only():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = tg.training_step({k: v.to(DEV) for k, v in batch.items()}, noise.to(DEV), t.to(DEV))
+        loss.backward()
+    num = den = 0.0
+    for name, _m in sites:
+        for pn in ("lora_A", "lora_B"):
+            go, gr = getattr(tm[name], pn).grad.float().cpu(), getattr(refm[name], pn).grad
+            num += (go - gr).pow(2).sum().item()
+            den += gr.pow(2).sum().item()
+    return (num / den) ** 0.5
+
+
+def _whole_network_bound(e_ours, e_torch):
+    """north_star's 2e-2 holds per site (test_gpu_lora / test_gpu_fullsize) and at SD1.5 width for the whole network
+    (test_gpu_sd15_step); at toy widths the bf16 host model around the sites dominates, for the reference's own bf16 path too,
+    so the bound is: not less accurate than that path."""
+    return e_ours <= max(2e-2, 1.25 * e_torch)
+
+
 def _grad_rel(ours, refm):
     num = den = 0.0
     for name, m in ours.arena.sites:
@@ -79,7 +111,8 @@ def test_cfg3_rank64_attention_ff_with_ema(sdt_lib):
     lr_ = ref.training_step({"latents": lat, "conds": cond}, noise, t)
     lr_.backward()
     assert abs(lo.item() - lr_.item()) <= 2e-2 * abs(lr_.item())
-    assert _grad_rel(ours, refm) <= 5e-2
+    e_torch = _torch_autocast_grad_rel(_LAST_FROZEN, targets, refm, ours.arena.sites, {"latents": lat, "conds": cond}, noise, t)
+    assert _whole_network_bound(_grad_rel(ours, refm), e_torch), (_grad_rel(ours, refm), e_torch)
     # optimizer + EMA step: bias-corrected first AdamW step moves every element by ~lr; compare against torch AdamW + RefEMA
     for name, m in ours.arena.sites:           # feed the oracle's exact gradients so that only the update rule is compared
         m.lora_A.grad.copy_(refm[name].lora_A.grad.to(DEV)); m.lora_B.grad.copy_(refm[name].lora_B.grad.to(DEV))
@@ -128,7 +161,9 @@ def test_cfg4_bucketed_mixed_resolution_prior_preservation(sdt_lib):
         lr_ = ref.training_step({"latents": lat, "conds": cond}, noise, t)
         lr_.backward()
         assert abs(lo.item() - lr_.item()) <= 2e-2 * abs(lr_.item()), (w, h)
-        assert _grad_rel(ours, refm) <= 5e-2, (w, h)
+        e_torch = _torch_autocast_grad_rel(_LAST_FROZEN, lora_unet_targets(rank=16, alpha=16), refm, ours.arena.sites,
+                                           {"latents": lat, "conds": cond}, noise, t, prior_preservation=True, prior_loss_weight=0.7)
+        assert _whole_network_bound(_grad_rel(ours, refm), e_torch), (w, h, _grad_rel(ours, refm), e_torch)
     assert len(seen) >= 2
 
 
