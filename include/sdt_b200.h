@@ -79,8 +79,8 @@ int sdt_lora_linear_fwd_group(const sdt_lora_problem* problems /* host */, int n
  * (configs/optim_targets/lora.yaml:23-27).  w [2I,K], bias [2I], B [2I,r] in their reference row order ([h rows ; gate rows]).
  *     proj [M,2I] = x W^T + bias + scaling (x A^T) B^T          (written: the backward needs it; reference column order)
  *     act  [M,I]  = proj[:, :I] * gelu(proj[:, I:])             (erf GELU, evaluated on the rounded proj values)
- * A 256 x 160 tile holds 80 h columns and the 80 matching gate columns (the two CTAs of a pair bring the two row blocks), so the
- * activation is formed in the epilogue and the separate pass over proj disappears.  Needs M >= 256, I % 80 == 0, padded rank
+ * A 256 x 128 tile holds 64 h columns and the 64 matching gate columns (the two CTAs of a pair bring the two row blocks), so the
+ * activation is formed in the epilogue and the separate pass over proj disappears.  Needs M >= 256, I % 64 == 0, padded rank
  * 16/32/64 (sdt_lora_linear_geglu_supported); otherwise call sdt_lora_linear_fwd and sdt_geglu.  SDT_BF16 / SDT_F16.
  */
 int sdt_lora_linear_geglu_supported(int64_t M, int64_t K, int64_t I, int r);

@@ -533,20 +533,22 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           if (lane == 0) remote_arrive_relaxed(acc_empty_leader[buf]);
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(49 + 2 * tile_ctr);
           if constexpr (GEGLU) {
-            // act = h * gelu(gate) from the STAGED (already rounded) halves of the tile, exactly what the unfused sequence computes
-            // from proj in HBM.  h and gate of one output column sit in different 64-column blocks, i.e. in the staging of both
-            // epilogue warps of this lane quarter: pair barrier, then each warp takes 16 of the quarter's 32 rows.
+            // Phase 2 (GEGLU): act = h * gelu(gate) from the STAGED (already rounded) halves of the tile -- exactly what the unfused
+            // sequence computes from proj in HBM.  h and gate of one output column sit in different 64-column blocks, i.e. in the
+            // staging of both epilogue warps of this lane quarter: pair barrier, then each warp takes 16 of the quarter's 32 rows
+            // and writes, per row, three full 128-byte lines: h and gate into proj (reference column order [h | gate], kept for the
+            // backward) and act.  Lanes walk the 16-byte slots of a row: a store instruction covers four full lines.
             asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+            if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(80 + tile_ctr);
             {
               const uint32_t stg_q = smem_u32(stg_smem) + (uint32_t)(e & 3) * (C::STG_BLOCKS * 4096);     // half 0's staging of this quarter
-              constexpr int kSlots = C::HN / 8;                                      // 16-byte slots per output row (80 columns: 10)
+              constexpr int kSlots = C::HN / 8;                                      // 16-byte slots per output row (64 columns: 8)
               auto staged = [&](int r, int tile_col) -> uint4 {
                 const int cb = tile_col >> 6, sl = (tile_col & 63) >> 3;
                 const uint32_t owner = (uint32_t)((cb + tile_ctr) & 1);               // which half staged block cb of this tile
                 const uint32_t base = stg_q + owner * (4u * C::STG_BLOCKS * 4096u) + (uint32_t)(cb >> 1) * 4096u;
                 return ld_shared_v4(base + r * 128 + ((sl ^ (r & 7)) << 4));
               };
-              uint8_t* act = p.act_out;
               for (int task = lane; task < 16 * kSlots; task += 32) {
                 const int r = half * 16 + task / kSlots, so = task % kSlots;
                 const int grow = m0 + q * 32 + r;
@@ -566,22 +568,20 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
                   }
                   ow[j] = pack_act2(h0 * gelu_erf(g0), h1 * gelu_erf(g1), f16);
                 }
-                if (grow < p.M)
-                  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(act + ((size_t)grow * p.geglu_I + nt * C::HN + 8 * so) * 2),
+                if (grow < p.M) {
+                  uint8_t* prow = yp + ((size_t)grow * p.N + nt * C::HN + 8 * so) * 2;
+                  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(prow), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
+                  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(prow + (size_t)p.geglu_I * 2), "r"(gv.x), "r"(gv.y), "r"(gv.z),
+                               "r"(gv.w)
+                               : "memory");
+                  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p.act_out + ((size_t)grow * p.geglu_I + nt * C::HN + 8 * so) * 2),
                                "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3])
                                : "memory");
+                }
               }
             }
+            if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(90 + tile_ctr);
             asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");      // the partner has read my staging: it may be rewritten
-            // proj (kept for the backward) in its reference layout [h | gate]: tile columns >= HN land I - HN columns further right
-            slot = 0;
-            for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot) {
-              const int tc0 = cb * 64;
-              int col0 = nt * C::HN + tc0, split_slot = 8, shift = 0;
-              if (tc0 >= C::HN) col0 += p.geglu_I - C::HN;
-              else if (tc0 + 64 > C::HN) { split_slot = (C::HN - tc0) / 8; shift = p.geglu_I - C::HN; }
-              write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, col0, p.N, 4 * min(2, n_sub - 2 * cb), split_slot, shift);
-            }
           } else {
             // Phase 2: stream the staged blocks out (full 128-byte lines); the next tile's phase 1 follows in program order
             slot = 0;
@@ -728,23 +728,25 @@ int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scali
 }
 
 // GEGLU epilogue (ff.net.0.proj): proj [M, 2I] = X W^T + b + s (X A^T) B^T  AND  act [M, I] = proj[:, :I] * gelu(proj[:, I:]) from ONE
-// launch.  Tile nt holds the h columns [80 nt, 80 nt + 80) and the matching gate columns (CTA 0 of the pair brings the h rows of W /
-// lora-up / bias, CTA 1 the gate rows), so the activation is formed from the staged tile and the separate GEGLU pass over
-// proj -- read 2I, write I per token -- disappears; proj is still written (the backward needs it), in its reference layout.
+// launch.  Tile nt (256 x 128) holds the h columns [64 nt, 64 nt + 64) and the matching gate columns (CTA 0 of the pair brings the
+// h rows of W / lora-up / bias, CTA 1 the gate rows), so the activation is formed from the staged tile and the separate GEGLU
+// pass over proj -- read 2I, write I per token -- disappears; proj is still written (the backward needs it), in its reference
+// layout.  64 columns = 128 bytes: h, gate and act of a row are each ONE full line (with 80-column halves -- 160-byte runs -- the
+// stores ran at half rate: 148 us instead of 60 + 45 for the K = 320 projection, measured).
 bool lora_gemm_pair_geglu_supported(int64_t M, int64_t K, int64_t I, int r) {
-  return (r == 16 || r == 32 || r == 64) && M >= 256 && K >= 64 && K % 8 == 0 && I % 80 == 0 && I >= 80;
+  return (r == 16 || r == 32 || r == 64) && M >= 256 && K >= 64 && K % 8 == 0 && I % 64 == 0 && I >= 64;
 }
 int lora_gemm_pair_geglu_bf16(const LoraProblem& pr, void* act_out, float scaling, int64_t M, int64_t K, int64_t I, int r, bool f16,
                               cudaStream_t st) {
   SDT_REQUIRE(lora_gemm_pair_geglu_supported(M, K, I, r), SDT_ERR_UNSUPPORTED,
-              "lora_gemm(geglu): needs padded rank 16/32/64, M >= 256, I %% 80 == 0 (got r=%d M=%lld I=%lld)", r, (long long)M, (long long)I);
+              "lora_gemm(geglu): needs padded rank 16/32/64, M >= 256, I %% 64 == 0 (got r=%d M=%lld I=%lld)", r, (long long)M, (long long)I);
   SDT_REQUIRE(pr.x && pr.w && pr.la && pr.lb && pr.y && pr.t_out && act_out, SDT_ERR_ARG, "lora_gemm(geglu): null pointer");
   SDT_REQUIRE(aligned16(pr.x) && aligned16(pr.w) && aligned16(pr.la) && aligned16(pr.lb) && aligned16(pr.y) && aligned16(pr.t_out) &&
                   aligned16(act_out), SDT_ERR_ARG, "lora_gemm(geglu): pointers must be 16-byte aligned");
   switch (r) {
-    case 16: return launch_pair<160, 16, 1, 1, true>(&pr, 1, scaling, M, K, 2 * I, f16, st, act_out);
-    case 32: return launch_pair<160, 32, 1, 1, true>(&pr, 1, scaling, M, K, 2 * I, f16, st, act_out);
-    default: return launch_pair<160, 64, 1, 1, true>(&pr, 1, scaling, M, K, 2 * I, f16, st, act_out);
+    case 16: return launch_pair<128, 16, 1, 1, true>(&pr, 1, scaling, M, K, 2 * I, f16, st, act_out);
+    case 32: return launch_pair<128, 32, 1, 1, true>(&pr, 1, scaling, M, K, 2 * I, f16, st, act_out);
+    default: return launch_pair<128, 64, 1, 1, true>(&pr, 1, scaling, M, K, 2 * I, f16, st, act_out);
   }
 }
 

@@ -179,20 +179,16 @@ __device__ __forceinline__ void stage_row_chunk(uint32_t stg, int lane, int h, c
   for (int j = 0; j < 4; ++j) st_shared_v4(row_base + (((4 * h + j) ^ (lane & 7)) << 4), pk + 4 * j);
 }
 // write the staged block out: rows [row0, row0 + 32) x 16-byte slots [0, n_slots) starting at column col0 of a row-major
-// bf16 matrix with N columns (N % 8 == 0); rows >= M and columns >= N are clipped.  split_slot / split_shift: slots from
-// split_slot on land split_shift columns further right (the GEGLU tile: [h | gate] halves of one tile go to column ranges that
-// are I columns apart); the defaults leave the block contiguous.
-__device__ __forceinline__ void write_staged_block(uint32_t stg, int lane, uint8_t* y, int row0, int M, int col0, int N, int n_slots,
-                                                   int split_slot = 8, int split_shift = 0) {
+// bf16 matrix with N columns (N % 8 == 0); rows >= M and columns >= N are clipped
+__device__ __forceinline__ void write_staged_block(uint32_t stg, int lane, uint8_t* y, int row0, int M, int col0, int N, int n_slots) {
   const int c = lane & 7;
-  const int col = col0 + 8 * c + (c >= split_slot ? split_shift : 0);
-  const bool col_ok = c < n_slots && col < N;
+  const bool col_ok = c < n_slots && col0 + 8 * c < N;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rl = 4 * i + (lane >> 3);
     if (col_ok && row0 + rl < M) {
       const uint4 v = ld_shared_v4(stg + rl * 128 + ((c ^ (rl & 7)) << 4));
-      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(y + ((size_t)(row0 + rl) * N + col) * 2), "r"(v.x),
+      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(y + ((size_t)(row0 + rl) * N + col0 + 8 * c) * 2), "r"(v.x),
                    "r"(v.y), "r"(v.z), "r"(v.w)
                    : "memory");
     }

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Optional
 
 import torch
@@ -276,6 +277,12 @@ class _LoRAGegluProjection(torch.autograd.Function):
 def geglu_projection_supported(mod, x: torch.Tensor) -> bool:
     """True when ``h * gelu(gate)`` of ``mod(x)`` can come out of the projection's own epilogue."""
     if not isinstance(mod, LoRALinear) or not x.is_cuda or x.numel() == 0 or mod.out_features % 2 != 0:
+        return False
+    # Opt-in (SDT_FUSED_GEGLU=1).  Measured on B200 (profiles/r02_geglu_epilogue_ab.txt): the erf GELU is ~25 instructions per
+    # element and only the 8 epilogue warps of a CTA can evaluate it, so at K = 320 the epilogue becomes issue-bound (146 us against
+    # 60 us projection + 45 us vectorised GEGLU pass) and at K >= 640 the 128-wide tiles it needs cost more than the pass saves.
+    # The default is therefore the 224-wide projection followed by the GEGLU kernel; `geglu_projection` itself ignores the switch.
+    if os.environ.get("SDT_FUSED_GEGLU", "0") != "1":
         return False
     if mod.training and mod.lora_dropout_p > 0.0:
         return False
