@@ -242,14 +242,18 @@ int sdt_geglu(const void* proj, const void* dout, void* out_or_dproj, int64_t M,
  * norm2 of a ResNet block (diffusers ResnetBlock2D: hidden = hidden + temb[:, :, None, None]; hidden = norm2(hidden)) folded
  * into the norm; x itself is not rewritten.
  * forward : stats f32[B,G,2] (written: per-group sum, sum of squares); y = act((x' - mean) * rstd * gamma + beta), x' = x + chan_bias
- * backward: dx (= dx') from (x, chan_bias, dout, stats); bstats f32[B,G,2] is scratch.  d chan_bias = sum over HW of dx (caller).
+ * backward: dx (= dx') from (x, chan_bias, dout, stats).  d chan_bias = sum over HW of dx (caller).
+ * ws: scratch of ws_floats >= sdt_group_norm_workspace_floats(B, G) f32 (no initialisation needed): the statistics pass leaves one
+ *     partial per CTA there and the apply pass sums them in CTA order -- no float atomics, results are bit-reproducible like
+ *     torch's native GroupNorm, and there is no zero-fill in front of the statistics launch.
  * Needs C % 8 == 0 and C / G >= 8.
  */
+int64_t sdt_group_norm_workspace_floats(int64_t B, int G);
 int sdt_group_norm_nhwc(const void* x, const void* chan_bias, const float* gamma, const float* beta, float* stats, void* y,
-                        int64_t B, int64_t HW, int C, int G, float eps, int silu, void* stream);
+                        int64_t B, int64_t HW, int C, int G, float eps, int silu, float* ws, int64_t ws_floats, void* stream);
 int sdt_group_norm_nhwc_bwd(const void* x, const void* chan_bias, const void* dout, const float* gamma, const float* beta,
-                            const float* stats, float* bstats, void* dx, int64_t B, int64_t HW, int C, int G, float eps, int silu,
-                            void* stream);
+                            const float* stats, float* ws, int64_t ws_floats, void* dx, int64_t B, int64_t HW, int C, int G, float eps,
+                            int silu, void* stream);
 
 /* ---- f2: residual add with folded per-channel bias on channels-last bf16 [rows, C]: out = a + b + bias[c] (bias f32[C]) ----
  * End of diffusers ResnetBlock2D: out = shortcut(x) + conv2(h); the convolutions run without bias and their frozen biases are

@@ -80,10 +80,11 @@ SIGNATURES = {
     "sdt_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(c_float), c_void_p,
                                c_float, c_void_p, c_float, c_void_p, c_void_p]),
     "sdt_geglu": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "sdt_group_norm_workspace_floats": (c_int64, [c_int64, c_int]),
     "sdt_group_norm_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
-                                    c_float, c_int, c_void_p]),
-    "sdt_group_norm_nhwc_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                        c_int64, c_int, c_int, c_float, c_int, c_void_p]),
+                                    c_float, c_int, c_void_p, c_int64, c_void_p]),
+    "sdt_group_norm_nhwc_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                        c_int64, c_int64, c_int, c_int, c_float, c_int, c_void_p]),
     "sdt_residual_bias_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "sdt_layer_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
                                    c_void_p]),

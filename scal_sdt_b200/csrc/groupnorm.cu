@@ -61,26 +61,60 @@ enum { T_A = 0, T_BC = 1, T_SC = 2, T_SH = 3, T_D = 2, T_E = 3 };
 //   kHalf (SiLU variants): A and Bc are stored halved
 //   cbias (optional, bf16 [B, C]): the tensor that is normalised is x + cbias[b, c] (the time-embedding add in front of norm2
 //   of a ResNet block); every row is an affine function of x, so the bias folds into the constant terms
+// Statistics reach the table builder either FINAL (fstats [B,G,2]: the forward's, saved for the backward) or as the per-CTA
+// PARTIALS of the statistics launch just before this one (part [B][n_part][2G]); partials are summed here in CTA order, by
+// every CTA of the apply launch for itself -- deterministic (no float atomics anywhere), no zero-fill, nothing on the critical
+// path of the statistics launch.  CTA (0, b) of the forward apply also writes the final statistics out for the backward.
+struct GnStats {
+  const float* fstats;      // final forward statistics, or null
+  const float* fpart;       // forward partials (used when fstats is null)
+  const float* bpart;       // backward partials (apply-backward only)
+  float* stats_out;         // where CTA (0, b) stores the summed forward statistics (or null)
+  int n_fpart, n_bpart;
+};
+__device__ __forceinline__ float sum_partials(const float* __restrict__ part, int n_part, int b, int two_g, int i) {
+  const float* p = part + (size_t)b * n_part * two_g + i;
+  float acc = 0.f;
+  int k = 0;
+  for (; k + 4 <= n_part; k += 4) {
+    const float v0 = __ldcg(p + (size_t)(k + 0) * two_g), v1 = __ldcg(p + (size_t)(k + 1) * two_g);
+    const float v2 = __ldcg(p + (size_t)(k + 2) * two_g), v3 = __ldcg(p + (size_t)(k + 3) * two_g);
+    acc += v0; acc += v1; acc += v2; acc += v3;
+  }
+  for (; k < n_part; ++k) acc += __ldcg(p + (size_t)k * two_g);
+  return acc;
+}
 template <bool kStatsBwd, bool kApplyBwd, bool kHalf>
 __device__ __forceinline__ void build_table(float* tab, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            const float* __restrict__ fstats, const float* __restrict__ bstats,
-                                            const uint16_t* __restrict__ cbias, int b, const GnShape& s, float eps) {
+                                            const GnStats& gs, const uint16_t* __restrict__ cbias, int b, const GnShape& s, float eps) {
   constexpr int TU = 8;
   const float inv_n = 1.0f / ((float)s.HW * (float)s.cpg);
   const float ab = kHalf ? 0.5f : 1.0f;
+  __shared__ float gsum[4 * 128];                 // [0, 2G): forward (sum, sum of squares) per group; [2G, 4G): backward sums
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) {
+    float f;
+    if (gs.fstats != nullptr) f = gs.fstats[(size_t)b * 2 * s.G + i];
+    else {
+      f = sum_partials(gs.fpart, gs.n_fpart, b, 2 * s.G, i);
+      if (gs.stats_out != nullptr && blockIdx.x == 0) gs.stats_out[(size_t)b * 2 * s.G + i] = f;
+    }
+    gsum[i] = f;
+    if (kApplyBwd) gsum[2 * s.G + i] = sum_partials(gs.bpart, gs.n_bpart, b, 2 * s.G, i);
+  }
+  __syncthreads();
   for (int cb = threadIdx.x; cb < s.C; cb += TU * blockDim.x) {
     float gm[TU], bt[TU], f0[TU], f1[TU], b0[TU], b1[TU], tb[TU];
 #pragma unroll
     for (int t = 0; t < TU; ++t) {
       const int c = cb + t * blockDim.x;
       if (c < s.C) {
-        const size_t gi = ((size_t)b * s.G + c / s.cpg) * 2;
+        const int gi = (c / s.cpg) * 2;
         gm[t] = __ldg(gamma + c);
         bt[t] = __ldg(beta + c);
         tb[t] = cbias != nullptr ? __uint_as_float((uint32_t)cbias[(size_t)b * s.C + c] << 16) : 0.f;
-        f0[t] = fstats[gi];
-        f1[t] = fstats[gi + 1];
-        if (kApplyBwd) { b0[t] = bstats[gi]; b1[t] = bstats[gi + 1]; }
+        f0[t] = gsum[gi];
+        f1[t] = gsum[gi + 1];
+        if (kApplyBwd) { b0[t] = gsum[2 * s.G + gi]; b1[t] = gsum[2 * s.G + gi + 1]; }
       }
     }
 #pragma unroll
@@ -112,15 +146,17 @@ __device__ __forceinline__ void build_table(float* tab, const float* __restrict_
 // ---- statistics: stats[b][g] = (sum x, sum x^2)   or, for the backward, (sum dz A, sum dz A xhat) = rstd (sum dzg, sum dzg xhat)
 template <bool BWD, bool SILU>
 __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dout, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const float* __restrict__ fstats, float* __restrict__ out_stats,
+                                const float* __restrict__ beta, const float* __restrict__ fstats, float* __restrict__ out_part,
                                 const uint16_t* __restrict__ cbias, GnShape s, float eps) {
   extern __shared__ float tab[];                 // BWD: [4][C] (A, Bc, Sc, Sh)
-  __shared__ float acc[2 * 128];
+  __shared__ float4 tpart[512];                  // per-thread (sum, sq) of its first / second group: summed in thread order below
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) acc[i] = 0.f;
   pdl_wait();                 // PDL (sdt_common.cuh): x / dout come from the kernel in front of us
   pdl_launch_dependents();
-  if (BWD) build_table<true, false, SILU>(tab, gamma, beta, fstats, nullptr, cbias, b, s, eps);
+  if (BWD) {
+    GnStats gs{fstats, nullptr, nullptr, nullptr, 0, 0};
+    build_table<true, false, SILU>(tab, gamma, beta, gs, cbias, b, s, eps);
+  }
   __syncthreads();
   const int v = threadIdx.x % s.vecs, rp = threadIdx.x / s.vecs;
   const int c0 = v * 8;
@@ -186,32 +222,44 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, const uint16_t* 
       accumulate(xu, du);
     }
     // elements j >= js of this thread's 8-channel vector belong to the next group (cpg >= 8: at most two groups per vector)
-    const int g0 = c0 / s.cpg, g1 = (c0 + 7) / s.cpg;
+    const int g0 = c0 / s.cpg;
     const int js = min(8, (g0 + 1) * s.cpg - c0);
     float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (j < js) { a0 += S[j]; q0 += Q[j]; } else { a1 += S[j]; q1 += Q[j]; }
     }
-    atomicAdd(&acc[2 * g0], a0);
-    atomicAdd(&acc[2 * g0 + 1], q0);
-    if (g1 != g0) { atomicAdd(&acc[2 * g1], a1); atomicAdd(&acc[2 * g1 + 1], q1); }
+    tpart[threadIdx.x] = make_float4(a0, q0, a1, q1);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) atomicAdd(out_stats + (size_t)b * s.G * 2 + i, acc[i]);
+  // group totals of this CTA in a FIXED order (pixel-row slot, then channel vector): thread i owns value i of [G][2]; the CTA's
+  // partial goes to out_part[b][blockIdx.x][2G] and is summed, in CTA order, by whoever consumes the statistics (build_table)
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) {
+    const int g = i >> 1, sq = i & 1;
+    const int v_lo = (g * s.cpg) / 8, v_hi = min(s.vecs - 1, ((g + 1) * s.cpg - 1) / 8);
+    float tot = 0.f;
+    for (int r = 0; r < s.rows_par; ++r)
+      for (int vv = v_lo; vv <= v_hi; ++vv) {
+        const float4 t = tpart[r * s.vecs + vv];
+        const int gg0 = (vv * 8) / s.cpg, gg1 = (vv * 8 + 7) / s.cpg;
+        if (gg0 == g) tot += sq ? t.y : t.x;
+        else if (gg1 == g) tot += sq ? t.w : t.z;
+      }
+    out_part[((size_t)b * gridDim.x + blockIdx.x) * 2 * s.G + i] = tot;
+  }
 }
 
 // ---- apply: forward y = act(x A + Bc);  backward dx = A dz - D - E x --------------------------------------------------
 // bstats of the backward hold (sum dz A, sum dz A xhat) = rstd * (sum dzg, sum dzg xhat): P1 = bstats0 / (rstd n) etc.
 template <bool BWD, bool SILU>
 __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dout, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const float* __restrict__ fstats, const float* __restrict__ bstats,
+                                const float* __restrict__ beta, const GnStats gs,
                                 uint16_t* __restrict__ out, const uint16_t* __restrict__ cbias, GnShape s, float eps) {
   extern __shared__ float tab[];                 // forward [2][C] (A, Bc); backward [4][C] (A, Bc, D, E); A, Bc halved for SiLU
   const int b = blockIdx.y;
   pdl_wait();                 // PDL: the statistics (and x) come from the kernels in front of us
   pdl_launch_dependents();
-  build_table<false, BWD, SILU>(tab, gamma, beta, fstats, bstats, cbias, b, s, eps);
+  build_table<false, BWD, SILU>(tab, gamma, beta, gs, cbias, b, s, eps);
   __syncthreads();
   const int r_begin = blockIdx.x * s.rows_per_cta;
   const int n_rows = min(s.rows_per_cta, (int)(s.HW - r_begin));
@@ -312,18 +360,27 @@ static int gn_grid(K kernel, GnShape* s, int64_t B, size_t smem, dim3* grid) {
 
 using namespace sdt;
 
-#define SDT_GN_LAUNCH(KERNEL, SMEM, WHAT, ...)                               \
+// one launch: grid from the occupancy calculator, PDL attribute; *n_ctas_x receives gridDim.x (the number of partials per sample
+// a statistics launch produces)
+#define SDT_GN_LAUNCH(KERNEL, SMEM, WHAT, NX, ...)                           \
   do {                                                                       \
     GnShape sk = s;                                                          \
     dim3 grid;                                                               \
     if ((rc = gn_grid(KERNEL, &sk, B, SMEM, &grid)) != SDT_OK) return rc;    \
+    if ((NX) != nullptr) *(NX) = (int)grid.x;                                \
     SDT_CUDA_OK(launch_kernel(KERNEL, grid, dim3(sk.threads), SMEM, st, true, __VA_ARGS__, cb, sk, eps)); \
     SDT_LAUNCH_OK(WHAT);                                                     \
   } while (0)
 
+// floats of partial-statistics workspace that any launch for this batch size / group count can need (grid.x <= 16 CTAs per SM)
+extern "C" int64_t sdt_group_norm_workspace_floats(int64_t B, int G) {
+  return ((int64_t)num_sms() * 16 + B) * 2 * G;
+}
+
 extern "C" int sdt_group_norm_nhwc(const void* x, const void* chan_bias, const float* gamma, const float* beta, float* stats, void* y,
-                                   int64_t B, int64_t HW, int C, int G, float eps, int silu, void* stream) {
-  SDT_REQUIRE(x && gamma && beta && stats && y, SDT_ERR_ARG, "sdt_group_norm_nhwc: null pointer");
+                                   int64_t B, int64_t HW, int C, int G, float eps, int silu, float* ws, int64_t ws_floats,
+                                   void* stream) {
+  SDT_REQUIRE(x && gamma && beta && stats && y && ws, SDT_ERR_ARG, "sdt_group_norm_nhwc: null pointer");
   SDT_REQUIRE(aligned16(x) && aligned16(y) && aligned16(chan_bias), SDT_ERR_ARG, "sdt_group_norm_nhwc: pointers must be 16-byte aligned");
   const uint16_t* cb = (const uint16_t*)chan_bias;
   GnShape s;
@@ -334,17 +391,26 @@ extern "C" int sdt_group_norm_nhwc(const void* x, const void* chan_bias, const f
   const uint16_t* xp = (const uint16_t*)x;
   const uint16_t* np = nullptr;
   const float* nf = nullptr;
-  SDT_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * G, st));
-  SDT_GN_LAUNCH((gn_stats_kernel<false, false>), 0, "gn_stats", xp, np, gamma, beta, nf, stats);
-  if (silu) SDT_GN_LAUNCH((gn_apply_kernel<false, true>), tab2, "gn_apply", xp, np, gamma, beta, (const float*)stats, nf, (uint16_t*)y);
-  else      SDT_GN_LAUNCH((gn_apply_kernel<false, false>), tab2, "gn_apply", xp, np, gamma, beta, (const float*)stats, nf, (uint16_t*)y);
+  {   // the statistics launch writes grid.x partials per sample: check the workspace before launching
+    GnShape sk = s;
+    dim3 grid;
+    if ((rc = gn_grid(gn_stats_kernel<false, false>, &sk, B, 0, &grid)) != SDT_OK) return rc;
+    SDT_REQUIRE((int64_t)grid.x * B * 2 * G <= ws_floats, SDT_ERR_ARG, "sdt_group_norm_nhwc: workspace of %lld floats, %lld needed",
+                (long long)ws_floats, (long long)grid.x * B * 2 * G);
+  }
+  int n_part = 0;
+  SDT_GN_LAUNCH((gn_stats_kernel<false, false>), 0, "gn_stats", &n_part, xp, np, gamma, beta, nf, ws);
+  const GnStats gs{nullptr, ws, nullptr, stats, n_part, 0};       // sum the partials; CTA (0, b) stores the totals for the backward
+  int* none = nullptr;
+  if (silu) SDT_GN_LAUNCH((gn_apply_kernel<false, true>), tab2, "gn_apply", none, xp, np, gamma, beta, gs, (uint16_t*)y);
+  else      SDT_GN_LAUNCH((gn_apply_kernel<false, false>), tab2, "gn_apply", none, xp, np, gamma, beta, gs, (uint16_t*)y);
   return SDT_OK;
 }
 
 extern "C" int sdt_group_norm_nhwc_bwd(const void* x, const void* chan_bias, const void* dout, const float* gamma, const float* beta,
-                                       const float* stats, float* bstats, void* dx, int64_t B, int64_t HW, int C, int G,
+                                       const float* stats, float* ws, int64_t ws_floats, void* dx, int64_t B, int64_t HW, int C, int G,
                                        float eps, int silu, void* stream) {
-  SDT_REQUIRE(x && dout && gamma && beta && stats && bstats && dx, SDT_ERR_ARG, "sdt_group_norm_nhwc_bwd: null pointer");
+  SDT_REQUIRE(x && dout && gamma && beta && stats && ws && dx, SDT_ERR_ARG, "sdt_group_norm_nhwc_bwd: null pointer");
   SDT_REQUIRE(aligned16(x) && aligned16(dout) && aligned16(dx) && aligned16(chan_bias), SDT_ERR_ARG,
               "sdt_group_norm_nhwc_bwd: pointers must be 16-byte aligned");
   const uint16_t* cb = (const uint16_t*)chan_bias;
@@ -355,13 +421,18 @@ extern "C" int sdt_group_norm_nhwc_bwd(const void* x, const void* chan_bias, con
   const size_t tab4 = sizeof(float) * 4 * C;      // <= 64 KiB (C <= 4096)
   const uint16_t* xp = (const uint16_t*)x;
   const uint16_t* dp = (const uint16_t*)dout;
-  SDT_CUDA_OK(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * B * G, st));
+  SDT_REQUIRE(sdt_group_norm_workspace_floats(B, G) <= ws_floats, SDT_ERR_ARG, "sdt_group_norm_nhwc_bwd: workspace of %lld floats, %lld needed",
+              (long long)ws_floats, (long long)sdt_group_norm_workspace_floats(B, G));
+  int n_part = 0;
+  int* none = nullptr;
   if (silu) {
-    SDT_GN_LAUNCH((gn_stats_kernel<true, true>), tab4, "gn_bwd_stats", xp, dp, gamma, beta, stats, bstats);
-    SDT_GN_LAUNCH((gn_apply_kernel<true, true>), tab4, "gn_bwd_apply", xp, dp, gamma, beta, stats, (const float*)bstats, (uint16_t*)dx);
+    SDT_GN_LAUNCH((gn_stats_kernel<true, true>), tab4, "gn_bwd_stats", &n_part, xp, dp, gamma, beta, stats, ws);
+    const GnStats gs{stats, nullptr, ws, nullptr, 0, n_part};
+    SDT_GN_LAUNCH((gn_apply_kernel<true, true>), tab4, "gn_bwd_apply", none, xp, dp, gamma, beta, gs, (uint16_t*)dx);
   } else {
-    SDT_GN_LAUNCH((gn_stats_kernel<true, false>), tab4, "gn_bwd_stats", xp, dp, gamma, beta, stats, bstats);
-    SDT_GN_LAUNCH((gn_apply_kernel<true, false>), tab4, "gn_bwd_apply", xp, dp, gamma, beta, stats, (const float*)bstats, (uint16_t*)dx);
+    SDT_GN_LAUNCH((gn_stats_kernel<true, false>), tab4, "gn_bwd_stats", &n_part, xp, dp, gamma, beta, stats, ws);
+    const GnStats gs{stats, nullptr, ws, nullptr, 0, n_part};
+    SDT_GN_LAUNCH((gn_apply_kernel<true, false>), tab4, "gn_bwd_apply", none, xp, dp, gamma, beta, gs, (uint16_t*)dx);
   }
   return SDT_OK;
 }

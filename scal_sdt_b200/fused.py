@@ -91,9 +91,11 @@ class _GroupNormNHWC(torch.autograd.Function):
         y = torch.empty_like(x, memory_format=torch.channels_last)
         stats = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
         cb = chan_bias.contiguous() if chan_bias is not None else None
-        _lib.check(_lib.load().sdt_group_norm_nhwc(x.data_ptr(), _lib.ptr(cb), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
-                                                   y.data_ptr(), B, H * W, C, groups, eps, int(silu), _lib.stream_ptr()),
-                   "sdt_group_norm_nhwc")
+        lib = _lib.load()
+        ws = torch.empty(int(lib.sdt_group_norm_workspace_floats(B, groups)), dtype=torch.float32, device=x.device)   # per-CTA partials
+        _lib.check(lib.sdt_group_norm_nhwc(x.data_ptr(), _lib.ptr(cb), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+                                           y.data_ptr(), B, H * W, C, groups, eps, int(silu), ws.data_ptr(), ws.numel(),
+                                           _lib.stream_ptr()), "sdt_group_norm_nhwc")
         ctx.save_for_backward(x, gamma, beta, stats, *([cb] if cb is not None else []))
         ctx.cfg = (groups, eps, silu)
         ctx.has_bias = cb is not None
@@ -109,10 +111,11 @@ class _GroupNormNHWC(torch.autograd.Function):
         if d.dtype != x.dtype:
             d = d.to(x.dtype)
         dx = torch.empty_like(x, memory_format=torch.channels_last)
-        bstats = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().sdt_group_norm_nhwc_bwd(x.data_ptr(), _lib.ptr(cb), d.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                                       stats.data_ptr(), bstats.data_ptr(), dx.data_ptr(), B, H * W, C, groups,
-                                                       eps, int(silu), _lib.stream_ptr()), "sdt_group_norm_nhwc_bwd")
+        lib = _lib.load()
+        ws = torch.empty(int(lib.sdt_group_norm_workspace_floats(B, groups)), dtype=torch.float32, device=x.device)
+        _lib.check(lib.sdt_group_norm_nhwc_bwd(x.data_ptr(), _lib.ptr(cb), d.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                               stats.data_ptr(), ws.data_ptr(), ws.numel(), dx.data_ptr(), B, H * W, C, groups,
+                                               eps, int(silu), _lib.stream_ptr()), "sdt_group_norm_nhwc_bwd")
         dcb = None
         if ctx.has_bias and ctx.needs_input_grad[1]:
             dcb = dx.sum(dim=(2, 3), dtype=torch.float32).to(cb.dtype)      # the backward of the broadcast add

@@ -122,11 +122,12 @@ def test_group_norm_and_residual_outputs_stay_inside_their_buffers(sdt_lib, B, H
     cb = torch.randn(B, C, device=DEV).bfloat16()
     gam, bet = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
     y, dx, out = (Guarded((B, HW, C), torch.bfloat16) for _ in range(3))
-    stats, bst = Guarded((B, G, 2), torch.float32), Guarded((B, G, 2), torch.float32)
+    n_ws = int(lib.sdt_group_norm_workspace_floats(B, G))
+    stats, bst = Guarded((B, G, 2), torch.float32), Guarded((n_ws,), torch.float32)
     _lib.check(lib.sdt_group_norm_nhwc(x.data_ptr(), cb.data_ptr(), gam.data_ptr(), bet.data_ptr(), stats.view.data_ptr(),
-                                       y.view.data_ptr(), B, HW, C, G, 1e-5, 1, st()))
+                                       y.view.data_ptr(), B, HW, C, G, 1e-5, 1, bst.view.data_ptr(), n_ws, st()))
     _lib.check(lib.sdt_group_norm_nhwc_bwd(x.data_ptr(), cb.data_ptr(), d.data_ptr(), gam.data_ptr(), bet.data_ptr(),
-                                           stats.view.data_ptr(), bst.view.data_ptr(), dx.view.data_ptr(), B, HW, C, G, 1e-5, 1, st()))
+                                           stats.view.data_ptr(), bst.view.data_ptr(), n_ws, dx.view.data_ptr(), B, HW, C, G, 1e-5, 1, st()))
     _lib.check(lib.sdt_residual_bias_add(x.data_ptr(), d.data_ptr(), gam.data_ptr(), out.view.data_ptr(), B * HW, C, st()))
     torch.cuda.synchronize()
     assert y.intact() and dx.intact() and out.intact() and stats.intact() and bst.intact()

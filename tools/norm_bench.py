@@ -42,13 +42,13 @@ for (B, C, H, W) in GN:
     g = torch.ones(C, device=dev)
     b = torch.zeros(C, device=dev)
     stats = torch.empty(B, 32, 2, device=dev)
-    bst = torch.empty(B, 32, 2, device=dev)
+    bst = torch.empty(int(lib.sdt_group_norm_workspace_floats(B, 32)), device=dev)
 
     def fwd():
-        _lib.check(lib.sdt_group_norm_nhwc(x.data_ptr(), None, g.data_ptr(), b.data_ptr(), stats.data_ptr(), y.data_ptr(), B, H * W, C, 32, 1e-5, 1, st))
+        _lib.check(lib.sdt_group_norm_nhwc(x.data_ptr(), None, g.data_ptr(), b.data_ptr(), stats.data_ptr(), y.data_ptr(), B, H * W, C, 32, 1e-5, 1, bst.data_ptr(), bst.numel(), st))
 
     def bwd():
-        _lib.check(lib.sdt_group_norm_nhwc_bwd(x.data_ptr(), None, d.data_ptr(), g.data_ptr(), b.data_ptr(), stats.data_ptr(), bst.data_ptr(),
+        _lib.check(lib.sdt_group_norm_nhwc_bwd(x.data_ptr(), None, d.data_ptr(), g.data_ptr(), b.data_ptr(), stats.data_ptr(), bst.data_ptr(), bst.numel(),
                                                y.data_ptr(), B, H * W, C, 32, 1e-5, 1, st))
     tf, tb = kernel_times(fwd), kernel_times(bwd)
     mb = x.numel() * 2 / 1e6
