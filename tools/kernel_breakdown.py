@@ -11,8 +11,9 @@ import bench  # noqa: E402
 from scal_sdt_b200 import GradExchange  # noqa: E402
 
 dev = torch.device("cuda:0")
-tr = bench.build_trainer(dev, GradExchange(0, 1))
-batches = [{k: v.to(dev) for k, v in b.items()} for b in bench.synthetic_batches(2, 8, 0, False)]
+wl = bench.WORKLOADS[os.environ.get("SDT_WORKLOAD", "cfg2")]
+tr = bench.build_trainer(wl, dev, GradExchange(0, 1))
+batches = [{k: v.to(dev) for k, v in b.items()} for b in bench.synthetic_batches(wl, 2, wl["batch"], 0, False)]
 for i in range(3):
     tr.step(batches[i % 2])
 torch.cuda.synchronize()

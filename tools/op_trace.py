@@ -12,8 +12,8 @@ import bench  # noqa: E402
 from scal_sdt_b200 import GradExchange  # noqa: E402
 
 dev = torch.device("cuda:0")
-tr = bench.build_trainer(dev, GradExchange(0, 1))
-batches = [{k: v.to(dev) for k, v in b.items()} for b in bench.synthetic_batches(2, 8, 0, False)]
+tr = bench.build_trainer(bench.WORKLOAD, dev, GradExchange(0, 1))
+batches = [{k: v.to(dev) for k, v in b.items()} for b in bench.synthetic_batches(bench.WORKLOAD, 2, 8, 0, False)]
 for i in range(2):
     tr.step(batches[i % 2])
 torch.cuda.synchronize()

@@ -1,6 +1,6 @@
 """Per-site A/B on this GPU: ONE fused launch of this repo against the sequence the reference executes for the same site
 (``modules/lora.py:14`` -> loralib 0.1 under autocast: ``F.linear`` + ``x @ A.T`` + ``@ B.T`` + ``* scaling`` + ``+`` = 5
-launches forward; autograd's 2 base GEMM-free... backward: dX = dY W, (dY B), (.. A), adds, dA, dB).
+launches forward, and autograd's chain of them backward: dY W, dY B, (dY B) A, the adds, dA, dB).
 
 Forward and backward, the twelve (M, K, N) of BASELINE cfg2, rank 16 and 64.  CUDA-event time over the whole
 sequence (L2-warm, 20 iterations after warm-up), so launch gaps between the torch kernels count -- they are what a training
