@@ -59,6 +59,16 @@ int sdt_lora_linear_fwd(const void* x, const void* w, const float* bias, const v
                         float scaling, void* y, void* t_save,
                         int64_t M, int64_t K, int64_t N, int r, int dtype, void* stream);
 
+/* ---- K1 + residual: y = round(round(x W^T + bias + scaling (x A^T) B^T) + residual) -----------------------------------
+ * The output of ff.net.2 / proj_out is added to the residual stream right away (diffusers BasicTransformerBlock:
+ * hidden_states = ff(norm3(hidden_states)) + hidden_states; Transformer2DModel: output = proj_out(...) + residual).  The
+ * epilogue reads the residual tile and adds it to the rounded output -- the values torch's separate add produces, without
+ * that add's pass over both tensors.  residual [M,N], same dtype as y; SDT_BF16 / SDT_F16.
+ */
+int sdt_lora_linear_fwd_res(const void* x, const void* w, const float* bias, const void* A, const void* B, float scaling,
+                            const void* residual, void* y, void* t_save, int64_t M, int64_t K, int64_t N, int r, int dtype,
+                            void* stream);
+
 /* ---- K1 (grouped): several projections of ONE shape in one launch ---------------------------
  * The reference calls to_q / to_k / to_v of a self-attention on the same normalised hidden states, and to_k / to_v
  * of a cross-attention on the same text context (diffusers CrossAttention.forward under modules/lora.py:12-14): three
@@ -70,6 +80,7 @@ int sdt_lora_linear_fwd(const void* x, const void* w, const float* bias, const v
 #define SDT_MAX_GROUP 4
 typedef struct {
   const void* x; const void* w; const float* bias; const void* A; const void* B; void* y; void* t_save;
+  const void* residual;       /* NULL, or [M,N] added to y in the epilogue (as sdt_lora_linear_fwd_res) */
 } sdt_lora_problem;
 int sdt_lora_linear_fwd_group(const sdt_lora_problem* problems /* host */, int n_problems, float scaling,
                               int64_t M, int64_t K, int64_t N, int r, int dtype, void* stream);

@@ -26,7 +26,7 @@ class PackSite(ctypes.Structure):
 
 class LoraProblem(ctypes.Structure):
     _fields_ = [("x", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("A", c_void_p), ("B", c_void_p), ("y", c_void_p),
-                ("t_save", c_void_p)]
+                ("t_save", c_void_p), ("residual", c_void_p)]
 
 
 class LoraBwdProblem(ctypes.Structure):
@@ -54,6 +54,8 @@ SIGNATURES = {
     "sdt_launch_count": (ctypes.c_longlong, []),
     "sdt_lora_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "sdt_lora_linear_fwd_res": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                        c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sdt_lora_linear_geglu_supported": (c_int, [c_int64, c_int64, c_int64, c_int]),
     "sdt_lora_linear_geglu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                           c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),

@@ -342,7 +342,8 @@ static int gn_shape(GnShape* s, int64_t B, int64_t HW, int C, int G) {
 // thread still sees >= 4 vectors so that the per-CTA table is amortised.
 template <typename K>
 static int gn_grid(K kernel, GnShape* s, int64_t B, size_t smem, dim3* grid) {
-  if (smem > 48 * 1024) SDT_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  // static shared memory (per-thread partials, group sums: ~10 KB) counts against the 48 KB default limit too
+  if (smem > 32 * 1024) SDT_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   int per_sm = 0;
   SDT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, s->threads, smem));
   if (per_sm < 1) per_sm = 1;

@@ -7,7 +7,7 @@
 
 namespace sdt {
 int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
-                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, bool f16, cudaStream_t st);
+                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, bool f16, cudaStream_t st, const void* res = nullptr);
 size_t lora_wgrad_workspace_bytes();
 int lora_wgrad_max_sites();
 int lora_fwd_f32(const float* x, const float* w, const float* bias, const float* A, const float* B, float scaling,
@@ -22,9 +22,26 @@ void debug_set(int key, uint64_t value);
 
 using namespace sdt;
 
+static int lora_linear_fwd_impl(const void* x, const void* w, const float* bias, const void* A, const void* B, float scaling, void* y,
+                                void* t_save, const void* residual, int64_t M, int64_t K, int64_t N, int r, int dtype, void* stream);
+
 extern "C" int sdt_lora_linear_fwd(const void* x, const void* w, const float* bias, const void* A, const void* B,
                                    float scaling, void* y, void* t_save, int64_t M, int64_t K, int64_t N, int r,
                                    int dtype, void* stream) {
+  return lora_linear_fwd_impl(x, w, bias, A, B, scaling, y, t_save, nullptr, M, K, N, r, dtype, stream);
+}
+
+extern "C" int sdt_lora_linear_fwd_res(const void* x, const void* w, const float* bias, const void* A, const void* B,
+                                       float scaling, const void* residual, void* y, void* t_save, int64_t M, int64_t K, int64_t N,
+                                       int r, int dtype, void* stream) {
+  SDT_REQUIRE(residual != nullptr, SDT_ERR_ARG, "sdt_lora_linear_fwd_res: null residual");
+  SDT_REQUIRE(dtype == SDT_BF16 || dtype == SDT_F16, SDT_ERR_UNSUPPORTED,
+              "sdt_lora_linear_fwd_res: the residual epilogue is bf16 / fp16 (fp32: add after sdt_lora_linear_fwd)");
+  return lora_linear_fwd_impl(x, w, bias, A, B, scaling, y, t_save, residual, M, K, N, r, dtype, stream);
+}
+
+static int lora_linear_fwd_impl(const void* x, const void* w, const float* bias, const void* A, const void* B, float scaling, void* y,
+                                void* t_save, const void* residual, int64_t M, int64_t K, int64_t N, int r, int dtype, void* stream) {
   SDT_REQUIRE(x && w && y, SDT_ERR_ARG, "sdt_lora_linear_fwd: null pointer");
   SDT_REQUIRE(M > 0 && K > 0 && N > 0 && r >= 0, SDT_ERR_ARG, "sdt_lora_linear_fwd: bad sizes M=%lld K=%lld N=%lld r=%d",
               (long long)M, (long long)K, (long long)N, r);
@@ -35,7 +52,7 @@ extern "C" int sdt_lora_linear_fwd(const void* x, const void* w, const float* bi
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SDT_BF16 || dtype == SDT_F16) {
     SDT_REQUIRE(r == 0 || t_save != nullptr, SDT_ERR_ARG, "sdt_lora_linear_fwd: t_save is required when r > 0");
-    return lora_gemm_bf16(x, w, bias, A, B, scaling, y, t_save, M, K, N, r, true, dtype == SDT_F16, st);
+    return lora_gemm_bf16(x, w, bias, A, B, scaling, y, t_save, M, K, N, r, true, dtype == SDT_F16, st, residual);
   }
   if (dtype == SDT_F32)
     return lora_fwd_f32((const float*)x, (const float*)w, bias, (const float*)A, (const float*)B, scaling, (float*)y,

@@ -430,6 +430,7 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
         const ItemCoord ic = decode_item<G>(item, p, C::BM);
         const int m0 = ic.m0, g = ic.g;
         uint8_t* yp = gm.y[ic.prob];
+        const uint8_t* rp = gm.res[ic.prob];
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, p.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -452,7 +453,7 @@ lora_gemm_kernel(const __grid_constant__ GemmGroup<G> gm, const LoraGemmParams p
               stage_row_chunk(stg, lane, h, pk);
             }
             __syncwarp();
-            write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * subs);
+            write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * subs, rp, p.f16 != 0);
             __syncwarp();
           }
           // every tcgen05.ld of this buffer has completed (wait::ld above): release it to the MMA warp
@@ -605,6 +606,7 @@ static int launch_lora_gemm(const LoraProblem* probs, int n_probs, float scaling
     }
     gm.bias[q] = pr.bias;
     gm.t_out[q] = reinterpret_cast<__nv_bfloat16*>(pr.t_out);
+    gm.res[q] = reinterpret_cast<const uint8_t*>(pr.res);
   }
   LoraGemmParams p;
   p.scaling = scaling;
@@ -657,8 +659,9 @@ static int check_group(const LoraProblem* probs, int n_probs, int r, bool main) 
                 "lora_gemm: lora operands must be given exactly when r > 0 (problem %d)", q);
     SDT_REQUIRE((pr.bias != nullptr) == (probs[0].bias != nullptr), SDT_ERR_ARG,
                 "lora_gemm: the problems of one launch must all have a bias or all have none");
-    SDT_REQUIRE(aligned16(pr.x) && aligned16(pr.w) && aligned16(pr.la) && aligned16(pr.lb) && aligned16(pr.y) && aligned16(pr.t_out),
-                SDT_ERR_ARG, "lora_gemm: pointers must be 16-byte aligned (problem %d)", q);
+    SDT_REQUIRE(aligned16(pr.x) && aligned16(pr.w) && aligned16(pr.la) && aligned16(pr.lb) && aligned16(pr.y) && aligned16(pr.t_out) &&
+                    aligned16(pr.res), SDT_ERR_ARG, "lora_gemm: pointers must be 16-byte aligned (problem %d)", q);
+    SDT_REQUIRE(pr.res == nullptr || main, SDT_ERR_ARG, "lora_gemm: a residual needs the base projection (problem %d)", q);
   }
   return SDT_OK;
 }
@@ -696,8 +699,8 @@ int lora_gemm_group_bf16(const LoraProblem* probs, int n_probs, float scaling, i
 }
 
 int lora_gemm_bf16(const void* x, const void* w, const float* bias, const void* la, const void* lb, float scaling, void* y,
-                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, bool f16, cudaStream_t st) {
-  const LoraProblem pr{x, w, bias, la, lb, y, t_out};
+                   void* t_out, int64_t M, int64_t K, int64_t N, int r, bool main, bool f16, cudaStream_t st, const void* res) {
+  const LoraProblem pr{x, w, bias, la, lb, y, t_out, res};
   return lora_gemm_group_bf16(&pr, 1, scaling, M, K, N, r, main, f16, st);
 }
 

@@ -17,6 +17,7 @@ struct LoraProblem {
   const void* lb;      // lora-up   [N,R] bf16
   void* y;             // [M,N] bf16
   void* t_out;         // [M,R] bf16 or null
+  const void* res;     // [M,N] bf16 residual added to the output in the epilogue (y = round(round(proj) + res)), or null
 };
 
 // Problems per launch: q/k/v of a self-attention (3), k/v of cross-attentions that read the same text context (2-4).
@@ -30,6 +31,7 @@ struct GemmGroup {
   uint8_t* y[G];               // outputs are written straight from registers (no tensor map)
   const float* bias[G];
   __nv_bfloat16* t_out[G];
+  const uint8_t* res[G];       // residual stream added in the epilogue, or null
 };
 
 // entry points (lora_gemm.cu / lora_gemm2.cu)

@@ -489,6 +489,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
       const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
       const int g = ic.g;
       uint8_t* yp = gm.y[ic.prob];
+      const uint8_t* rp = S > 1 ? nullptr : gm.res[ic.prob];
       const int nt0 = g * p.group_size;
       const int nt1 = min(nt0 + p.group_size, p.n_tiles);
       for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
@@ -586,7 +587,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             // Phase 2: stream the staged blocks out (full 128-byte lines); the next tile's phase 1 follows in program order
             slot = 0;
             for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot)
-              write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * min(2, n_sub - 2 * cb));
+              write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * min(2, n_sub - 2 * cb), rp, f16);
           }
           __syncwarp();
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(70 + tile_ctr);
@@ -601,7 +602,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
               stage_row_chunk(stg, lane, h, pk);
             }
             __syncwarp();
-            write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * subs);
+            write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * subs, rp, f16);
             __syncwarp();
           }
           tc_fence_before();
@@ -670,6 +671,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
     }
     gm.bias[q] = pr.bias;
     gm.t_out[q] = reinterpret_cast<__nv_bfloat16*>(pr.t_out);
+    gm.res[q] = reinterpret_cast<const uint8_t*>(pr.res);
   }
   PairParams p;
   p.scaling = scaling;

@@ -2,6 +2,8 @@
 // commit / ld / fences) and the UMMA shared-memory + instruction descriptors.  No CUTLASS.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>      // CUtensorMap (types only; the encode function is fetched at run time)
 #include <stdint.h>
 
@@ -178,18 +180,58 @@ __device__ __forceinline__ void stage_row_chunk(uint32_t stg, int lane, int h, c
 #pragma unroll
   for (int j = 0; j < 4; ++j) st_shared_v4(row_base + (((4 * h + j) ^ (lane & 7)) << 4), pk + 4 * j);
 }
+// a + b on four packed pairs of 16-bit values (bf16 or fp16), each sum rounded once: what torch's elementwise add of two
+// bf16 / fp16 tensors produces
+__device__ __forceinline__ uint32_t add_packed_pair(uint32_t a, uint32_t b, bool f16) {
+  if (f16) {
+    const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&a)), y = __half22float2(*reinterpret_cast<const __half2*>(&b));
+    const __half2 r = __floats2half2_rn(x.x + y.x, x.y + y.y);
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const float lo = __uint_as_float(a << 16) + __uint_as_float(b << 16);
+  const float hi = __uint_as_float(a & 0xffff0000u) + __uint_as_float(b & 0xffff0000u);
+  const __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 // write the staged block out: rows [row0, row0 + 32) x 16-byte slots [0, n_slots) starting at column col0 of a row-major
-// bf16 matrix with N columns (N % 8 == 0); rows >= M and columns >= N are clipped
-__device__ __forceinline__ void write_staged_block(uint32_t stg, int lane, uint8_t* y, int row0, int M, int col0, int N, int n_slots) {
+// bf16 matrix with N columns (N % 8 == 0); rows >= M and columns >= N are clipped.  res (optional, same shape as y): the
+// residual stream the projection's output is added to (x + ff(h), y + res of a transformer block) -- read here, added to the
+// rounded output and rounded again, exactly torch's separate add, without that add's pass over both tensors.
+__device__ __forceinline__ void write_staged_block(uint32_t stg, int lane, uint8_t* y, int row0, int M, int col0, int N, int n_slots,
+                                                   const uint8_t* res = nullptr, bool f16 = false) {
   const int c = lane & 7;
   const bool col_ok = c < n_slots && col0 + 8 * c < N;
+  if (res == nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = 4 * i + (lane >> 3);
+      if (col_ok && row0 + rl < M) {
+        const uint4 v = ld_shared_v4(stg + rl * 128 + ((c ^ (rl & 7)) << 4));
+        asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(y + ((size_t)(row0 + rl) * N + col0 + 8 * c) * 2), "r"(v.x),
+                     "r"(v.y), "r"(v.z), "r"(v.w)
+                     : "memory");
+      }
+    }
+    return;
+  }
+  uint4 r[8];                                        // all residual loads in flight before the first store
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = 4 * i + (lane >> 3);
+    if (col_ok && row0 + rl < M)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(r[i].x), "=r"(r[i].y), "=r"(r[i].z), "=r"(r[i].w)
+                   : "l"(res + ((size_t)(row0 + rl) * N + col0 + 8 * c) * 2));
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rl = 4 * i + (lane >> 3);
     if (col_ok && row0 + rl < M) {
       const uint4 v = ld_shared_v4(stg + rl * 128 + ((c ^ (rl & 7)) << 4));
-      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(y + ((size_t)(row0 + rl) * N + col0 + 8 * c) * 2), "r"(v.x),
-                   "r"(v.y), "r"(v.z), "r"(v.w)
+      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(y + ((size_t)(row0 + rl) * N + col0 + 8 * c) * 2),
+                   "r"(add_packed_pair(v.x, r[i].x, f16)), "r"(add_packed_pair(v.y, r[i].y, f16)), "r"(add_packed_pair(v.z, r[i].z, f16)),
+                   "r"(add_packed_pair(v.w, r[i].w, f16))
                    : "memory");
     }
   }

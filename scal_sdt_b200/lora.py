@@ -87,7 +87,9 @@ class _LoRAProjection(torch.autograd.Function):
     """y[M,N] = x[M,K] W^T + b + s (x A^T) B^T through the C ABI; W and b are frozen (model.py:137)."""
 
     @staticmethod
-    def forward(ctx, x2, lora_A, lora_B, mod):
+    def forward(ctx, x2, lora_A, lora_B, mod, res2=None):
+        """``res2`` (optional, [M,N], the dtype of x2): the residual stream the output is added to -- in the epilogue of the same
+        launch (``sdt_lora_linear_fwd_res``); its gradient is the output's."""
         lib = _lib.load()
         M, K = x2.shape
         N = mod.out_features
@@ -101,10 +103,17 @@ class _LoRAProjection(torch.autograd.Function):
             t_save = torch.empty(M, ops.R, dtype=x2.dtype, device=x2.device)
             if PROFILE is not None:
                 ev0 = _ev()
-            _lib.check(lib.sdt_lora_linear_fwd(x2.data_ptr(), w.data_ptr(), _lib.ptr(mod._bias_f32()), ops.A_p.data_ptr(),
-                                               ops.B_p.data_ptr(), mod.scaling, y.data_ptr(), t_save.data_ptr(), M, K, N,
-                                               ops.R, code, st), "sdt_lora_linear_fwd")
+            if res2 is None:
+                _lib.check(lib.sdt_lora_linear_fwd(x2.data_ptr(), w.data_ptr(), _lib.ptr(mod._bias_f32()), ops.A_p.data_ptr(),
+                                                   ops.B_p.data_ptr(), mod.scaling, y.data_ptr(), t_save.data_ptr(), M, K, N,
+                                                   ops.R, code, st), "sdt_lora_linear_fwd")
+            else:
+                _lib.check(lib.sdt_lora_linear_fwd_res(x2.data_ptr(), w.data_ptr(), _lib.ptr(mod._bias_f32()), ops.A_p.data_ptr(),
+                                                       ops.B_p.data_ptr(), mod.scaling, res2.data_ptr(), y.data_ptr(),
+                                                       t_save.data_ptr(), M, K, N, ops.R, code, st), "sdt_lora_linear_fwd_res")
         else:
+            if res2 is not None:
+                raise SdtError("the residual epilogue is bf16 / fp16 only")
             if mod.weight.dtype != torch.float32:
                 raise SdtError("fp32 activations need fp32 frozen weights")
             r = mod.r
@@ -119,13 +128,14 @@ class _LoRAProjection(torch.autograd.Function):
         ctx.need_dx = x2.requires_grad
         ctx.need_w = lora_A.requires_grad or lora_B.requires_grad
         ctx.save_for_backward(x2, t_save, lora_A, lora_B)
+        ctx.res_grad = res2 is not None and res2.requires_grad
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x2, t_save, lora_A, lora_B = ctx.saved_tensors
         dx, dA, dB = _site_backward(ctx.mod, ctx.code, x2, t_save, lora_A, lora_B, dy, ctx.need_dx)
-        return dx, dA, dB, None
+        return dx, dA, dB, None, (dy if ctx.res_grad else None)
 
 
 # ---- deferred weight-gradient reductions --------------------------------------------------------------------------------------
@@ -616,18 +626,23 @@ class _LoRABase(nn.Module):
             self._ops.versions = ver
         return self._ops
 
-    def _project(self, x2: torch.Tensor) -> torch.Tensor:
-        _lib.require_cuda(x2, self.weight, self.lora_A)
+    def _project(self, x2: torch.Tensor, res2: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``res2`` (optional [M, out]): added to the projection -- in the launch's epilogue on the 16-bit path, with torch otherwise."""
+        _lib.require_cuda(x2, self.weight, self.lora_A, res2)
         _lib.device_check()
         if torch.is_autocast_enabled():
             x2 = x2.to(torch.get_autocast_dtype("cuda"))
         if x2.shape[0] == 0:                 # empty batch: nothing to launch (F.linear returns an empty tensor too)
-            return x2.new_zeros(0, self.out_features) + 0.0 * (self.lora_A.sum() + self.lora_B.sum()).to(x2.dtype)
+            y = x2.new_zeros(0, self.out_features) + 0.0 * (self.lora_A.sum() + self.lora_B.sum()).to(x2.dtype)
+            return y if res2 is None else y + res2
         if self.training and self.lora_dropout_p > 0.0:       # loralib: dropout acts on the rank path's input, training mode only
             if x2.dtype == torch.float32:
                 raise SdtError("lora dropout > 0 runs on the bf16 / fp16 tensor-core path only (fp32 is the parity path)")
-            return _LoRADropoutProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self)
-        return _LoRAProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self)
+            y = _LoRADropoutProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self)
+            return y if res2 is None else y + res2
+        if res2 is not None and (x2.dtype == torch.float32 or res2.dtype != x2.dtype or not res2.is_contiguous()):
+            return _LoRAProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self) + res2
+        return _LoRAProjection.apply(x2.contiguous(), self.lora_A, self.lora_B, self, res2)
 
     def extra_repr(self) -> str:
         return f"in={self.in_features}, out={self.out_features}, r={self.r}, scaling={self.scaling}"
@@ -642,9 +657,12 @@ class LoRALinear(_LoRABase):
         self.bias = None
         self._init_lora(in_features, out_features, rank, alpha, dropout)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``residual`` (optional, the shape of the output): returns ``proj(x) + residual`` with the add done in the projection's
+        epilogue (the block's residual connection)."""
         lead = x.shape[:-1]
-        y = self._project(x.reshape(-1, self.in_features))
+        res2 = None if residual is None else residual.reshape(-1, self.out_features)
+        y = self._project(x.reshape(-1, self.in_features), res2)
         return y.view(*lead, self.out_features)
 
 
@@ -664,10 +682,13 @@ class LoRAConv2d(_LoRABase):
         self.bias = None
         self._init_lora(in_channels, out_channels, rank, alpha, dropout)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         b, c, h, w = x.shape
         tokens = x.permute(0, 2, 3, 1).reshape(b * h * w, c)        # a view when x is channels-last
-        y = self._project(tokens)
+        res2 = None
+        if residual is not None:                                    # [b, out, h, w]; a token view when it is channels-last
+            res2 = residual.permute(0, 2, 3, 1).reshape(b * h * w, self.out_channels)
+        y = self._project(tokens, res2)
         return y.view(b, h, w, self.out_channels).permute(0, 3, 1, 2)
 
 

@@ -163,15 +163,26 @@ class GEGLU(nn.Module):
         return h * F.gelu(gate)
 
 
+def _accepts_residual(m) -> bool:
+    """LoRA sites add a residual in their own epilogue (``LoRALinear.forward(x, residual=...)``); plain modules do not."""
+    from .lora import _LoRABase
+    return isinstance(m, _LoRABase) and fused_enabled()
+
+
 class FeedForward(nn.Module):
     def __init__(self, dim: int):
         super().__init__()
         self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
 
-    def forward(self, x):
-        for m in self.net:
-            x = m(x)
-        return x
+    def forward(self, x, residual=None):
+        """``residual``: returns ``residual + net(x)`` -- the add goes into the last projection's epilogue when it is a LoRA site"""
+        x = self.net[1](self.net[0](x))
+        out = self.net[2]
+        if residual is None:
+            return out(x)
+        if _accepts_residual(out) and x.is_cuda:
+            return out(x, residual=residual)
+        return residual + out(x)
 
 
 class BasicTransformerBlock(nn.Module):
@@ -188,7 +199,7 @@ class BasicTransformerBlock(nn.Module):
         # residual add + the LayerNorm that follows it are one pass
         x, h = add_layer_norm(self.norm2, x, self.attn1(add_layer_norm(self.norm1, x)))
         x, h = add_layer_norm(self.norm3, x, self.attn2(h, context))
-        return x + self.ff(h)
+        return self.ff(h, residual=x)
 
 
 class Transformer2DModel(nn.Module):
@@ -210,9 +221,14 @@ class Transformer2DModel(nn.Module):
             y = self.proj_in(y).permute(0, 2, 3, 1).reshape(b, h * w, c)
         for blk in self.transformer_blocks:
             y = blk(y, context)
+        fuse = _accepts_residual(self.proj_out) and res.is_cuda       # the residual add in the projection's epilogue
         if self.linear_proj:
+            if fuse:
+                return self.proj_out(y, residual=res.permute(0, 2, 3, 1).reshape(b, h * w, c)).reshape(b, h, w, c).permute(0, 3, 1, 2)
             y = self.proj_out(y).reshape(b, h, w, c).permute(0, 3, 1, 2)
         else:
+            if fuse:
+                return self.proj_out(y.reshape(b, h, w, c).permute(0, 3, 1, 2), residual=res)
             y = self.proj_out(y.reshape(b, h, w, c).permute(0, 3, 1, 2))
         return y + res
 

@@ -408,7 +408,7 @@ GEGLU_CASES = [(32768, 320, 1280, 16), (8192, 640, 2560, 16), (2048, 1280, 5120,
 
 
 @pytest.mark.parametrize("M,K,I,rank", GEGLU_CASES, ids=[f"{m}x{k}x2*{i}-r{r}" for m, k, i, r in GEGLU_CASES])
-def test_geglu_epilogue_equals_projection_then_geglu(sdt_lib, M, K, I, rank):
+def test_geglu_epilogue_equals_projection_then_geglu(sdt_lib, M, K, I, rank, monkeypatch):
     """ff.net.0.proj with the GEGLU activation formed in the GEMM's epilogue: bit-identical to the projection
     launch followed by the GEGLU kernel (same rounded proj values go into the same arithmetic), equal to the fp64 oracle
     ``h * gelu(gate)`` of the reference expression within the bf16 bound, same gradients."""
@@ -418,6 +418,8 @@ def test_geglu_epilogue_equals_projection_then_geglu(sdt_lib, M, K, I, rank):
     g = torch.Generator(device=DEV).manual_seed(M + I)
     x = torch.randn(M, K, device=DEV, generator=g).bfloat16()
     dact = torch.randn(M, I, device=DEV, generator=g).bfloat16()
+    assert not geglu_projection_supported(ours, x)          # opt-in: measured slower than the two launches (profiles/)
+    monkeypatch.setenv("SDT_FUSED_GEGLU", "1")
     assert geglu_projection_supported(ours, x)
     xa = x.clone().requires_grad_(True)
     act = geglu_projection(ours, xa)
@@ -436,3 +438,31 @@ def test_geglu_epilogue_equals_projection_then_geglu(sdt_lib, M, K, I, rank):
     h, gate = proj.chunk(2, dim=-1)
     act_ref = h * torch.nn.functional.gelu(gate)
     assert rel(act[rows.to(DEV)], act_ref) <= 2e-2, rel(act[rows.to(DEV)], act_ref)
+
+
+@pytest.mark.parametrize("M,K,N,rank,dtype", [(32768, 1280, 320, 16, torch.bfloat16), (8192, 640, 640, 16, torch.bfloat16),
+                                              (1000, 2560, 640, 64, torch.bfloat16), (100, 320, 320, 4, torch.bfloat16),
+                                              (2048, 5120, 1280, 16, torch.float16)])
+def test_residual_added_in_the_epilogue(sdt_lib, M, K, N, rank, dtype):
+    """``proj(x) + residual`` (ff.net.2 / proj_out and the block's residual stream) with the add in the projection's epilogue:
+    the bits of the projection launch followed by torch's add, gradient of the residual = gradient of the output, and the oracle
+    expression within the bf16 / fp16 bound."""
+    ref, ours = make_pair("linear", K, N, rank, rank, True, 4, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    x = torch.randn(M, K, device=DEV, generator=g).to(dtype)
+    res = torch.randn(M, N, device=DEV, generator=g).to(dtype)
+    dy = torch.randn(M, N, device=DEV, generator=g).to(dtype)
+    xa, ra = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    ya = ours(xa, residual=ra)
+    ya.backward(dy)
+    gA, gB = ours.lora_A.grad.clone(), ours.lora_B.grad.clone()
+    ours.lora_A.grad = ours.lora_B.grad = None
+    xb, rb = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    yb = ours(xb) + rb
+    yb.backward(dy)
+    assert torch.equal(ya, yb)
+    assert torch.equal(xa.grad, xb.grad) and torch.equal(ra.grad, rb.grad) and torch.equal(ra.grad, dy)
+    assert torch.equal(gA, ours.lora_A.grad) and torch.equal(gB, ours.lora_B.grad)
+    rows = torch.randperm(M, generator=torch.Generator().manual_seed(2))[:256]
+    yr = ref(x[rows.to(DEV)].double().cpu()) + res[rows.to(DEV)].double().cpu()
+    assert rel(ya[rows.to(DEV)], yr) <= 2e-2
