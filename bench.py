@@ -324,7 +324,7 @@ def build_trainer(wl: dict, device, exchange):
 
 def site_flops(records):
     # one record per lora_gemm* launch; G = same-shape projections computed by that launch (grouped q/k/v, k/v)
-    fwd = sum(G * (2.0 * M * K * N + 2.0 * M * R * (K + N)) for kind, M, K, N, R, G, *_ in records if kind == "fwd")
+    fwd = sum(G * (2.0 * M * K * N + 2.0 * M * R * (K + N)) for kind, M, K, N, R, G, *_ in records if kind.startswith("fwd"))
     bwd = sum(G * ((2.0 * M * K * N if dx else 0.0) + 4.0 * M * R * (K + N)) for kind, M, K, N, R, G, dx, *_ in records if kind == "bwd")
     return fwd, bwd
 
@@ -566,7 +566,7 @@ def ours_main(args):
         allreduce_us = {"launches": len(nccl), "raw_us": sum(k[2] for k in nccl), "exclusive_us": sum(k[1] for k in nccl)} if nccl else None
         step_kernel_us = sum(k[1] for k in ks)
     if rank == 0 and rec:
-        fwd_sites = [r for r in rec if r[0] == "fwd"]
+        fwd_sites = [r for r in rec if r[0].startswith("fwd")]
         bwd_sites = [r for r in rec if r[0] == "bwd"]
         n_fwd = len(fwd_sites)
         timing = "cuda_events (eager step)"
@@ -586,15 +586,18 @@ def ours_main(args):
         # per-shape view of the same forward launches: which bound applies to which class of site
         shapes_acc = {}
         for (kind, M, K, N, R, G, *_), sec in zip(fwd_sites, fwd_t):
-            e = shapes_acc.setdefault((M, K, N, R, G), [0, 0.0])
+            e = shapes_acc.setdefault((M, K, N, R, G, kind == "fwd+res"), [0, 0.0])
             e[0] += 1
             e[1] += sec
         by_shape = []
-        for (M, K, N, R, G), (cnt, sec) in sorted(shapes_acc.items(), key=lambda kv: -kv[1][1]):
+        for (M, K, N, R, G, with_res), (cnt, sec) in sorted(shapes_acc.items(), key=lambda kv: -kv[1][1]):
             fl = G * (2.0 * M * K * N + 2.0 * M * R * (K + N))
             by = 2.0 * (M * K + G * (K * N + R * (K + N) + M * N + M * R))      # a grouped launch reads its shared X once
+            if with_res:
+                by += 2.0 * M * N                                                # the residual tile read by the epilogue
             tf, gbs = fl * cnt / sec / 1e12, by * cnt / sec / 1e9
-            by_shape.append({"M": M, "K": K, "N": N, "R": R, "projections_per_launch": G, "launches": cnt, "avg_us": 1e6 * sec / cnt, "tflops": tf,
+            by_shape.append({"M": M, "K": K, "N": N, "R": R, "projections_per_launch": G, "residual_in_epilogue": with_res,
+                             "launches": cnt, "avg_us": 1e6 * sec / cnt, "tflops": tf,
                              "frac_tensor": tf / peaks["tf_sustained"], "algorithmic_gbs": gbs, "frac_hbm": gbs / peaks["hbm"],
                              "bound": "tensor" if fl / by > peaks["tf_sustained"] * 1e3 / peaks["hbm"] else "hbm"})
         # DRAM bytes per GEMM launch from the committed ncu pass over one training step (dram__bytes_read + write summed over
@@ -611,7 +614,10 @@ def ours_main(args):
                 traffic = sum((v["dram_read_MB"] + v["dram_write_MB"]) * 1e6 for v in gl) / sum(v["launches"] for v in gl)
                 traffic_src = f"profiles/{tname} (avg over the forward + dX GEMM launches of a step)"
                 break
-        alg_bytes = sum(2.0 * (M * K + G * (K * N + R * (K + N) + M * N + M * R)) for kind, M, K, N, R, G, *_ in fwd_sites) / max(n_fwd, 1)
+        alg_bytes = sum(2.0 * (M * K + G * (K * N + R * (K + N) + M * N + M * R)) + (2.0 * M * N if kind == "fwd+res" else 0.0)
+                        for kind, M, K, N, R, G, *_ in fwd_sites) / max(n_fwd, 1)
+        n_res = sum(1 for r in fwd_sites if r[0] == "fwd+res")
+        res_bytes = sum(4.0 * r[1] * r[3] for r in fwd_sites if r[0] == "fwd+res")          # bytes the separate add would move on top
         dx_flops = sum(G * (2.0 * M * K * N + 2.0 * M * R * (K + N)) for kind, M, K, N, R, G, dx, *_ in bwd_sites if dx) + \
             sum(G * 2.0 * M * R * N for kind, M, K, N, R, G, dx, *_ in bwd_sites if not dx)
         backward = {"kernels": "lora_gemm* (dX, G) + lora_wgrad_kernel (dA and dB of up to 16 sites per launch)", "timing": "cuda_events (eager step)",
@@ -633,6 +639,11 @@ def ours_main(args):
                 "raw_cupti_seconds_per_step": fwd_raw,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peaks["source"] + ", sustained bf16",
                 "launches_timed": n_fwd, "avg_launch_us": 1e6 * t_fwd / max(n_fwd, 1),
+                "launches_with_residual_epilogue": n_res,
+                "note": (f"{n_res} of the {n_fwd} forward launches also add the block's residual stream in their epilogue (ff.net.2, proj_out): "
+                         f"their time contains the residual read, the FLOP count does not; the torch adds they replace moved "
+                         f"{res_bytes / 1e6:.0f} MB more per step.  SDT_FUSED_RESIDUAL=0 gives the plain-GEMM figure "
+                         "(profiles/README.md: 0.577 on the same code)") if n_res else None,
                 "flops_per_step": f_fwd, "forward_gemm_seconds_per_step": t_fwd,
                 "backward": backward, "by_shape": by_shape, "elementwise": elementwise_roofline(device, peaks)}
     elif rank == 0 and ks is not None:

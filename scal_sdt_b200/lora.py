@@ -122,7 +122,7 @@ class _LoRAProjection(torch.autograd.Function):
                                                lora_A.data_ptr(), lora_B.data_ptr(), mod.scaling, y.data_ptr(),
                                                t_save.data_ptr(), M, K, N, r, code, st), "sdt_lora_linear_fwd")
         if ev0 is not None:
-            PROFILE.append(("fwd", M, K, N, ops.R, 1, ev0, _ev()))
+            PROFILE.append(("fwd+res" if res2 is not None else "fwd", M, K, N, ops.R, 1, ev0, _ev()))
         ctx.mod = mod
         ctx.code = code
         ctx.need_dx = x2.requires_grad

@@ -165,8 +165,10 @@ class GEGLU(nn.Module):
 
 def _accepts_residual(m) -> bool:
     """LoRA sites add a residual in their own epilogue (``LoRALinear.forward(x, residual=...)``); plain modules do not."""
+    import os
+
     from .lora import _LoRABase
-    return isinstance(m, _LoRABase) and fused_enabled()
+    return isinstance(m, _LoRABase) and fused_enabled() and os.environ.get("SDT_FUSED_RESIDUAL", "1") != "0"
 
 
 class FeedForward(nn.Module):

@@ -29,17 +29,20 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(batches[0])
     torch.cuda.synchronize()
-evs = [e for e in prof.events() if str(getattr(e, "device_type", "")).endswith("CUDA")]
-agg = collections.defaultdict(lambda: [0, 0.0])
-t0 = min(e.time_range.start for e in evs)
-t1 = max(e.time_range.end for e in evs)
-busy = 0.0
-for e in evs:
-    d = e.time_range.end - e.time_range.start
-    a = agg[e.name[:110]]
+evs = [e for e in prof.events() if str(getattr(e, "device_type", "")).endswith("CUDA") and e.time_range.end > e.time_range.start]
+# Under programmatic dependent launch a kernel is resident while its predecessor drains, so raw durations overlap; the time a
+# kernel ADDS to the step is its exclusive time on the timeline (bench.exclusive_durations)
+ks = sorted(((e.name, e.time_range.start, e.time_range.end - e.time_range.start) for e in evs), key=lambda k: k[1])
+agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+t0 = min(k[1] for k in ks)
+t1 = max(k[1] + k[2] for k in ks)
+for name, excl, raw in bench.exclusive_durations(ks):
+    a = agg[name[:110]]
     a[0] += 1
-    a[1] += d
-    busy += d
-print(f"graph={graph} events={len(evs)} span={1e-3 * (t1 - t0):.2f} ms  sum of kernel durations={1e-3 * busy:.2f} ms")
-for name, (n, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
-    print(f"{1e-3 * d:8.3f} ms {n:5d} x {d / n:8.1f} us  {name}")
+    a[1] += excl
+    a[2] += raw
+print(f"graph={graph} events={len(ks)} span={1e-3 * (t1 - t0):.2f} ms  exclusive kernel time={1e-3 * sum(a[1] for a in agg.values()):.2f} ms  "
+      f"(sum of raw durations {1e-3 * sum(a[2] for a in agg.values()):.2f} ms)")
+print("  exclusive ms  launches   avg excl us   (raw ms)  kernel")
+for name, (n, d, raw) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+    print(f"{1e-3 * d:8.3f} ms {n:5d} x {d / n:8.1f} us  ({1e-3 * raw:7.3f})  {name}")
