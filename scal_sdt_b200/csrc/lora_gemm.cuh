@@ -32,7 +32,14 @@ struct GemmGroup {
   const float* bias[G];
   __nv_bfloat16* t_out[G];
   const uint8_t* res[G];       // residual stream added in the epilogue, or null
+  // mixed-width launches (PairParams::mixed): output width of every problem and the prefix of its column tiles
+  int n[G];
+  int tile_begin[G + 1];
 };
+
+// Problems of ONE (M, K, rank) but different output widths in one launch: to_k / to_v of every cross-attention of the UNet read
+// the same text context (616 x 768) and project it to 320 / 640 / 1280 columns
+constexpr int kMaxMixed = 32;
 
 // entry points (lora_gemm.cu / lora_gemm2.cu)
 // (the names say bf16 for history: `f16` selects IEEE fp16 operands and outputs on the same kernels)
@@ -45,6 +52,11 @@ int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scali
 bool lora_gemm_pair_sum_supported(int n_src, int64_t M, int64_t K, int64_t N, int r);
 int lora_gemm_pair_sum_bf16(const LoraProblem* probs, int n_src, float scaling, int64_t M, int64_t K, int64_t N, int r, bool f16,
                             cudaStream_t st);
+
+// mixed output widths (one X, many projections): see lora_gemm2.cu
+bool lora_gemm_pair_mixed_supported(int n_probs, int64_t M, int64_t K, const int64_t* Ns, int r);
+int lora_gemm_pair_mixed_bf16(const LoraProblem* probs, const int64_t* Ns, int n_probs, float scaling, int64_t M, int64_t K, int r,
+                              bool f16, cudaStream_t st);
 
 // GEGLU epilogue (ff.net.0.proj): see lora_gemm2.cu
 bool lora_gemm_pair_geglu_supported(int64_t M, int64_t K, int64_t I, int r);

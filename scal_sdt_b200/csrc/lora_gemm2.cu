@@ -149,24 +149,38 @@ struct PairParams {
   // I + [nt HN, (nt+1) HN); besides proj (y, for the backward) the epilogue writes act = h * gelu(gate) [M, I]
   int geglu_I;
   uint8_t* act_out;
+  int mixed;              // problems have their own output width (GemmGroup::n / tile_begin); one column tile per work item
   long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
 };
 
-// item -> (problem, 256-row tile index, n-group); consecutive items share the row tile (see lora_gemm.cu)
-struct PairItem { int prob, mt, g; };
+// item -> (problem, 256-row tile index, n-group); consecutive items share the row tile (see lora_gemm.cu).  N / n_tiles are the
+// problem's own in a mixed-width launch, the launch's otherwise.
+struct PairItem { int prob, mt, g, N, n_tiles; };
 template <int G>
-__device__ __forceinline__ PairItem decode_pair_item(int item, const PairParams& p) {
+__device__ __forceinline__ PairItem decode_pair_item(int item, const PairParams& p, const GemmGroup<G>& gm) {
   PairItem c;
+  c.N = p.N;
+  c.n_tiles = p.n_tiles;
   if (G == 1) {
     c.prob = 0;
     c.mt = item / p.n_groups;
     c.g = item % p.n_groups;
-  } else {
+  } else if (p.mixed == 0) {
     const int per_m = p.n_probs * p.n_groups;
     c.mt = item / per_m;
     const int rem = item - c.mt * per_m;
     c.prob = rem / p.n_groups;
     c.g = rem - c.prob * p.n_groups;
+  } else {
+    const int per_m = gm.tile_begin[p.n_probs];
+    c.mt = item / per_m;
+    const int rem = item - c.mt * per_m;
+    int q = 0;
+    while (q + 1 < p.n_probs && rem >= gm.tile_begin[q + 1]) ++q;
+    c.prob = q;
+    c.g = rem - gm.tile_begin[q];
+    c.N = gm.n[q];
+    c.n_tiles = gm.tile_begin[q + 1] - gm.tile_begin[q];
   }
   return c;
 }
@@ -263,11 +277,11 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
       const uint32_t lb_full_leader = map_to_rank(lb_full, 0);
       uint32_t it = 0, tile_ctr = 0;
       for (int item = pair_id; item < p.n_items; item += n_pairs) {
-        const PairItem ic = decode_pair_item<G>(item, p);
+        const PairItem ic = decode_pair_item<G>(item, p, gm);
         const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
         const int g = ic.g;
         const int nt0 = g * p.group_size;
-        const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+        const int nt1 = min(nt0 + p.group_size, ic.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
           // rows of W / lora-up this CTA contributes to the tile.  cta_group::2 runs the N index over CTA 0's rows, then CTA 1's:
@@ -342,9 +356,10 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
       };
 
       for (int item = pair_id; item < p.n_items; item += n_pairs) {
-        const int g = decode_pair_item<G>(item, p).g;
+        const PairItem ic = decode_pair_item<G>(item, p, gm);
+        const int g = ic.g;
         const int nt0 = g * p.group_size;
-        const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+        const int nt1 = min(nt0 + p.group_size, ic.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
           const uint32_t buf = tile_ctr & 1;
@@ -415,19 +430,19 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
     uint32_t tile_ctr = 0, first_ctr = 0;
     if (has_tail) {
       for (int item = pair_id; item < p.n_items; item += n_pairs) {
-        const PairItem ic = decode_pair_item<G>(item, p);
+        const PairItem ic = decode_pair_item<G>(item, p, gm);
         const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
         const int g = ic.g;
         const float* bias = gm.bias[ic.prob];
         const int nt0 = g * p.group_size;
-        const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+        const int nt1 = min(nt0 + p.group_size, ic.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
           if (has_bias) {
             if (tile_ctr > 0) mbar_wait(lb_empty, (tile_ctr - 1) & 1);
             const int n0 = GEGLU ? nt * C::HN + (int)rank * p.geglu_I : nt * C::BN + (int)rank * C::HN;
             for (int n = tid; n < C::HN; n += 128) {
-              const float b = (n0 + n < p.N) ? __ldg(bias + n0 + n) : 0.f;
+              const float b = (n0 + n < ic.N) ? __ldg(bias + n0 + n) : 0.f;
               const float hi = round_act(b, f16);
               *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) = make_uint4(pack_act2(hi, b - hi, f16), 0u, 0u, 0u);
             }
@@ -485,13 +500,13 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
     uint32_t acc_empty_leader[2] = {map_to_rank(&acc_empty[0], 0), map_to_rank(&acc_empty[1], 0)};
     uint32_t tile_ctr = 0;
     for (int item = pair_id; item < p.n_items; item += n_pairs) {
-      const PairItem ic = decode_pair_item<G>(item, p);
+      const PairItem ic = decode_pair_item<G>(item, p, gm);
       const int m0 = ic.mt * 2 * C::BM + (int)rank * C::BM;
       const int g = ic.g;
       uint8_t* yp = gm.y[ic.prob];
       const uint8_t* rp = S > 1 ? nullptr : gm.res[ic.prob];
       const int nt0 = g * p.group_size;
-      const int nt1 = min(nt0 + p.group_size, p.n_tiles);
+      const int nt1 = min(nt0 + p.group_size, ic.n_tiles);
       for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
         const uint32_t buf = tile_ctr & 1;
         const int n0 = nt * C::BN;
@@ -499,7 +514,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
         if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(48 + 2 * tile_ctr);
         tc_fence_after();
-        const int n_sub = GEGLU ? C::BN / 32 : min(C::BN / 32, (p.N - n0 + 31) / 32);      // GEGLU: I % HN == 0, tiles are full
+        const int n_sub = GEGLU ? C::BN / 32 : min(C::BN / 32, (ic.N - n0 + 31) / 32);     // GEGLU: I % HN == 0, tiles are full
         uint32_t v[32];
         // 32 output columns of this tile -> registers: one TMEM load, or two 16-column loads where the block straddles the gap of
         // a merged first tile (HN is a multiple of 16, so a half never straddles it)
@@ -587,7 +602,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             // Phase 2: stream the staged blocks out (full 128-byte lines); the next tile's phase 1 follows in program order
             slot = 0;
             for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot)
-              write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * min(2, n_sub - 2 * cb), rp, f16);
+              write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, ic.N, 4 * min(2, n_sub - 2 * cb), rp, f16);
           }
           __syncwarp();
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(70 + tile_ctr);
@@ -602,7 +617,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
               stage_row_chunk(stg, lane, h, pk);
             }
             __syncwarp();
-            write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, p.N, 4 * subs, rp, f16);
+            write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, ic.N, 4 * subs, rp, f16);
             __syncwarp();
           }
           tc_fence_before();
@@ -672,8 +687,12 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
     gm.bias[q] = pr.bias;
     gm.t_out[q] = reinterpret_cast<__nv_bfloat16*>(pr.t_out);
     gm.res[q] = reinterpret_cast<const uint8_t*>(pr.res);
+    gm.n[q] = (int)N;
+    gm.tile_begin[q] = 0;
   }
+  gm.tile_begin[G] = 0;
   PairParams p;
+  p.mixed = 0;
   p.scaling = scaling;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.n_probs = S > 1 ? 1 : n_probs;
@@ -727,6 +746,93 @@ int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scali
   if (bn160) { SDT_PAIR_R(160, kMaxGroup) } else { SDT_PAIR_R(128, kMaxGroup) }
 #undef SDT_PAIR_R
 #undef SDT_PAIR
+}
+
+// Mixed output widths: n_probs projections of ONE (M, K, padded rank) with their own N_q -- to_k / to_v of every cross-attention of
+// the UNet on the text context (SD1.5: 32 projections of the 616 x 768 context to 320 / 640 / 1280 columns).  Work items are
+// (row tile, problem, column tile); eight launches of 9-15 us at 5-25 % of the tensor peak become one.
+bool lora_gemm_pair_mixed_supported(int n_probs, int64_t M, int64_t K, const int64_t* Ns, int r) {
+  if (n_probs < 1 || n_probs > kMaxMixed || !(r == 16 || r == 32 || r == 64) || M < 256 || K < 256 || K % 8 != 0) return false;
+  for (int q = 0; q < n_probs; ++q)
+    if (Ns[q] <= 0 || Ns[q] % 8 != 0 || Ns[q] >= (1ll << 31)) return false;
+  return true;
+}
+
+template <int R>
+static int launch_pair_mixed(const LoraProblem* probs, const int64_t* Ns, int n_probs, float scaling, int64_t M, int64_t K, bool f16,
+                             cudaStream_t st) {
+  constexpr int BN = 160, G = kMaxMixed;
+  using C = PairCfg<BN, R, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R, G, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  static thread_local GemmGroup<G> gm;           // ~18 KB of tensor maps: not on the caller's stack
+  int tiles = 0;
+  for (int q = 0; q < G; ++q) {
+    const int qq = q < n_probs ? q : 0;
+    const LoraProblem& pr = probs[qq];
+    const int64_t N = Ns[qq];
+    int rc = make_tmap_2d_bf16(&gm.x[q], pr.x, M, K, K * 2, C::BM, C::BK, TMAP_SW_128);
+    if (rc != SDT_OK) return rc;
+    rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);
+    if (rc != SDT_OK) return rc;
+    rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
+    if (rc != SDT_OK) return rc;
+    rc = make_tmap_2d_bf16(&gm.lb[q], pr.lb, N, R, (uint64_t)R * 2, C::HN, R, R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
+    if (rc != SDT_OK) return rc;
+    gm.y[q] = reinterpret_cast<uint8_t*>(pr.y);
+    gm.bias[q] = pr.bias;
+    gm.t_out[q] = reinterpret_cast<__nv_bfloat16*>(pr.t_out);
+    gm.res[q] = reinterpret_cast<const uint8_t*>(pr.res);
+    gm.n[q] = (int)N;
+    gm.tile_begin[q] = tiles;
+    if (q < n_probs) tiles += (int)((N + BN - 1) / BN);
+  }
+  gm.tile_begin[G] = tiles;
+  for (int q = n_probs; q <= G; ++q) gm.tile_begin[q] = tiles;
+  PairParams p;
+  p.mixed = 1;
+  p.scaling = scaling;
+  p.M = (int)M; p.N = 0; p.K = (int)K;
+  p.n_probs = n_probs;
+  p.n_src = 1;
+  p.has_bias = probs[0].bias != nullptr ? 1 : 0;
+  p.f16 = f16 ? 1 : 0;
+  p.geglu_I = 0;
+  p.act_out = nullptr;
+  p.trace = reinterpret_cast<long long*>(debug_get(10));
+  const int m_tiles = (int)((M + 2 * C::BM - 1) / (2 * C::BM));
+  p.n_tiles = 0;
+  p.group_size = 1;
+  p.n_groups = 0;
+  p.n_items = m_tiles * tiles;
+  const int pairs_max = num_sms() / 2;
+  const int pairs = p.n_items < pairs_max ? p.n_items : pairs_max;
+  SDT_CUDA_OK(launch_kernel(lora_gemm_pair_kernel<BN, R, G, 1, false>, dim3(2 * pairs), dim3(kPairThreads), C::SMEM_BYTES, st, true, gm, p));
+  SDT_LAUNCH_OK("lora_gemm_pair(mixed)");
+  return SDT_OK;
+}
+
+int lora_gemm_pair_mixed_bf16(const LoraProblem* probs, const int64_t* Ns, int n_probs, float scaling, int64_t M, int64_t K, int r,
+                              bool f16, cudaStream_t st) {
+  SDT_REQUIRE(probs != nullptr && Ns != nullptr && lora_gemm_pair_mixed_supported(n_probs, M, K, Ns, r), SDT_ERR_UNSUPPORTED,
+              "lora_gemm(mixed): needs 1..%d problems, padded rank 16/32/64, M >= 256, K >= 256 (got %d problems, r=%d, M=%lld, K=%lld)",
+              kMaxMixed, n_probs, r, (long long)M, (long long)K);
+  for (int q = 0; q < n_probs; ++q) {
+    const LoraProblem& pr = probs[q];
+    SDT_REQUIRE(pr.x && pr.w && pr.la && pr.lb && pr.y && pr.t_out, SDT_ERR_ARG, "lora_gemm(mixed): null pointer in problem %d", q);
+    SDT_REQUIRE((pr.bias != nullptr) == (probs[0].bias != nullptr), SDT_ERR_ARG,
+                "lora_gemm(mixed): the problems of one launch must all have a bias or all have none");
+    SDT_REQUIRE(aligned16(pr.x) && aligned16(pr.w) && aligned16(pr.la) && aligned16(pr.lb) && aligned16(pr.y) && aligned16(pr.t_out) &&
+                    aligned16(pr.res), SDT_ERR_ARG, "lora_gemm(mixed): pointers must be 16-byte aligned (problem %d)", q);
+  }
+  switch (r) {
+    case 16: return launch_pair_mixed<16>(probs, Ns, n_probs, scaling, M, K, f16, st);
+    case 32: return launch_pair_mixed<32>(probs, Ns, n_probs, scaling, M, K, f16, st);
+    default: return launch_pair_mixed<64>(probs, Ns, n_probs, scaling, M, K, f16, st);
+  }
 }
 
 // GEGLU epilogue (ff.net.0.proj): proj [M, 2I] = X W^T + b + s (X A^T) B^T  AND  act [M, I] = proj[:, :I] * gelu(proj[:, I:]) from ONE
