@@ -322,6 +322,19 @@ def build_trainer(wl: dict, device, exchange):
     return tr
 
 
+def expand_multi(records):
+    """a mixed-width launch (("fwd_multi", M, K, [N...], R, n, ev0, ev1)) counts as ONE timed launch; its FLOPs / bytes are the sums
+    over its projections: rewritten as ("fwd", M, K, N_total, R, 1, ...) with the shared X read once (N_total = sum of widths)"""
+    out = []
+    for r in records:
+        if r[0] == "fwd_multi":
+            kind, M, K, Ns, R, n, *rest = r
+            out.append(("fwd*", M, K, int(sum(Ns)), R, 1, *rest))        # (the n - 1 extra rank-down products are not counted)
+        else:
+            out.append(r)
+    return out
+
+
 def site_flops(records):
     # one record per lora_gemm* launch; G = same-shape projections computed by that launch (grouped q/k/v, k/v)
     fwd = sum(G * (2.0 * M * K * N + 2.0 * M * R * (K + N)) for kind, M, K, N, R, G, *_ in records if kind.startswith("fwd"))
@@ -554,7 +567,7 @@ def ours_main(args):
     lora_mod.PROFILE = [] if rank == 0 else None
     tr.step(prof_batch)
     torch.cuda.synchronize()
-    rec = lora_mod.PROFILE or []
+    rec = expand_multi(lora_mod.PROFILE or [])
     lora_mod.PROFILE = None
     ks = None
     try:

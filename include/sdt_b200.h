@@ -85,6 +85,17 @@ typedef struct {
 int sdt_lora_linear_fwd_group(const sdt_lora_problem* problems /* host */, int n_problems, float scaling,
                               int64_t M, int64_t K, int64_t N, int r, int dtype, void* stream);
 
+/* ---- K1 (one input, many widths): up to SDT_MAX_MULTI projections of ONE (M, K, padded rank) with their own output width ----
+ * to_k / to_v of EVERY cross-attention of the UNet read the same frozen text context (SD1.5: 32 projections of the 616 x 768
+ * context to 320 / 640 / 1280 columns): one launch whose work items are (row tile, problem, column tile) instead of eight launches
+ * of 9-15 us at 5-25 % of the tensor peak.  Ns[q] = output width of problem q (HOST array); x may be shared; every problem has a
+ * bias or none has.  Needs M >= 256, K >= 256 (sdt_lora_linear_fwd_multi_supported); SDT_BF16 / SDT_F16.
+ */
+#define SDT_MAX_MULTI 32
+int sdt_lora_linear_fwd_multi_supported(int n_problems, int64_t M, int64_t K, const int64_t* Ns /* host */, int r);
+int sdt_lora_linear_fwd_multi(const sdt_lora_problem* problems /* host */, const int64_t* Ns /* host */, int n_problems,
+                              float scaling, int64_t M, int64_t K, int r, int dtype, void* stream);
+
 /* ---- K1 + GEGLU epilogue: ff.net.0.proj and the activation that follows it, one launch ------------------
  * diffusers GEGLU.forward: proj = self.proj(x); h, gate = proj.chunk(2, -1); return h * gelu(gate) -- with self.proj a LoRA site
  * (configs/optim_targets/lora.yaml:23-27).  w [2I,K], bias [2I], B [2I,r] in their reference row order ([h rows ; gate rows]).

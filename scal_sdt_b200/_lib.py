@@ -40,6 +40,7 @@ class WgradSite(ctypes.Structure):
 
 
 MAX_GROUP = 4
+MAX_MULTI = 32
 
 
 class Chunk(ctypes.Structure):
@@ -56,6 +57,8 @@ SIGNATURES = {
                                     c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sdt_lora_linear_fwd_res": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                         c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "sdt_lora_linear_fwd_multi_supported": (c_int, [c_int, c_int64, c_int64, c_void_p, c_int]),
+    "sdt_lora_linear_fwd_multi": (c_int, [c_void_p, c_void_p, c_int, c_float, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sdt_lora_linear_geglu_supported": (c_int, [c_int64, c_int64, c_int64, c_int]),
     "sdt_lora_linear_geglu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                           c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),

@@ -61,6 +61,18 @@ static int lora_linear_fwd_impl(const void* x, const void* w, const float* bias,
   return SDT_ERR_UNSUPPORTED;
 }
 
+extern "C" int sdt_lora_linear_fwd_multi_supported(int n_problems, int64_t M, int64_t K, const int64_t* Ns, int r) {
+  return (Ns != nullptr && lora_gemm_pair_mixed_supported(n_problems, M, K, Ns, r)) ? 1 : 0;
+}
+
+extern "C" int sdt_lora_linear_fwd_multi(const sdt_lora_problem* problems, const int64_t* Ns, int n_problems, float scaling, int64_t M,
+                                         int64_t K, int r, int dtype, void* stream) {
+  SDT_REQUIRE(problems != nullptr && Ns != nullptr, SDT_ERR_ARG, "sdt_lora_linear_fwd_multi: null pointer");
+  SDT_REQUIRE(dtype == SDT_BF16 || dtype == SDT_F16, SDT_ERR_UNSUPPORTED, "sdt_lora_linear_fwd_multi: bf16 / fp16 only (there is no fallback)");
+  return lora_gemm_pair_mixed_bf16(reinterpret_cast<const LoraProblem*>(problems), Ns, n_problems, scaling, M, K, r, dtype == SDT_F16,
+                                   (cudaStream_t)stream);
+}
+
 extern "C" int sdt_lora_linear_geglu_supported(int64_t M, int64_t K, int64_t I, int r) {
   return lora_gemm_pair_geglu_supported(M, K, I, r) ? 1 : 0;
 }

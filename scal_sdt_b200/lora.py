@@ -495,6 +495,88 @@ class _LoRAProjectionGroup(torch.autograd.Function):
         return (dx, None, *grads)
 
 
+class _LoRAProjectionMulti(torch.autograd.Function):
+    """Projections of ONE input with DIFFERENT output widths as the work items of one launch (``sdt_lora_linear_fwd_multi``):
+    to_k / to_v of every cross-attention of the UNet on the text context.  The input needs no gradient (frozen text
+    embeddings); the backward runs the rank projections G = s dY B of same-width sites as grouped launches and queues the dA / dB
+    reductions like every other site."""
+
+    @staticmethod
+    def forward(ctx, x2, mods, *lora_params):
+        lib = _lib.load()
+        M, K = x2.shape
+        n = len(mods)
+        code = _lib.dtype_code(x2.dtype)
+        ops = [m._packed_operands(x2.dtype) for m in mods]
+        R = ops[0].R
+        ys = [torch.empty(M, m.out_features, dtype=x2.dtype, device=x2.device) for m in mods]
+        ts = [torch.empty(M, R, dtype=x2.dtype, device=x2.device) for _ in mods]
+        probs = (_lib.LoraProblem * n)(*[
+            _lib.LoraProblem(x2.data_ptr(), m._weight_lp(x2.dtype).data_ptr(), _lib.ptr(m._bias_f32()), o.A_p.data_ptr(),
+                             o.B_p.data_ptr(), y.data_ptr(), t.data_ptr())
+            for m, o, y, t in zip(mods, ops, ys, ts)])
+        widths = (ctypes.c_int64 * n)(*[m.out_features for m in mods])
+        ev0 = _ev() if PROFILE is not None else None
+        _lib.check(lib.sdt_lora_linear_fwd_multi(ctypes.addressof(probs), ctypes.addressof(widths), n, mods[0].scaling, M, K, R, code,
+                                                 _lib.stream_ptr()), "sdt_lora_linear_fwd_multi")
+        if ev0 is not None:
+            PROFILE.append(("fwd_multi", M, K, [m.out_features for m in mods], R, n, ev0, _ev()))
+        ctx.mods = mods
+        ctx.save_for_backward(x2, *ts, *lora_params)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        mods = ctx.mods
+        n = len(mods)
+        saved = ctx.saved_tensors
+        x2, ts, lora_params = saved[0], saved[1:1 + n], saved[1 + n:]
+        code = _lib.dtype_code(x2.dtype)
+        grads = []
+        for g, (m, dy) in enumerate(zip(mods, dys)):
+            if dy is None:
+                grads += [None, None]
+                continue
+            _dx, dA, dB = _site_backward(m, code, x2, ts[g], lora_params[2 * g], lora_params[2 * g + 1], dy, False)
+            grads += [dA, dB]
+        return (None, None, *grads)
+
+
+def multi_projectable(mods, x2: torch.Tensor) -> bool:
+    """True when ``mods`` (LoRA Linear sites of one in-width, rank, scaling and bias-ness, any out-widths) can share ONE launch on
+    ``x2`` [M,K] that needs no gradient."""
+    if not (1 <= len(mods) <= _lib.MAX_MULTI) or not all(isinstance(m, LoRALinear) for m in mods):
+        return False
+    if not x2.is_cuda or x2.requires_grad or os.environ.get("SDT_MULTI_CONTEXT", "1") == "0":
+        return False
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x2.dtype
+    if dt not in (torch.bfloat16, torch.float16):
+        return False
+    m0 = mods[0]
+    if not all(m.in_features == m0.in_features and m.r == m0.r and m.scaling == m0.scaling and (m.bias is None) == (m0.bias is None)
+               and not (m.training and m.lora_dropout_p > 0.0) for m in mods):
+        return False
+    widths = (ctypes.c_int64 * len(mods))(*[m.out_features for m in mods])
+    return bool(_lib.load().sdt_lora_linear_fwd_multi_supported(len(mods), x2.shape[0], x2.shape[1], ctypes.addressof(widths),
+                                                                padded_rank(m0.r)))
+
+
+def project_multi(mods, x: torch.Tensor):
+    """``[m(x) for m in mods]`` for sites of different out-widths on one gradient-free input -- one launch
+    (``multi_projectable`` says when)."""
+    mods = list(mods)
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    _lib.require_cuda(x2, *(m.weight for m in mods))
+    _lib.device_check()
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x2.dtype
+    if x2.dtype != dt:
+        x2 = x2.to(dt)
+    params = [p for m in mods for p in (m.lora_A, m.lora_B)]
+    ys = _LoRAProjectionMulti.apply(x2.contiguous(), mods, *params)
+    return [y.view(*lead, m.out_features) for y, m in zip(ys, mods)]
+
+
 def groupable(mods, x2: torch.Tensor) -> bool:
     """True when ``mods`` can share one grouped launch on ``x2`` [M,K]: LoRA sites of one shape, rank, scaling and bias-ness,
     bf16 tensor-core path.  Anything else goes through the per-site launches (same kernels, one problem each)."""

@@ -375,6 +375,16 @@ class UNet2DConditionModel(nn.Module):
             a._kv_pre = None                      # never reuse a pair from an earlier (possibly interrupted) forward
             if ctx.is_cuda and isinstance(a.to_k, LoRALinear) and isinstance(a.to_v, LoRALinear):
                 by_width.setdefault(a.to_k.out_features, []).append(a)
+        from .lora import multi_projectable, project_multi
+        every = [a for attns in by_width.values() for a in attns]
+        sites = [p for a in every for p in (a.to_k, a.to_v)]
+        ctx2 = ctx.reshape(-1, ctx.shape[-1])
+        if sites and multi_projectable(sites, ctx2):
+            # ONE launch for to_k / to_v of every cross-attention of the UNet (different widths, same context)
+            outs = project_multi(sites, ctx)
+            for j, a in enumerate(every):
+                a._kv_pre = (outs[2 * j], outs[2 * j + 1])
+            return
         per = _lib.MAX_GROUP // 2
         for attns in by_width.values():
             for i in range(0, len(attns), per):
