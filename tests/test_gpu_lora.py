@@ -466,3 +466,28 @@ def test_residual_added_in_the_epilogue(sdt_lib, M, K, N, rank, dtype):
     rows = torch.randperm(M, generator=torch.Generator().manual_seed(2))[:256]
     yr = ref(x[rows.to(DEV)].double().cpu()) + res[rows.to(DEV)].double().cpu()
     assert rel(ya[rows.to(DEV)], yr) <= 2e-2
+
+
+@pytest.mark.parametrize("rank,bias,dtype", [(16, False, torch.bfloat16), (64, False, torch.bfloat16), (4, True, torch.float16)])
+def test_multi_width_projection_of_the_text_context(sdt_lib, rank, bias, dtype):
+    """to_k / to_v of every cross-attention on ONE text context as the work items of one launch (sdt_lora_linear_fwd_multi):
+    bit-identical to the per-site launches, gradients equal to the oracle's, the context itself gets no gradient."""
+    from scal_sdt_b200.lora import multi_projectable, project_multi
+    widths = [320, 320, 640, 640, 1280, 1280, 1280, 320, 640, 1280, 1280]
+    pairs = [make_pair("linear", 768, n, rank, rank, bias, 500 + i, torch.bfloat16) for i, n in enumerate(widths)]
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(8, 77, 768, generator=gen).bfloat16().float()
+    dys = [torch.randn(8, 77, n, generator=gen).bfloat16().float() for n in widths]
+    yrs = [ref(x.double()) for ref, _ in pairs]
+    torch.autograd.backward(yrs, [d.double() for d in dys])
+    mods = [ours for _, ours in pairs]
+    xo = x.to(DEV).to(dtype)
+    assert multi_projectable(mods, xo.reshape(-1, 768))
+    yos = project_multi(mods, xo)
+    torch.autograd.backward(yos, [d.to(DEV).to(dtype) for d in dys])
+    for g, n in enumerate(widths):
+        assert yos[g].shape == (8, 77, n) and yos[g].dtype == dtype
+        assert rel(yos[g], yrs[g]) <= 2e-2, ("y", g, rel(yos[g], yrs[g]))
+        assert torch.equal(mods[g](xo), yos[g]), f"multi-width launch differs from the single launch (site {g})"
+        assert rel(mods[g].lora_A.grad, pairs[g][0].lora_A.grad) <= 2e-2 and rel(mods[g].lora_B.grad, pairs[g][0].lora_B.grad) <= 2e-2, g
+    assert not multi_projectable(mods, xo.reshape(-1, 768).clone().requires_grad_(True))     # inputs that need dX go per site
