@@ -655,8 +655,7 @@ def ours_main(args):
                 "launches_with_residual_epilogue": n_res,
                 "note": (f"{n_res} of the {n_fwd} forward launches also add the block's residual stream in their epilogue (ff.net.2, proj_out): "
                          f"their time contains the residual read, the FLOP count does not; the torch adds they replace moved "
-                         f"{res_bytes / 1e6:.0f} MB more per step.  SDT_FUSED_RESIDUAL=0 gives the plain-GEMM figure "
-                         "(profiles/README.md: 0.577 on the same code)") if n_res else None,
+                         f"{res_bytes / 1e6:.0f} MB more per step (SDT_FUSED_RESIDUAL=1 is on)") if n_res else None,
                 "flops_per_step": f_fwd, "forward_gemm_seconds_per_step": t_fwd,
                 "backward": backward, "by_shape": by_shape, "elementwise": elementwise_roofline(device, peaks)}
     elif rank == 0 and ks is not None:

@@ -532,13 +532,44 @@ class _LoRAProjectionMulti(torch.autograd.Function):
         saved = ctx.saved_tensors
         x2, ts, lora_params = saved[0], saved[1:1 + n], saved[1 + n:]
         code = _lib.dtype_code(x2.dtype)
-        grads = []
+        lib = _lib.load()
+        M, K = x2.shape
+        R = mods[0]._packed_operands(x2.dtype).R
+        grads: list = [None] * (2 * n)
+        # same-width sites whose outputs all received a gradient go out MAX_GROUP at a time: their rank projections G = s dY B are
+        # the work items of one launch (sdt_lora_linear_bwd_group without dX); anything else per site
+        by_width: dict = {}
         for g, (m, dy) in enumerate(zip(mods, dys)):
-            if dy is None:
-                grads += [None, None]
-                continue
-            _dx, dA, dB = _site_backward(m, code, x2, ts[g], lora_params[2 * g], lora_params[2 * g + 1], dy, False)
-            grads += [dA, dB]
+            if dy is not None:
+                by_width.setdefault(m.out_features, []).append(g)
+        for N, idx in by_width.items():
+            for i in range(0, len(idx), _lib.MAX_GROUP):
+                chunk = idx[i:i + _lib.MAX_GROUP]
+                G = len(chunk)
+                direct = all(mods[g]._grad_A is not None for g in chunk)
+                if G < 2 or not direct or not lib.sdt_lora_linear_bwd_group_supported(G, 0, M, K, N, R):
+                    for g in chunk:
+                        _dx, dA, dB = _site_backward(mods[g], code, x2, ts[g], lora_params[2 * g], lora_params[2 * g + 1], dys[g], False)
+                        grads[2 * g], grads[2 * g + 1] = dA, dB
+                    continue
+                st = _lib.stream_ptr()
+                dcs = [dys[g].contiguous() if dys[g].dtype == x2.dtype else dys[g].to(x2.dtype).contiguous() for g in chunk]
+                gws = [torch.empty(M, R, dtype=x2.dtype, device=x2.device) for _ in chunk]
+                q = _wgrad_queue
+                probs = (_lib.LoraBwdProblem * G)(*[
+                    _lib.LoraBwdProblem(dc.data_ptr(), x2.data_ptr(), None, mods[g]._packed_operands(x2.dtype).At_p.data_ptr(),
+                                        mods[g]._packed_operands(x2.dtype).Bt_p.data_ptr(), ts[g].data_ptr(), gw.data_ptr(),
+                                        None if q is not None else mods[g]._grad_A.data_ptr(),
+                                        None if q is not None else mods[g]._grad_B.data_ptr())
+                    for g, dc, gw in zip(chunk, dcs, gws)])
+                ev0 = _ev() if PROFILE is not None else None
+                _lib.check(lib.sdt_lora_linear_bwd_group(ctypes.addressof(probs), G, mods[chunk[0]].scaling, None, M, K, N, R,
+                                                         mods[chunk[0]].r, code, _lib.wgrad_workspace(), st), "sdt_lora_linear_bwd_group")
+                if ev0 is not None:
+                    PROFILE.append(("bwd", M, K, N, R, G, False, ev0, _ev()))
+                if q is not None:
+                    for g, dc, gw in zip(chunk, dcs, gws):
+                        q.add(x2, gw, mods[g]._grad_A, dc, ts[g], mods[g]._grad_B, M, K, N, R, mods[g].r, code)
         return (None, None, *grads)
 
 

@@ -168,7 +168,9 @@ def _accepts_residual(m) -> bool:
     import os
 
     from .lora import _LoRABase
-    return isinstance(m, _LoRABase) and fused_enabled() and os.environ.get("SDT_FUSED_RESIDUAL", "1") != "0"
+    # Opt-in (SDT_FUSED_RESIDUAL=1): measured neutral on B200 (profiles/README.md: 28.60 vs 28.63 ms per step) -- the 32 torch adds
+    # it removes (0.19 ms) come back as residual reads inside store-bound epilogues (+0.15 ms of GEMM time)
+    return isinstance(m, _LoRABase) and fused_enabled() and os.environ.get("SDT_FUSED_RESIDUAL", "0") == "1"
 
 
 class FeedForward(nn.Module):
