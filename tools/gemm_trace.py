@@ -110,5 +110,5 @@ if len(sys.argv) > 2 and sys.argv[2] == "gs":
         run(32768, 2560, 320, 16)
     lib.sdt_debug_set(20, 0)
     sys.exit(0)
-for shape in [(32768, 320, 320, 16), (32768, 320, 2560, 16), (2048, 1280, 1280, 16), (8192, 640, 5120, 16)]:
+for shape in [(32768, 320, 320, 16), (8192, 640, 640, 16), (2048, 1280, 1280, 16), (32768, 320, 2560, 16), (8192, 640, 5120, 16)]:
     run(*shape)
