@@ -1,6 +1,7 @@
 """Aggregate an `ncu --csv` metric log of ONE training step into a per-kernel JSON summary (runs without a GPU).
 
-    ncu --profile-from-start off --clock-control none -k regex:sdt \
+    ncu --profile-from-start off --clock-control none \
+        -k "regex:lora_|gn_|ln_|geglu|residual_bias|adamw|ema_|mse_loss|noise_target" \
         --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
         --csv --log-file gpurun_out/r02_sdt_metrics.csv python bench.py --profile-step
     python tools/ncu_step_summary.py gpurun_out/r02_sdt_metrics.csv > profiles/r02_kernels_per_step_ncu.json
