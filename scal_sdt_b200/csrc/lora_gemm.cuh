@@ -28,7 +28,8 @@ constexpr int kMaxGroup = 4;
 template <int G>
 struct GemmGroup {
   CUtensorMap x[G], w[G], la[G], lb[G];
-  uint8_t* y[G];               // outputs are written straight from registers (no tensor map)
+  CUtensorMap ym[G];           // outputs as [32 rows x 32 columns] boxes, 64-byte swizzle (CTA-pair kernel: TMA stores)
+  uint8_t* y[G];               // outputs again, for the paths that store from registers (residual / GEGLU epilogues, single-CTA kernel)
   const float* bias[G];
   __nv_bfloat16* t_out[G];
   const uint8_t* res[G];       // residual stream added in the epilogue, or null

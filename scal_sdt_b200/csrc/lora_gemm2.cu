@@ -227,6 +227,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         prefetch_tmap(&gm.w[q]);
         if (R > 0) { prefetch_tmap(&gm.la[q]); prefetch_tmap(&gm.lb[q]); }
       }
+      for (int q = 0; q < (S > 1 || G == 1 ? 1 : p.n_probs); ++q) prefetch_tmap(&gm.ym[q]);
       for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 16); }
       mbar_init(t_full, 1);
@@ -534,6 +535,13 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           // Phase 1: drain this warp's share of the accumulator into its staging buffers and hand the TMEM buffer back at once.
           // Store-bound shapes (K = 320: 8x more bytes out than in per tile) spend ~3000 cycles per tile on the stores; holding
           // the accumulator that long left the MMA warp idle and the store stream with gaps (timeline in profiles/).
+          // Plain outputs leave through the TMA: each 32-column sub-block is staged as a [32 x 64 B] box in the 64-byte swizzle and
+          // one lane issues its store.  The warp never waits on the TPC's store port (with st.global a warp sat ~2000 cycles per
+          // tile in the issue of its stores, and the next accumulator waited for it); rows >= M and columns >= N are clipped by
+          // the tensor map.  Residual / GEGLU epilogues keep the [32 x 128 B] staging and the register stores below.
+          const bool tma_out = !GEGLU && rp == nullptr;
+          if (lane == 0) tma_store_wait_read();      // the previous tile's boxes have left the staging buffers
+          __syncwarp();
           int slot = 0;
           for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot) {
             const int subs = min(2, n_sub - 2 * cb);
@@ -541,13 +549,27 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
               load_sub(2 * cb + h);
               uint32_t pk[16];
               pack_acc32(v, pk, f16);
-              stage_row_chunk(stg + slot * 4096, lane, h, pk);
+              if (tma_out) stage_row_sw64(stg + slot * 4096 + h * 2048, lane, pk);
+              else         stage_row_chunk(stg + slot * 4096, lane, h, pk);
             }
           }
           tc_fence_before();
+          if (tma_out) fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) remote_arrive_relaxed(acc_empty_leader[buf]);
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(49 + 2 * tile_ctr);
+          if (tma_out) {
+            if (lane == 0) {
+              slot = 0;
+              for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot)
+                for (int h = 0; h < min(2, n_sub - 2 * cb); ++h)
+                  tma_store_2d(&gm.ym[ic.prob], stg + slot * 4096 + h * 2048, n0 + cb * 64 + h * 32, m0 + q * 32);
+              tma_store_commit();
+            }
+            __syncwarp();
+            if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(70 + tile_ctr);
+            continue;
+          }
           if constexpr (GEGLU) {
             // Phase 2 (GEGLU): act = h * gelu(gate) from the STAGED (already rounded) halves of the tile -- exactly what the unfused
             // sequence computes from proj in HBM.  h and gate of one output column sit in different 64-column blocks, i.e. in the
@@ -608,17 +630,31 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(70 + tile_ctr);
         } else {
           // one staging block per warp: stage and store block by block, release the accumulator after the last load
+          const bool tma_out = rp == nullptr;
           for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2) {
             const int subs = min(2, n_sub - 2 * cb);
+            if (lane == 0) tma_store_wait_read();    // the previous block's boxes have left the staging buffer
+            __syncwarp();
             for (int h = 0; h < subs; ++h) {
               load_sub(2 * cb + h);
               uint32_t pk[16];
               pack_acc32(v, pk, f16);
-              stage_row_chunk(stg, lane, h, pk);
+              if (tma_out) stage_row_sw64(stg + h * 2048, lane, pk);
+              else         stage_row_chunk(stg, lane, h, pk);
             }
-            __syncwarp();
-            write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, ic.N, 4 * subs, rp, f16);
-            __syncwarp();
+            if (tma_out) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                for (int h = 0; h < subs; ++h) tma_store_2d(&gm.ym[ic.prob], stg + h * 2048, n0 + cb * 64 + h * 32, m0 + q * 32);
+                tma_store_commit();
+              }
+              __syncwarp();
+            } else {
+              __syncwarp();
+              write_staged_block(stg, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, ic.N, 4 * subs, rp, f16);
+              __syncwarp();
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -627,6 +663,8 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         }
       }
     }
+    if (lane == 0) tma_store_wait_read();          // shared memory stays until the last boxes have been read out of it
+    __syncwarp();
     if (warp == 6 && lane == 0) SDT_TRACE2(62);
   }
 
@@ -675,6 +713,8 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
     rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);     // GEGLU: same map, rows addressed per CTA
     if (rc != SDT_OK) return rc;
     gm.y[q] = reinterpret_cast<uint8_t*>(S > 1 ? probs[0].y : pr.y);
+    rc = make_tmap_2d_bf16(&gm.ym[q], gm.y[q], M, N, N * 2, 32, 32, TMAP_SW_64);
+    if (rc != SDT_OK) return rc;
     if (R > 0) {
       rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
       if (rc != SDT_OK) return rc;
@@ -783,6 +823,8 @@ static int launch_pair_mixed(const LoraProblem* probs, const int64_t* Ns, int n_
     rc = make_tmap_2d_bf16(&gm.lb[q], pr.lb, N, R, (uint64_t)R * 2, C::HN, R, R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
     if (rc != SDT_OK) return rc;
     gm.y[q] = reinterpret_cast<uint8_t*>(pr.y);
+    rc = make_tmap_2d_bf16(&gm.ym[q], pr.y, M, N, N * 2, 32, 32, TMAP_SW_64);
+    if (rc != SDT_OK) return rc;
     gm.bias[q] = pr.bias;
     gm.t_out[q] = reinterpret_cast<__nv_bfloat16*>(pr.t_out);
     gm.res[q] = reinterpret_cast<const uint8_t*>(pr.res);

@@ -180,6 +180,24 @@ __device__ __forceinline__ void stage_row_chunk(uint32_t stg, int lane, int h, c
 #pragma unroll
   for (int j = 0; j < 4; ++j) st_shared_v4(row_base + (((4 * h + j) ^ (lane & 7)) << 4), pk + 4 * j);
 }
+// The same 32 values as one row of a [32 rows x 64 bytes] block in the 64-byte TMA swizzle (16-byte chunk j of row r at chunk
+// j ^ ((r >> 1) & 3)): what a tensor map with a 32-column box and SWIZZLE_64B reads.  Eight consecutive lanes cover eight distinct
+// 16-byte bank groups: conflict-free.
+__device__ __forceinline__ void stage_row_sw64(uint32_t stg, int lane, const uint32_t (&pk)[16]) {
+  const uint32_t row_base = stg + lane * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st_shared_v4(row_base + ((j ^ ((lane >> 1) & 3)) << 4), pk + 4 * j);
+}
+// TMA store of one box from (own) shared memory; completion is tracked by the thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int c_inner, int c_row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c_inner), "r"(c_row), "r"(src_smem)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every bulk group committed by this thread has finished READING shared memory (the buffers may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // a + b on four packed pairs of 16-bit values (bf16 or fp16), each sum rounded once: what torch's elementwise add of two
 // bf16 / fp16 tensors produces
 __device__ __forceinline__ uint32_t add_packed_pair(uint32_t a, uint32_t b, bool f16) {
