@@ -91,6 +91,14 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
       : "memory");
 }
 
+// the same, on the leader's barrier only
+__device__ __forceinline__ void umma2_commit_leader(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)1)
+      : "memory");
+}
+
 }  // namespace pair
 
 using namespace pair;
@@ -135,7 +143,7 @@ struct PairCfg {
   static_assert(W_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
 };
 
-constexpr int kPairThreads = 14 * 32;
+constexpr int kPairThreads = 15 * 32;      // producer, UMMA issuer, 4 side warps, 8 epilogue warps, tail issuer
 
 struct PairParams {
   float scaling;
@@ -208,7 +216,8 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
   uint64_t* t_ready = t_full + 1;              //            leader's (8 arrivals)
   uint64_t* lb_full = t_ready + 1;             //            leader's
   uint64_t* lb_empty = lb_full + 1;            //            both
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lb_empty + 1);
+  uint64_t* kdone = lb_empty + 1;              // [2]        leader's: every UMMA of the tile's K loop has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kdone + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
@@ -234,6 +243,8 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
       mbar_init(t_ready, 8);
       mbar_init(lb_full, 1);
       mbar_init(lb_empty, 1);
+      mbar_init(&kdone[0], 1);
+      mbar_init(&kdone[1], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -313,49 +324,17 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer (leader CTA only) =================================
+    // ===================================== UMMA issuer: K loops (leader CTA only) ========================
+    // Only the K loops: the tail of a tile (rank-R up-projection and bias, two or three UMMAs behind two or three barriers) is
+    // issued by its own warp below.  A lone warp runs ~6 cycles per dependent instruction: with the tails in this loop the issuer
+    // spent 1000-1300 cycles between the K loops of consecutive tiles (timeline in profiles/), half of a K = 320 K loop.
     if (leader) {
       constexpr int RR = R > 0 ? R : 16;
       const uint32_t idesc_main = idesc_operand_format(make_idesc_bf16(256, BN, 0, 0), f16);
       const uint32_t idesc_both = idesc_operand_format(make_idesc_bf16(256, BN + R, 0, 0), f16);    // first tile of an item: [W ; lora-down]
       const uint32_t idesc_rank = idesc_operand_format(make_idesc_bf16(256, RR, 0, 0), f16);        // S > 1: the rank projection as its own UMMA
       constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
-      constexpr uint32_t lb_layout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
-      constexpr uint64_t d_lb = make_smem_desc_base(16, 8 * RR * 2, lb_layout);
-      constexpr uint64_t d_t = make_smem_desc_base(128, C::T_SBO, kLayoutNone);
-      constexpr uint64_t d_bias = make_smem_desc_base(128, 256, kLayoutNone);
-      uint32_t it = 0, tile_ctr = 0, first_ctr = 0, ready_ctr = 0;
-      bool pending = false, pend_needs_ready = false, pend_first = false;
-      uint32_t pend_tile = 0, pend_ready = 0;
-
-      auto tail_ready = [&]() -> bool {
-        if (R > 0 && !mbar_test(lb_full, pend_tile & 1)) return false;
-        if (pend_needs_ready && !mbar_test(t_ready, pend_ready & 1)) return false;
-        return true;
-      };
-      auto issue_tail = [&]() {
-        if (R > 0) mbar_wait(lb_full, pend_tile & 1);
-        if (pend_needs_ready) mbar_wait(t_ready, pend_ready & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t d = tmem_base + (pend_tile & 1) * C::ACC1_COL;
-          const uint32_t ta = smem_u32(t_smem), ba = smem_u32(lb_smem);
-          const uint32_t idesc_tail = (kMerged && pend_first) ? idesc_both : idesc_main;   // same column layout as the tile's K loop
-          for (int src = 0; src < n_src; ++src) {
-#pragma unroll
-            for (int k = 0; k < R / 16; ++k)
-              umma2_f16_ss(d, smem_desc(d_t, ta + (src * (R / 16) + k) * 256), smem_desc(d_lb, ba + src * C::LB_TILE + k * 32),
-                           idesc_tail, 1u);
-          }
-          if (has_bias) umma2_f16_ss(d, smem_desc(d_t, ta + (S * R / 16) * 256), smem_desc(d_bias, smem_u32(bias_smem)), idesc_tail, 1u);
-          umma2_commit_both(lb_empty);
-          umma2_commit_both(&acc_full[pend_tile & 1]);
-        }
-        __syncwarp();
-        if (lane == 0 && pend_tile < 6) SDT_TRACE2(11 + 4 * pend_tile);
-        pending = false;
-      };
-
+      uint32_t it = 0, tile_ctr = 0;
       for (int item = pair_id; item < p.n_items; item += n_pairs) {
         const PairItem ic = decode_pair_item<G>(item, p, gm);
         const int g = ic.g;
@@ -365,9 +344,6 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           const bool first = (nt == nt0) && R > 0;
           const uint32_t buf = tile_ctr & 1;
           const uint32_t d_main = tmem_base + buf * C::ACC1_COL;
-          // a pending tail goes out while the accumulator buffer is still with the epilogue (see lora_gemm.cu)
-          while (pending && !mbar_test(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1))
-            if (tail_ready()) issue_tail();
           mbar_wait(&acc_empty[buf], ((tile_ctr >> 1) & 1) ^ 1);
           tc_fence_after();
           if (lane == 0 && tile_ctr < 6) SDT_TRACE2(8 + 4 * tile_ctr);
@@ -395,30 +371,64 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
                 umma2_commit_both(&empty[s]);
               }
               __syncwarp();
-              if (pending && ((src == n_src - 1 && kb == nk - 1) || tail_ready())) issue_tail();
             }
           }
           if (lane == 0 && tile_ctr < 6) SDT_TRACE2(10 + 4 * tile_ctr);
-          if (first) {
-            if (elect_one()) umma2_commit_both(t_full);
-            __syncwarp();
-            ++first_ctr;
+          if (elect_one()) {
+            if (first) umma2_commit_both(t_full);                    // side warps: the rank-R intermediate is complete
+            if (has_tail) umma2_commit_leader(&kdone[buf]);          // tail issuer: the accumulator is ready for the tail
+            else          umma2_commit_both(&acc_full[buf]);
           }
-          if (has_tail) {
-            pending = true;
-            pend_tile = tile_ctr;
-            pend_first = first;
-            pend_needs_ready = first || has_bias;
-            pend_ready = ready_ctr;
-            if (pend_needs_ready) ++ready_ctr;
-            if (tail_ready()) issue_tail();
-          } else {
-            if (elect_one()) umma2_commit_both(&acc_full[buf]);
-            __syncwarp();
-          }
+          __syncwarp();
         }
       }
-      if (pending) issue_tail();
+    }
+  } else if (warp == 14) {
+    // ===================================== tail issuer (leader CTA only) ==================================
+    // Per tile: Y += T' lb^T (+ bias through the [1, 1, 0...] columns of T') once the K loop has completed (kdone: UMMAs of two
+    // threads are ordered only through a commit), the lora-up tile has landed and the side warps have written T' / the bias
+    // operand; then the accumulator goes to the epilogue and the lora-up / bias buffers back to their writers.
+    if (leader && has_tail) {
+      constexpr int RR = R > 0 ? R : 16;
+      const uint32_t idesc_main = idesc_operand_format(make_idesc_bf16(256, BN, 0, 0), f16);
+      const uint32_t idesc_both = idesc_operand_format(make_idesc_bf16(256, BN + R, 0, 0), f16);
+      constexpr uint32_t lb_layout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
+      constexpr uint64_t d_lb = make_smem_desc_base(16, 8 * RR * 2, lb_layout);
+      constexpr uint64_t d_t = make_smem_desc_base(128, C::T_SBO, kLayoutNone);
+      constexpr uint64_t d_bias = make_smem_desc_base(128, 256, kLayoutNone);
+      const uint32_t ta = smem_u32(t_smem), ba = smem_u32(lb_smem);
+      uint32_t tile_ctr = 0, ready_ctr = 0;
+      for (int item = pair_id; item < p.n_items; item += n_pairs) {
+        const PairItem ic = decode_pair_item<G>(item, p, gm);
+        const int nt0 = ic.g * p.group_size;
+        const int nt1 = min(nt0 + p.group_size, ic.n_tiles);
+        for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
+          const bool first = (nt == nt0) && R > 0;
+          const uint32_t buf = tile_ctr & 1;
+          if (first || has_bias) {
+            mbar_wait(t_ready, ready_ctr & 1);
+            ++ready_ctr;
+          }
+          if (R > 0) mbar_wait(lb_full, tile_ctr & 1);
+          mbar_wait(&kdone[buf], (tile_ctr >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d = tmem_base + buf * C::ACC1_COL;
+            const uint32_t idesc_tail = (kMerged && first) ? idesc_both : idesc_main;   // same column layout as the tile's K loop
+            for (int src = 0; src < n_src; ++src) {
+#pragma unroll
+              for (int k = 0; k < R / 16; ++k)
+                umma2_f16_ss(d, smem_desc(d_t, ta + (src * (R / 16) + k) * 256), smem_desc(d_lb, ba + src * C::LB_TILE + k * 32),
+                             idesc_tail, 1u);
+            }
+            if (has_bias) umma2_f16_ss(d, smem_desc(d_t, ta + (S * R / 16) * 256), smem_desc(d_bias, smem_u32(bias_smem)), idesc_tail, 1u);
+            umma2_commit_both(lb_empty);
+            umma2_commit_both(&acc_full[buf]);
+          }
+          __syncwarp();
+          if (lane == 0 && tile_ctr < 6) SDT_TRACE2(11 + 4 * tile_ctr);
+        }
+      }
     }
   } else if (warp < 6) {
     // ===================================== side warps (both CTAs) ========================================
@@ -439,8 +449,10 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         const int nt1 = min(nt0 + p.group_size, ic.n_tiles);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
+          // the previous tile's tail has read T' and the bias operand (K loops and tails are issued by different threads: nothing
+          // else orders the next K loop's completion behind that tail)
+          if (tile_ctr > 0 && (first || has_bias)) mbar_wait(lb_empty, (tile_ctr - 1) & 1);
           if (has_bias) {
-            if (tile_ctr > 0) mbar_wait(lb_empty, (tile_ctr - 1) & 1);
             const int n0 = GEGLU ? nt * C::HN + (int)rank * p.geglu_I : nt * C::BN + (int)rank * C::HN;
             for (int n = tid; n < C::HN; n += 128) {
               const float b = (n0 + n < ic.N) ? __ldg(bias + n0 + n) : 0.f;
@@ -490,7 +502,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         }
       }
     }
-  } else {
+  } else if (warp < 14) {
     // ===================================== epilogue warps (both CTAs) ====================================
     // TMEM -> registers -> bf16 -> per-warp transpose buffer -> global in [32 rows x 64 columns] blocks (see lora_gemm.cu)
     const int e = warp - 6;
