@@ -591,6 +591,7 @@ static int launch_lora_gemm(const LoraProblem* probs, int n_probs, float scaling
     }
     gm.y[q] = reinterpret_cast<uint8_t*>(pr.y);
     gm.ym[q] = gm.x[q];                                     // this kernel stores from registers
+    gm.ym32[q] = gm.x[q];
     if (R > 0) {
       rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, R, C::BK, TMAP_SW_128);
       if (rc != SDT_OK) return rc;

@@ -28,7 +28,8 @@ constexpr int kMaxGroup = 4;
 template <int G>
 struct GemmGroup {
   CUtensorMap x[G], w[G], la[G], lb[G];
-  CUtensorMap ym[G];           // outputs as [32 rows x 32 columns] boxes, 64-byte swizzle (CTA-pair kernel: TMA stores)
+  CUtensorMap ym[G];           // outputs as [32 rows x 64 columns] boxes, 128-byte swizzle (CTA-pair kernel: TMA stores)
+  CUtensorMap ym32[G];         // ... and as [32 x 32] boxes, 64-byte swizzle, for the odd 32-column block of a tile
   uint8_t* y[G];               // outputs again, for the paths that store from registers (residual / GEGLU epilogues, single-CTA kernel)
   const float* bias[G];
   __nv_bfloat16* t_out[G];

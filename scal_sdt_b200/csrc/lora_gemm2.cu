@@ -236,7 +236,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         prefetch_tmap(&gm.w[q]);
         if (R > 0) { prefetch_tmap(&gm.la[q]); prefetch_tmap(&gm.lb[q]); }
       }
-      for (int q = 0; q < (S > 1 || G == 1 ? 1 : p.n_probs); ++q) prefetch_tmap(&gm.ym[q]);
+      for (int q = 0; q < (S > 1 || G == 1 ? 1 : p.n_probs); ++q) { prefetch_tmap(&gm.ym[q]); prefetch_tmap(&gm.ym32[q]); }
       for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 16); }
       mbar_init(t_full, 1);
@@ -405,12 +405,13 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
           const uint32_t buf = tile_ctr & 1;
+          // the last of the three to complete is T' (it needs the K loop, then the side warps): waited for last
+          mbar_wait(&kdone[buf], (tile_ctr >> 1) & 1);
+          if (R > 0) mbar_wait(lb_full, tile_ctr & 1);
           if (first || has_bias) {
             mbar_wait(t_ready, ready_ctr & 1);
             ++ready_ctr;
           }
-          if (R > 0) mbar_wait(lb_full, tile_ctr & 1);
-          mbar_wait(&kdone[buf], (tile_ctr >> 1) & 1);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d = tmem_base + buf * C::ACC1_COL;
@@ -465,18 +466,24 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             tc_fence_after();
             for (int src = 0; src < n_src; ++src) {
               uint32_t packed[RR / 2];
+              // two 8-column loads in flight per wait (this round trip is on the critical path of every first tile)
 #pragma unroll
-              for (int c = 0; c < RR / 8; ++c) {
+              for (int c = 0; c < RR / 8; c += 2) {
                 // merged tile: rank column t lives at HN + t (t < HR: CTA 0's lora-down rows) or BN + t (CTA 1's);
                 // otherwise source src owns columns BN + src R + t
-                const int t0 = c * 8;
-                const int col = kMerged ? (t0 < C::HR ? C::HN + t0 : C::BN + t0) : C::BN + src * R + t0;
-                uint32_t v[8];
-                tmem_ld_x8(lane_addr + (tile_ctr & 1) * C::ACC1_COL + col, v);
+                uint32_t v[2][8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int t0 = (c + u) * 8;
+                  const int col = kMerged ? (t0 < C::HR ? C::HN + t0 : C::BN + t0) : C::BN + src * R + t0;
+                  tmem_ld_x8(lane_addr + (tile_ctr & 1) * C::ACC1_COL + col, v[u]);
+                }
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  packed[c * 4 + j] = pack_act2(__uint_as_float(v[2 * j]) * p.scaling, __uint_as_float(v[2 * j + 1]) * p.scaling, f16);
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    packed[(c + u) * 4 + j] = pack_act2(__uint_as_float(v[u][2 * j]) * p.scaling, __uint_as_float(v[u][2 * j + 1]) * p.scaling, f16);
               }
               uint8_t* trow = t_smem + (row >> 3) * C::T_SBO + (row & 7) * 16 + src * (RR / 8) * 128;
 #pragma unroll
@@ -547,8 +554,8 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           // Phase 1: drain this warp's share of the accumulator into its staging buffers and hand the TMEM buffer back at once.
           // Store-bound shapes (K = 320: 8x more bytes out than in per tile) spend ~3000 cycles per tile on the stores; holding
           // the accumulator that long left the MMA warp idle and the store stream with gaps (timeline in profiles/).
-          // Plain outputs leave through the TMA: each 32-column sub-block is staged as a [32 x 64 B] box in the 64-byte swizzle and
-          // one lane issues its store.  The warp never waits on the TPC's store port (with st.global a warp sat ~2000 cycles per
+          // Plain outputs leave through the TMA: each 64-column block is staged as a [32 x 128 B] box in the 128-byte swizzle (full
+          // lines per row: 64-byte rows run the memory system at about half its write bandwidth) and one lane issues its store.  The warp never waits on the TPC's store port (with st.global a warp sat ~2000 cycles per
           // tile in the issue of its stores, and the next accumulator waited for it); rows >= M and columns >= N are clipped by
           // the tensor map.  Residual / GEGLU epilogues keep the [32 x 128 B] staging and the register stores below.
           const bool tma_out = !GEGLU && rp == nullptr;
@@ -561,8 +568,10 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
               load_sub(2 * cb + h);
               uint32_t pk[16];
               pack_acc32(v, pk, f16);
-              if (tma_out) stage_row_sw64(stg + slot * 4096 + h * 2048, lane, pk);
-              else         stage_row_chunk(stg + slot * 4096, lane, h, pk);
+              // a full 64-column block is one [32 x 128 B] box in the 128-byte swizzle -- the layout the register path stages in;
+              // the odd 32-column block of a tile is a [32 x 64 B] box in the 64-byte swizzle
+              if (tma_out && subs == 1) stage_row_sw64(stg + slot * 4096, lane, pk);
+              else                      stage_row_chunk(stg + slot * 4096, lane, h, pk);
             }
           }
           tc_fence_before();
@@ -574,8 +583,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             if (lane == 0) {
               slot = 0;
               for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot)
-                for (int h = 0; h < min(2, n_sub - 2 * cb); ++h)
-                  tma_store_2d(&gm.ym[ic.prob], stg + slot * 4096 + h * 2048, n0 + cb * 64 + h * 32, m0 + q * 32);
+                tma_store_2d(n_sub - 2 * cb >= 2 ? &gm.ym[ic.prob] : &gm.ym32[ic.prob], stg + slot * 4096, n0 + cb * 64, m0 + q * 32);
               tma_store_commit();
             }
             __syncwarp();
@@ -651,14 +659,14 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
               load_sub(2 * cb + h);
               uint32_t pk[16];
               pack_acc32(v, pk, f16);
-              if (tma_out) stage_row_sw64(stg + h * 2048, lane, pk);
-              else         stage_row_chunk(stg, lane, h, pk);
+              if (tma_out && subs == 1) stage_row_sw64(stg, lane, pk);
+              else                      stage_row_chunk(stg, lane, h, pk);
             }
             if (tma_out) {
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
-                for (int h = 0; h < subs; ++h) tma_store_2d(&gm.ym[ic.prob], stg + h * 2048, n0 + cb * 64 + h * 32, m0 + q * 32);
+                tma_store_2d(subs == 2 ? &gm.ym[ic.prob] : &gm.ym32[ic.prob], stg, n0 + cb * 64, m0 + q * 32);
                 tma_store_commit();
               }
               __syncwarp();
@@ -725,7 +733,9 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
     rc = make_tmap_2d_bf16(&gm.w[q], pr.w, N, K, K * 2, C::HN, C::BK, TMAP_SW_128);     // GEGLU: same map, rows addressed per CTA
     if (rc != SDT_OK) return rc;
     gm.y[q] = reinterpret_cast<uint8_t*>(S > 1 ? probs[0].y : pr.y);
-    rc = make_tmap_2d_bf16(&gm.ym[q], gm.y[q], M, N, N * 2, 32, 32, TMAP_SW_64);
+    rc = make_tmap_2d_bf16(&gm.ym[q], gm.y[q], M, N, N * 2, 32, 64, TMAP_SW_128);
+    if (rc != SDT_OK) return rc;
+    rc = make_tmap_2d_bf16(&gm.ym32[q], gm.y[q], M, N, N * 2, 32, 32, TMAP_SW_64);
     if (rc != SDT_OK) return rc;
     if (R > 0) {
       rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
@@ -835,7 +845,9 @@ static int launch_pair_mixed(const LoraProblem* probs, const int64_t* Ns, int n_
     rc = make_tmap_2d_bf16(&gm.lb[q], pr.lb, N, R, (uint64_t)R * 2, C::HN, R, R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
     if (rc != SDT_OK) return rc;
     gm.y[q] = reinterpret_cast<uint8_t*>(pr.y);
-    rc = make_tmap_2d_bf16(&gm.ym[q], pr.y, M, N, N * 2, 32, 32, TMAP_SW_64);
+    rc = make_tmap_2d_bf16(&gm.ym[q], pr.y, M, N, N * 2, 32, 64, TMAP_SW_128);
+    if (rc != SDT_OK) return rc;
+    rc = make_tmap_2d_bf16(&gm.ym32[q], pr.y, M, N, N * 2, 32, 32, TMAP_SW_64);
     if (rc != SDT_OK) return rc;
     gm.bias[q] = pr.bias;
     gm.t_out[q] = reinterpret_cast<__nv_bfloat16*>(pr.t_out);
