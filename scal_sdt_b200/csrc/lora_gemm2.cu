@@ -83,6 +83,20 @@ __device__ __forceinline__ void umma2_f16_ss(uint32_t d_tmem, uint64_t a_desc, u
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// TS mode: the A operand (this CTA's 128 rows x 16 k) comes from tensor memory (lane = row, 32-bit column c = elements 2c, 2c+1)
+__device__ __forceinline__ void umma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 128 rows x 32 bytes (one K = 16 slice of a K-major tile, any swizzle the descriptor names) from shared memory into 8 TMEM columns,
+// in both CTAs of the pair; ordered with the UMMAs of the issuing thread (tcgen05.cp and tcgen05.mma execute in issue order)
+__device__ __forceinline__ void cp2_128x256b(uint32_t taddr, uint64_t s_desc) {
+  asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(taddr), "l"(s_desc) : "memory");
+}
 // arrive on the barrier at the same offset in BOTH CTAs when all prior UMMAs of this thread have completed
 __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
   asm volatile(
@@ -137,6 +151,9 @@ struct PairCfg {
   // With S > 1 the tiles are never merged: main accumulator [Y 0..BN) and S rank accumulators [T_s 0..R) behind it.
   static constexpr int ACC1_COL = BN + S * R;
   static_assert(2 * ACC1_COL <= 512, "TMEM budget");
+  // TS mode: k-blocks of X ([128 rows x 64 k] = 32 columns) staged in the TMEM columns behind the two accumulators
+  static constexpr int A_TM_COL = 2 * ACC1_COL;
+  static constexpr int A_SLOTS = (512 - A_TM_COL) / 32;
   static_assert(BN % 32 == 0 && HN % 8 == 0 && BN <= 256, "BN");
   static_assert(R == 0 || R == 16 || R == 32 || R == 64, "rank must be padded to 16/32/64");
   static_assert(kStages >= 3, "pipeline depth");
@@ -158,6 +175,7 @@ struct PairParams {
   int geglu_I;
   uint8_t* act_out;
   int mixed;              // problems have their own output width (GemmGroup::n / tile_begin); one column tile per work item
+  int ts;                 // A operand through tensor memory (tcgen05.cp of each k-block, then TS-mode UMMAs); needs C::A_SLOTS >= 1
   long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
 };
 
@@ -357,15 +375,33 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
                 const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
                 const uint32_t wa = xa + C::X_BYTES;
                 const uint32_t la = wa + C::W_BYTES;
+                if (C::A_SLOTS >= 1 && p.ts) {
+                  // TS mode: the k-block of X goes to tensor memory first; an SS-mode UMMA pays ~38 cycles for fetching its A
+                  // operand from shared memory before the math starts, a TS-mode one ~1 (tools/umma_bench.cu)
+                  constexpr uint32_t kASlots = C::A_SLOTS >= 1 ? C::A_SLOTS : 1;
+                  const uint32_t a_tm = tmem_base + C::A_TM_COL + (it % kASlots) * 32;
 #pragma unroll
-                for (int k = 0; k < C::BK / 16; ++k) {
-                  const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
-                  if (kMerged) {
-                    umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main, (kb | k) != 0);
-                  } else {
-                    // every source accumulates into the same main columns; its rank projection has its own columns
-                    umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), idesc_main, (src | kb | k) != 0);
-                    if (first) umma2_f16_ss(d_main + BN + src * R, a_desc, smem_desc(d_sw128, la + k * 32), idesc_rank, (kb | k) != 0);
+                  for (int k = 0; k < C::BK / 16; ++k) cp2_128x256b(a_tm + k * 8, smem_desc(d_sw128, xa + k * 32));
+#pragma unroll
+                  for (int k = 0; k < C::BK / 16; ++k) {
+                    if (kMerged) {
+                      umma2_f16_ts(d_main, a_tm + k * 8, smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main, (kb | k) != 0);
+                    } else {
+                      umma2_f16_ts(d_main, a_tm + k * 8, smem_desc(d_sw128, wa + k * 32), idesc_main, (src | kb | k) != 0);
+                      if (first) umma2_f16_ts(d_main + BN + src * R, a_tm + k * 8, smem_desc(d_sw128, la + k * 32), idesc_rank, (kb | k) != 0);
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < C::BK / 16; ++k) {
+                    const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
+                    if (kMerged) {
+                      umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main, (kb | k) != 0);
+                    } else {
+                      // every source accumulates into the same main columns; its rank projection has its own columns
+                      umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), idesc_main, (src | kb | k) != 0);
+                      if (first) umma2_f16_ss(d_main + BN + src * R, a_desc, smem_desc(d_sw128, la + k * 32), idesc_rank, (kb | k) != 0);
+                    }
                   }
                 }
                 umma2_commit_both(&empty[s]);
@@ -764,6 +800,7 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
   p.geglu_I = GEGLU ? (int)(N / 2) : 0;
   p.act_out = reinterpret_cast<uint8_t*>(act_out);
   p.trace = reinterpret_cast<long long*>(debug_get(10));
+  p.ts = (C::A_SLOTS >= 1 && debug_get(30)) ? 1 : 0;
   const int m_tiles = (int)((M + 2 * C::BM - 1) / (2 * C::BM));
   p.n_tiles = (int)((N + BN - 1) / BN);
   const int pairs_max = num_sms() / 2;
@@ -869,6 +906,7 @@ static int launch_pair_mixed(const LoraProblem* probs, const int64_t* Ns, int n_
   p.geglu_I = 0;
   p.act_out = nullptr;
   p.trace = reinterpret_cast<long long*>(debug_get(10));
+  p.ts = (C::A_SLOTS >= 1 && debug_get(30)) ? 1 : 0;
   const int m_tiles = (int)((M + 2 * C::BM - 1) / (2 * C::BM));
   p.n_tiles = 0;
   p.group_size = 1;

@@ -50,15 +50,21 @@ def case(M, K, N, R, G, settings):
             _lib.check(lib.sdt_lora_linear_fwd_group(ctypes.addressof(probs), G, 0.5, M, K, N, R, 1, st))
     fl = G * (2.0 * M * K * N + 2.0 * M * R * (K + N))
     out = []
+    ref_out = None
     for name, kv in settings:
-        for k in (11, 12, 13, 14, 20, 22):
+        for k in (11, 12, 13, 14, 20, 22, 30):
             lib.sdt_debug_set(k, 0)
         for k, v in kv.items():
             lib.sdt_debug_set(k, v)
         warm, kn = kernel_us(run)
         cold, _ = kernel_us(run, cold=True)
-        out.append(f"{name}: warm {warm:6.1f} us {fl / warm / 1e6:6.0f} TF/s | cold {cold:6.1f} us {fl / cold / 1e6:6.0f} TF/s [{kn}]")
-    for k in (11, 12, 13, 14, 20, 22):
+        same = ""
+        if ref_out is None:
+            ref_out = [y.clone() for y in ys] + [t.clone() for t in ts]
+        else:
+            same = " bit-equal to the first setting" if all(torch.equal(a, b) for a, b in zip(ref_out, ys + ts)) else " DIFFERS from the first setting"
+        out.append(f"{name}: warm {warm:6.1f} us {fl / warm / 1e6:6.0f} TF/s | cold {cold:6.1f} us {fl / cold / 1e6:6.0f} TF/s [{kn}]{same}")
+    for k in (11, 12, 13, 14, 20, 22, 30):
         lib.sdt_debug_set(k, 0)
     print(f"M={M} K={K} N={N} R={R} G={G}")
     for o in out:
@@ -68,12 +74,14 @@ def case(M, K, N, R, G, settings):
 SET = [("auto  ", {}), ("single", {11: 1}), ("pair  ", {14: 64}), ("pair160", {14: 64, 12: 1})]
 if len(sys.argv) > 1 and sys.argv[1] == "wide":
     SET = [("auto    ", {}), ("160-wide", {12: 1}), ("224 >=1280", {22: 1280}), ("224 >=1280 gs1", {22: 1280, 20: 1})]
+if len(sys.argv) > 1 and sys.argv[1] == "ts":        # A operand through tensor memory (tcgen05.cp + TS-mode UMMAs) vs shared memory
+    SET = [("SS", {}), ("TS", {30: 1}), ("SS", {}), ("TS", {30: 1})]
 if len(sys.argv) > 1 and sys.argv[1] == "groups":
     SET = [("auto", {}), ("gs1 ", {20: 1}), ("gs2 ", {20: 2}), ("gs3 ", {20: 3}), ("gs4 ", {20: 4}), ("gs6 ", {20: 6})]
 SHAPES_BWD = [(32768, 320, 1280, 16, 1), (8192, 640, 2560, 16, 1), (2048, 1280, 5120, 16, 1), (32768, 2560, 320, 16, 1),
               (8192, 5120, 640, 16, 1), (2048, 10240, 1280, 16, 1)]      # dX of ff.net.2 / ff.net.0.proj: (M, contraction, outputs)
 if len(sys.argv) > 2 and sys.argv[2] == "bwd":
-    if sys.argv[1] == "wide":
+    if sys.argv[1] in ("wide", "ts"):
         SHAPES_BWD = SHAPES_BWD + [(2048, 1280, 1280, 16, 1), (2048, 5120, 1280, 16, 1), (2048, 1280, 1280, 16, 3), (8192, 640, 5120, 16, 1)]
     for shp in SHAPES_BWD:
         case(*shp, SET)
