@@ -636,9 +636,22 @@ def ours_main(args):
         backward = {"kernels": "lora_gemm* (dX, G) + lora_wgrad_kernel (dA and dB of up to 16 sites per launch)", "timing": "cuda_events (eager step)",
                     "achieved": f_bwd / t_bwd / 1e12, "frac": f_bwd / t_bwd / 1e12 / peaks["tf_sustained"]}
         if bwd_gemm_t is not None:
+            # per-shape view of the input-gradient launches: M tokens, contraction over the site's N outputs, K input columns out;
+            # a grouped launch with dX sums its G sources into one dX (q / k / v), one without dX only forms the rank projections
+            dx_acc = {}
+            for (kind, M, K, N, R, G, dx, *_), sec in zip(bwd_sites, bwd_gemm_t):
+                e = dx_acc.setdefault((M, N, K, R, G, bool(dx)), [0, 0.0])
+                e[0] += 1
+                e[1] += sec
+            dx_by_shape = []
+            for (M, N, K, R, G, dx), (cnt, sec) in sorted(dx_acc.items(), key=lambda kv: -kv[1][1]):
+                fl = G * (2.0 * M * K * N + 2.0 * M * R * (K + N)) if dx else G * 2.0 * M * R * N
+                dx_by_shape.append({"M": M, "contraction": N, "outputs": K, "R": R, "sources_per_launch": G, "writes_dx": dx, "launches": cnt,
+                                    "avg_us": 1e6 * sec / cnt, "tflops": fl * cnt / sec / 1e12,
+                                    "frac_tensor": fl * cnt / sec / 1e12 / peaks["tf_sustained"]})
             backward["dx_gemm"] = {"timing": timing, "achieved": dx_flops / sum(bwd_gemm_t) / 1e12,
                                    "frac": dx_flops / sum(bwd_gemm_t) / 1e12 / peaks["tf_sustained"],
-                                   "seconds_per_step": sum(bwd_gemm_t)}
+                                   "seconds_per_step": sum(bwd_gemm_t), "by_shape": dx_by_shape}
             wg = [k for k in ks if "lora_wgrad" in k[0]]
             if wg:
                 wg_bytes = sum(G * 2.0 * M * (K + N + 2 * R) for kind, M, K, N, R, G, *_ in bwd_sites)

@@ -450,59 +450,86 @@ lora_pack_kernel(const sdt_pack_site* __restrict__ sites, int f16) {
 // =============================================================================================
 // gelu_erf / gelu_erf_grad: sdt_common.cuh (shared with the GEGLU epilogue of the fused projection)
 
-// proj [M, 2I] bf16 -> out [M, I] bf16; one 16-byte vector (8 elements) of h and of gate per thread per iteration
+// proj [M, 2I] bf16 -> out [M, I] bf16.  A thread handles 16-byte vectors (8 elements) of h and of gate, TWO of them per
+// iteration with all four loads issued before the math (the erf GELU is ~20 instructions per element: with one vector per
+// iteration the loads of the next iteration waited behind it), and 32-bit index arithmetic (a 64-bit division per vector cost as
+// much as two elements of GELU).
+__device__ __forceinline__ uint4 geglu_fwd_vec(const uint4& hv, const uint4& gv) {
+  const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
+  uint4 ov;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float h0 = bf16_bits_to_f32(hw[j] & 0xffffu), h1 = bf16_bits_to_f32(hw[j] >> 16);
+    const float g0 = bf16_bits_to_f32(gw[j] & 0xffffu), g1 = bf16_bits_to_f32(gw[j] >> 16);
+    ow[j] = pack_bf16x2(h0 * gelu_erf(g0), h1 * gelu_erf(g1));
+  }
+  return ov;
+}
 __global__ void __launch_bounds__(kThreads)
-geglu_fwd_bf16_kernel(const uint16_t* __restrict__ proj, uint16_t* __restrict__ out, int64_t M, int64_t I8) {
+geglu_fwd_bf16_kernel(const uint16_t* __restrict__ proj, uint16_t* __restrict__ out, uint32_t total, uint32_t I8) {
   pdl_wait();                 // PDL (sdt_common.cuh)
   pdl_launch_dependents();
-  const int64_t total = M * I8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / I8, c = i - row * I8;
-    const uint4* base = reinterpret_cast<const uint4*>(proj) + row * 2 * I8;
-    const uint4 hv = ld_stream(base + c), gv = ld_stream(base + I8 + c);
-    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
-    const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
-    uint4 ov;
-    uint32_t* ow = reinterpret_cast<uint32_t*>(&ov);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float h0 = bf16_bits_to_f32(hw[j] & 0xffffu), h1 = bf16_bits_to_f32(hw[j] >> 16);
-      const float g0 = bf16_bits_to_f32(gw[j] & 0xffffu), g1 = bf16_bits_to_f32(gw[j] >> 16);
-      ow[j] = pack_bf16x2(h0 * gelu_erf(g0), h1 * gelu_erf(g1));
-    }
-    st_stream(reinterpret_cast<uint4*>(out) + i, ov);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint4* pv = reinterpret_cast<const uint4*>(proj);
+  uint4* ov = reinterpret_cast<uint4*>(out);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    const uint32_t i2 = i + stride;
+    const bool two = i2 < total;
+    const uint32_t r0 = i / I8, r1 = two ? i2 / I8 : 0u;
+    const uint4* b0 = pv + (size_t)r0 * (2 * I8) + (i - r0 * I8);
+    const uint4* b1 = pv + (size_t)r1 * (2 * I8) + (two ? i2 - r1 * I8 : 0u);
+    const uint4 h0 = ld_stream(b0), g0 = ld_stream(b0 + I8);
+    uint4 h1 = make_uint4(0u, 0u, 0u, 0u), g1 = h1;
+    if (two) { h1 = ld_stream(b1); g1 = ld_stream(b1 + I8); }
+    st_stream(ov + i, geglu_fwd_vec(h0, g0));
+    if (two) st_stream(ov + i2, geglu_fwd_vec(h1, g1));
   }
 }
 
-// dproj[:, :I] = dout * gelu(gate) ; dproj[:, I:] = dout * h * gelu'(gate)
+// dproj[:, :I] = dout * gelu(gate) ; dproj[:, I:] = dout * h * gelu'(gate); same structure (six loads in flight per thread)
+__device__ __forceinline__ void geglu_bwd_vec(const uint4& hv, const uint4& gv, const uint4& dv, uint4& dhv, uint4& dgv) {
+  const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
+  const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv);
+  uint32_t* dhw = reinterpret_cast<uint32_t*>(&dhv);
+  uint32_t* dgw = reinterpret_cast<uint32_t*>(&dgv);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float h0 = bf16_bits_to_f32(hw[j] & 0xffffu), h1 = bf16_bits_to_f32(hw[j] >> 16);
+    const float g0 = bf16_bits_to_f32(gw[j] & 0xffffu), g1 = bf16_bits_to_f32(gw[j] >> 16);
+    const float d0 = bf16_bits_to_f32(dw[j] & 0xffffu), d1 = bf16_bits_to_f32(dw[j] >> 16);
+    dhw[j] = pack_bf16x2(d0 * gelu_erf(g0), d1 * gelu_erf(g1));
+    dgw[j] = pack_bf16x2(d0 * h0 * gelu_erf_grad(g0), d1 * h1 * gelu_erf_grad(g1));
+  }
+}
 __global__ void __launch_bounds__(kThreads)
 geglu_bwd_bf16_kernel(const uint16_t* __restrict__ proj, const uint16_t* __restrict__ dout, uint16_t* __restrict__ dproj,
-                      int64_t M, int64_t I8) {
+                      uint32_t total, uint32_t I8) {
   pdl_wait();                 // PDL (sdt_common.cuh)
   pdl_launch_dependents();
-  const int64_t total = M * I8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / I8, c = i - row * I8;
-    const uint4* base = reinterpret_cast<const uint4*>(proj) + row * 2 * I8;
-    const uint4 hv = ld_stream(base + c), gv = ld_stream(base + I8 + c);
-    const uint4 dv = ld_stream(reinterpret_cast<const uint4*>(dout) + i);
-    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
-    const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
-    const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv);
-    uint4 dhv, dgv;
-    uint32_t* dhw = reinterpret_cast<uint32_t*>(&dhv);
-    uint32_t* dgw = reinterpret_cast<uint32_t*>(&dgv);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float h0 = bf16_bits_to_f32(hw[j] & 0xffffu), h1 = bf16_bits_to_f32(hw[j] >> 16);
-      const float g0 = bf16_bits_to_f32(gw[j] & 0xffffu), g1 = bf16_bits_to_f32(gw[j] >> 16);
-      const float d0 = bf16_bits_to_f32(dw[j] & 0xffffu), d1 = bf16_bits_to_f32(dw[j] >> 16);
-      dhw[j] = pack_bf16x2(d0 * gelu_erf(g0), d1 * gelu_erf(g1));
-      dgw[j] = pack_bf16x2(d0 * h0 * gelu_erf_grad(g0), d1 * h1 * gelu_erf_grad(g1));
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint4* pv = reinterpret_cast<const uint4*>(proj);
+  const uint4* dov = reinterpret_cast<const uint4*>(dout);
+  uint4* dpv = reinterpret_cast<uint4*>(dproj);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    const uint32_t i2 = i + stride;
+    const bool two = i2 < total;
+    const uint32_t r0 = i / I8, r1 = two ? i2 / I8 : 0u;
+    const size_t o0 = (size_t)r0 * (2 * I8) + (i - r0 * I8), o1 = (size_t)r1 * (2 * I8) + (two ? i2 - r1 * I8 : 0u);
+    const uint4 h0 = ld_stream(pv + o0), g0 = ld_stream(pv + o0 + I8), d0 = ld_stream(dov + i);
+    uint4 h1 = make_uint4(0u, 0u, 0u, 0u), g1 = h1, d1 = h1;
+    if (two) { h1 = ld_stream(pv + o1); g1 = ld_stream(pv + o1 + I8); d1 = ld_stream(dov + i2); }
+    uint4 dh, dg;
+    geglu_bwd_vec(h0, g0, d0, dh, dg);
+    st_stream(dpv + o0, dh);
+    st_stream(dpv + o0 + I8, dg);
+    if (two) {
+      geglu_bwd_vec(h1, g1, d1, dh, dg);
+      st_stream(dpv + o1, dh);
+      st_stream(dpv + o1 + I8, dg);
     }
-    uint4* obase = reinterpret_cast<uint4*>(dproj) + row * 2 * I8;
-    st_stream(obase + c, dhv);
-    st_stream(obase + I8 + c, dgv);
   }
 }
 
@@ -689,13 +716,16 @@ extern "C" int sdt_geglu(const void* proj, const void* dout, void* out_or_dproj,
   if (dtype == SDT_BF16) {
     SDT_REQUIRE(I % 8 == 0 && aligned16(proj) && aligned16(out_or_dproj) && aligned16(dout), SDT_ERR_UNSUPPORTED,
                 "sdt_geglu(bf16): inner width must be a multiple of 8 and pointers 16-byte aligned");
-    const int grid = grid_for(M * (I / 8), kThreads, 8);
+    SDT_REQUIRE(M * (I / 8) < (1ll << 31), SDT_ERR_UNSUPPORTED, "sdt_geglu(bf16): more than 2^31 vectors (M = %lld, I = %lld)", (long long)M,
+                (long long)I);
+    const uint32_t total = (uint32_t)(M * (I / 8));
+    const int grid = grid_for((int64_t)(total + 1) / 2, kThreads, 8);          // two vectors per thread and iteration
     if (!backward)
       SDT_CUDA_OK(launch_kernel(geglu_fwd_bf16_kernel, dim3(grid), dim3(kThreads), 0, st, true, (const uint16_t*)proj,
-                                (uint16_t*)out_or_dproj, M, I / 8));
+                                (uint16_t*)out_or_dproj, total, (uint32_t)(I / 8)));
     else
       SDT_CUDA_OK(launch_kernel(geglu_bwd_bf16_kernel, dim3(grid), dim3(kThreads), 0, st, true, (const uint16_t*)proj,
-                                (const uint16_t*)dout, (uint16_t*)out_or_dproj, M, I / 8));
+                                (const uint16_t*)dout, (uint16_t*)out_or_dproj, total, (uint32_t)(I / 8)));
   } else if (dtype == SDT_F32) {
     const int grid = grid_for(M * I, kThreads, 8);
     geglu_f32_kernel<<<grid, kThreads, 0, st>>>((const float*)proj, (const float*)dout, (float*)out_or_dproj, M, I, backward);

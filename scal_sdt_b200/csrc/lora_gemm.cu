@@ -552,6 +552,39 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return SDT_OK;
 }
 
+// A [rows, cols] matrix seen as its two row halves, [2][rows/2][cols] (128-byte swizzle): a box of box_rows >= rows/2 rows that
+// starts at a NEGATIVE row coordinate brings one half surrounded by zero rows (out-of-bounds elements are zero-filled and still
+// counted by the barrier).  The summed-source kernel uses it to place a source's lora-down rows inside a block of zeros.
+int make_tmap_halves_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                          uint32_t box_rows, uint32_t box_cols) {
+  const TmapKey key{reinterpret_cast<uint64_t>(base), rows, cols, pitch_bytes, box_rows, box_cols, 0x100u | (uint32_t)TMAP_SW_128};
+  {
+    std::lock_guard<std::mutex> lk(g_tmaps_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) { *out = it->second; return SDT_OK; }
+  }
+  PFN_encodeTiled enc = get_encode();
+  SDT_REQUIRE(enc != nullptr, SDT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  SDT_REQUIRE(aligned16(base) && pitch_bytes % 16 == 0 && rows % 2 == 0, SDT_ERR_ARG,
+              "TMA operand must be 16-byte aligned with a 16-byte row pitch and an even number of rows");
+  cuuint64_t dims[3] = {cols, rows / 2, 2};
+  cuuint64_t strides[2] = {pitch_bytes, (rows / 2) * pitch_bytes};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SDT_REQUIRE(r == CUDA_SUCCESS, SDT_ERR_CUDA,
+              "cuTensorMapEncodeTiled failed (%d) for 2 x [%llu x %llu] pitch %llu box [%u x %u]", (int)r,
+              (unsigned long long)rows / 2, (unsigned long long)cols, (unsigned long long)pitch_bytes, box_rows, box_cols);
+  {
+    std::lock_guard<std::mutex> lk(g_tmaps_mu);
+    if (g_tmaps.size() > 16384) g_tmaps.clear();
+    g_tmaps.emplace(key, *out);
+  }
+  return SDT_OK;
+}
+
 // Pick the number of n-groups per m-tile: fewer groups = less recomputation of the rank-R projection, more groups =
 // more work items to balance over the SMs.  Cost of a schedule ~ rounds * (columns per item + per-item overhead).
 static void choose_groups(int m_tiles, int n_tiles, int BN, int R, int sms, int* group_size, int* n_groups) {

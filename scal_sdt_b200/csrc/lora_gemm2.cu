@@ -21,6 +21,8 @@ using namespace ptx;
 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                       uint32_t box_rows, uint32_t box_cols, TmapSwizzle swz);
+int make_tmap_halves_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                          uint32_t box_rows, uint32_t box_cols);
 uint64_t debug_get(int key);
 
 // debug timeline of pair 0's leader CTA (same slots as lora_gemm.cu; enabled with sdt_debug_set(10, ptr))
@@ -65,6 +67,14 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(c_inner), "r"(c_row), "r"(bar_cluster_addr)
+      : "memory");
+}
+// the same for a box of a 3-D tensor map (make_tmap_halves_bf16: inner element, row inside the half -- may be negative --, half)
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m, int c_inner, int c_row, int c_half, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(c_inner), "r"(c_row), "r"(c_half), "r"(bar_cluster_addr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
@@ -125,9 +135,11 @@ struct PairCfg {
   static constexpr int BM = 128, BN = BN_, BK = 64, R = R_, HN = BN_ / 2, HR = R_ / 2, S = S_;
   static constexpr int X_BYTES = BM * BK * 2;                       // own 128 rows of X
   static constexpr int W_BYTES = HN * BK * 2;                       // own half of the W tile
-  static constexpr int LA_BYTES = ((HR * BK * 2 + 1023) / 1024) * 1024;   // own half of the lora-down k-block
+  // own half of the lora-down k-block; with S sources a block of S HR rows in which only the current source's rows are non-zero
+  static constexpr int LA_ROWS = S * HR;
+  static constexpr int LA_BYTES = ((LA_ROWS * BK * 2 + 1023) / 1024) * 1024;
   static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + LA_BYTES;
-  static constexpr int LB_TILE = (((HN + HR) * R * 2 + 1023) / 1024) * 1024;    // own half of one lora-up tile [BN/2, R] + HR zero rows
+  static constexpr int LB_TILE = (((HN + LA_ROWS) * R * 2 + 1023) / 1024) * 1024;    // own half of one lora-up tile [BN/2, R] + S HR zero rows
   static constexpr int LB_BYTES = S * LB_TILE;
   static constexpr int KEXT = S * R + 16;
   static constexpr int T_SBO = (KEXT / 8) * 128;
@@ -148,7 +160,11 @@ struct PairCfg {
   // cta_group::2 the N index runs over CTA 0's rows, then CTA 1's, so the columns of such a tile are
   //   [Y 0..HN) | T 0..HR) | Y HN..BN) | T HR..R)]      (acc_col(y) = y < HN ? y : y + HR ; acc_col(t) = t < HR ? HN + t : BN + t)
   // and the tail UMMAs use the same N with zero rows appended to the lora-up / bias operands.  Other tiles are plain [Y].
-  // With S > 1 the tiles are never merged: main accumulator [Y 0..BN) and S rank accumulators [T_s 0..R) behind it.
+  // With S > 1 sources the rank block of a CTA has S HR rows, source s owning rows [s HR, (s+1) HR) and the TMA zero-filling the
+  // others (a source adds 0 to the other sources' columns), so the first tile is
+  //   [Y 0..HN) | T_0 0..HR) .. T_{S-1} 0..HR) | Y HN..BN) | T_0 HR..R) .. T_{S-1} HR..R)]
+  // A separate N = R UMMA for the rank projection costs as much as the N = BN one next to it: in a CTA pair every UMMA takes
+  // max(113, N/2) cycles (profiles/r02_umma_pair_ss_vs_ts.txt).
   static constexpr int ACC1_COL = BN + S * R;
   static_assert(2 * ACC1_COL <= 512, "TMEM budget");
   // TS mode: k-blocks of X ([128 rows x 64 k] = 32 columns) staged in the TMEM columns behind the two accumulators
@@ -217,7 +233,6 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
   using C = PairCfg<BN, R, S>;
   static_assert(S == 1 || (G >= S && R > 0), "summed sources live in the entries of the group");
   static_assert(!GEGLU || (G == 1 && S == 1 && R > 0 && C::STG_BLOCKS >= 2 && C::HN % 8 == 0), "GEGLU epilogue: one merged problem, <= 160-wide tiles");
-  constexpr bool kMerged = S == 1;             // first tile of an item: base GEMM and rank projection as one UMMA
   const int n_src = S == 1 ? 1 : p.n_src;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -282,7 +297,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
       if (n >= C::HN) *reinterpret_cast<uint4*>(bias_smem + (n >> 3) * 256 + (n & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     // zero rows behind the lora-up tile (rows of R*2 bytes; the TMA box only ever writes the first HN rows)
-    for (int i = row; i < C::HR * R * 2 / 16; i += 128)
+    for (int i = row; i < C::LA_ROWS * R * 2 / 16; i += 128)
       for (int q = 0; q < S; ++q)
         *reinterpret_cast<uint4*>(lb_smem + q * C::LB_TILE + C::HN * R * 2 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
@@ -317,7 +332,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           // rows of W / lora-up this CTA contributes to the tile.  cta_group::2 runs the N index over CTA 0's rows, then CTA 1's:
           // for GEGLU CTA 0 brings the h rows and CTA 1 the gate rows of the same output columns -- no permuted weight copy
           const int n0 = GEGLU ? nt * C::HN + (int)rank * p.geglu_I : nt * C::BN + (int)rank * C::HN;
-          const uint32_t tx = 2u * (C::X_BYTES + C::W_BYTES + (first ? C::HR * C::BK * 2 : 0));
+          const uint32_t tx = 2u * (C::X_BYTES + C::W_BYTES + (first ? C::LA_ROWS * C::BK * 2 : 0));     // zero-filled rows count too
           for (int src = 0; src < n_src; ++src) {
             const int q = S > 1 ? src : ic.prob;          // operand set: the source, or the problem of a grouped launch
             for (int kb = 0; kb < nk; ++kb, ++it) {
@@ -329,7 +344,11 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
               if (it == 0) SDT_TRACE2(2);
               tma_load_2d_pair(st, &gm.x[q], kb * C::BK, m0, full_leader);
               tma_load_2d_pair(st + C::X_BYTES, &gm.w[q], kb * C::BK, n0, full_leader);
-              if (first) tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES, &gm.la[q], kb * C::BK, (int)rank * C::HR, full_leader);
+              if (first) {
+                // this CTA's half of the lora-down k-block; with S sources as rows [src HR, (src + 1) HR) of a zero-filled block
+                if (S == 1) tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES, &gm.la[q], kb * C::BK, (int)rank * C::HR, full_leader);
+                else        tma_load_3d_pair(st + C::X_BYTES + C::W_BYTES, &gm.la[q], kb * C::BK, -src * C::HR, (int)rank, full_leader);
+              }
             }
           }
           if (R > 0) {
@@ -347,10 +366,8 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
     // issued by its own warp below.  A lone warp runs ~6 cycles per dependent instruction: with the tails in this loop the issuer
     // spent 1000-1300 cycles between the K loops of consecutive tiles (timeline in profiles/), half of a K = 320 K loop.
     if (leader) {
-      constexpr int RR = R > 0 ? R : 16;
       const uint32_t idesc_main = idesc_operand_format(make_idesc_bf16(256, BN, 0, 0), f16);
-      const uint32_t idesc_both = idesc_operand_format(make_idesc_bf16(256, BN + R, 0, 0), f16);    // first tile of an item: [W ; lora-down]
-      const uint32_t idesc_rank = idesc_operand_format(make_idesc_bf16(256, RR, 0, 0), f16);        // S > 1: the rank projection as its own UMMA
+      const uint32_t idesc_both = idesc_operand_format(make_idesc_bf16(256, BN + S * R, 0, 0), f16);    // first tile of an item: [W ; lora-down]
       constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
       uint32_t it = 0, tile_ctr = 0;
       for (int item = pair_id; item < p.n_items; item += n_pairs) {
@@ -373,8 +390,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
-                const uint32_t wa = xa + C::X_BYTES;
-                const uint32_t la = wa + C::W_BYTES;
+                const uint32_t wa = xa + C::X_BYTES;        // [W half ; lora-down block] is one B operand
                 if (C::A_SLOTS >= 1 && p.ts) {
                   // TS mode: the k-block of X goes to tensor memory first; an SS-mode UMMA pays ~38 cycles for fetching its A
                   // operand from shared memory before the math starts, a TS-mode one ~1 (tools/umma_bench.cu)
@@ -383,26 +399,15 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
 #pragma unroll
                   for (int k = 0; k < C::BK / 16; ++k) cp2_128x256b(a_tm + k * 8, smem_desc(d_sw128, xa + k * 32));
 #pragma unroll
-                  for (int k = 0; k < C::BK / 16; ++k) {
-                    if (kMerged) {
-                      umma2_f16_ts(d_main, a_tm + k * 8, smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main, (kb | k) != 0);
-                    } else {
-                      umma2_f16_ts(d_main, a_tm + k * 8, smem_desc(d_sw128, wa + k * 32), idesc_main, (src | kb | k) != 0);
-                      if (first) umma2_f16_ts(d_main + BN + src * R, a_tm + k * 8, smem_desc(d_sw128, la + k * 32), idesc_rank, (kb | k) != 0);
-                    }
-                  }
+                  for (int k = 0; k < C::BK / 16; ++k)
+                    umma2_f16_ts(d_main, a_tm + k * 8, smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main, (src | kb | k) != 0);
                 } else {
+                  // every source accumulates into the same Y columns; the zero rows of its lora-down block leave the other
+                  // sources' rank columns as they are
 #pragma unroll
-                  for (int k = 0; k < C::BK / 16; ++k) {
-                    const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
-                    if (kMerged) {
-                      umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main, (kb | k) != 0);
-                    } else {
-                      // every source accumulates into the same main columns; its rank projection has its own columns
-                      umma2_f16_ss(d_main, a_desc, smem_desc(d_sw128, wa + k * 32), idesc_main, (src | kb | k) != 0);
-                      if (first) umma2_f16_ss(d_main + BN + src * R, a_desc, smem_desc(d_sw128, la + k * 32), idesc_rank, (kb | k) != 0);
-                    }
-                  }
+                  for (int k = 0; k < C::BK / 16; ++k)
+                    umma2_f16_ss(d_main, smem_desc(d_sw128, xa + k * 32), smem_desc(d_sw128, wa + k * 32), first ? idesc_both : idesc_main,
+                                 (src | kb | k) != 0);
                 }
                 umma2_commit_both(&empty[s]);
               }
@@ -427,7 +432,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
     if (leader && has_tail) {
       constexpr int RR = R > 0 ? R : 16;
       const uint32_t idesc_main = idesc_operand_format(make_idesc_bf16(256, BN, 0, 0), f16);
-      const uint32_t idesc_both = idesc_operand_format(make_idesc_bf16(256, BN + R, 0, 0), f16);
+      const uint32_t idesc_both = idesc_operand_format(make_idesc_bf16(256, BN + S * R, 0, 0), f16);
       constexpr uint32_t lb_layout = R == 64 ? kLayoutSW128 : (R == 32 ? kLayoutSW64 : kLayoutSW32);
       constexpr uint64_t d_lb = make_smem_desc_base(16, 8 * RR * 2, lb_layout);
       constexpr uint64_t d_t = make_smem_desc_base(128, C::T_SBO, kLayoutNone);
@@ -451,7 +456,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d = tmem_base + buf * C::ACC1_COL;
-            const uint32_t idesc_tail = (kMerged && first) ? idesc_both : idesc_main;   // same column layout as the tile's K loop
+            const uint32_t idesc_tail = first ? idesc_both : idesc_main;   // same column layout as the tile's K loop
             for (int src = 0; src < n_src; ++src) {
 #pragma unroll
               for (int k = 0; k < R / 16; ++k)
@@ -505,13 +510,13 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
               // two 8-column loads in flight per wait (this round trip is on the critical path of every first tile)
 #pragma unroll
               for (int c = 0; c < RR / 8; c += 2) {
-                // merged tile: rank column t lives at HN + t (t < HR: CTA 0's lora-down rows) or BN + t (CTA 1's);
-                // otherwise source src owns columns BN + src R + t
+                // rank column t of source src lives at HN + src HR + t (t < HR: CTA 0's lora-down rows) or, for CTA 1's rows,
+                // behind the Y columns and CTA 0's whole rank block: BN + S HR + src HR + (t - HR)
                 uint32_t v[2][8];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                   const int t0 = (c + u) * 8;
-                  const int col = kMerged ? (t0 < C::HR ? C::HN + t0 : C::BN + t0) : C::BN + src * R + t0;
+                  const int col = t0 < C::HR ? C::HN + src * C::HR + t0 : C::BN + (S - 1) * C::HR + src * C::HR + t0;
                   tmem_ld_x8(lane_addr + (tile_ctr & 1) * C::ACC1_COL + col, v[u]);
                 }
                 tmem_ld_wait();
@@ -566,7 +571,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
       for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
         const uint32_t buf = tile_ctr & 1;
         const int n0 = nt * C::BN;
-        const int gap = (kMerged && nt == nt0 && R > 0) ? C::HR : 0;      // merged first tile: Y columns >= HN sit HR further right
+        const int gap = (nt == nt0 && R > 0) ? C::LA_ROWS : 0;      // first tile: Y columns >= HN sit behind CTA 0's rank block
         mbar_wait(&acc_full[buf], (tile_ctr >> 1) & 1);
         if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(48 + 2 * tile_ctr);
         tc_fence_after();
@@ -774,7 +779,8 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
     rc = make_tmap_2d_bf16(&gm.ym32[q], gm.y[q], M, N, N * 2, 32, 32, TMAP_SW_64);
     if (rc != SDT_OK) return rc;
     if (R > 0) {
-      rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
+      if (S == 1) rc = make_tmap_2d_bf16(&gm.la[q], pr.la, R, K, K * 2, C::HR, C::BK, TMAP_SW_128);
+      else        rc = make_tmap_halves_bf16(&gm.la[q], pr.la, R, K, K * 2, C::LA_ROWS, C::BK);
       if (rc != SDT_OK) return rc;
       rc = make_tmap_2d_bf16(&gm.lb[q], pr.lb, N, R, (uint64_t)R * 2, C::HN, R, R == 64 ? TMAP_SW_128 : (R == 32 ? TMAP_SW_64 : TMAP_SW_32));
       if (rc != SDT_OK) return rc;
