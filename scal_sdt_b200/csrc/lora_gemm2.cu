@@ -163,8 +163,8 @@ struct PairCfg {
   // With S > 1 sources the rank block of a CTA has S HR rows, source s owning rows [s HR, (s+1) HR) and the TMA zero-filling the
   // others (a source adds 0 to the other sources' columns), so the first tile is
   //   [Y 0..HN) | T_0 0..HR) .. T_{S-1} 0..HR) | Y HN..BN) | T_0 HR..R) .. T_{S-1} HR..R)]
-  // A separate N = R UMMA for the rank projection costs as much as the N = BN one next to it: in a CTA pair every UMMA takes
-  // max(113, N/2) cycles (profiles/r02_umma_pair_ss_vs_ts.txt).
+  // A separate N = R UMMA for the rank projection costs 39 cycles next to the N/2 = 80 of the BN-wide one: in a CTA pair a UMMA takes
+  // max(39, N/2) cycles (profiles/r02_umma_pair_ss_vs_ts.txt).
   static constexpr int ACC1_COL = BN + S * R;
   static_assert(2 * ACC1_COL <= 512, "TMEM budget");
   // TS mode: k-blocks of X ([128 rows x 64 k] = 32 columns) staged in the TMEM columns behind the two accumulators
@@ -392,8 +392,8 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
                 const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
                 const uint32_t wa = xa + C::X_BYTES;        // [W half ; lora-down block] is one B operand
                 if (C::A_SLOTS >= 1 && p.ts) {
-                  // TS mode: the k-block of X goes to tensor memory first; an SS-mode UMMA pays ~38 cycles for fetching its A
-                  // operand from shared memory before the math starts, a TS-mode one ~1 (tools/umma_bench.cu)
+                  // TS mode (opt-in, for A/B only): the k-block of X goes to tensor memory first.  A single-CTA SS-mode UMMA pays ~38
+                  // cycles for fetching A from shared memory, but a CTA-pair one does not (tools/umma_pair_bench.cu): measured slower
                   constexpr uint32_t kASlots = C::A_SLOTS >= 1 ? C::A_SLOTS : 1;
                   const uint32_t a_tm = tmem_base + C::A_TM_COL + (it % kASlots) * 32;
 #pragma unroll

@@ -2,7 +2,8 @@
 occur (``cuobjdump -sass``; runs without a GPU).  `python tools/sass_histogram.py > profiles/r02_sass_histogram.txt`
 
     UTCHMMA[.2CTA]   tcgen05.mma kind::f16 (bf16 / fp16 operands, f32 accumulate in TMEM); .2CTA = cta_group::2
-    UTMALDG          cp.async.bulk.tensor (TMA tile loads); UTMACCTL = prefetch.tensormap
+    UTMALDG / UTMASTG cp.async.bulk.tensor (TMA tile loads / stores); UTMACCTL = prefetch.tensormap
+    UTCCP            tcgen05.cp (shared -> tensor memory; the opt-in TS-mode main loop)
     LDTM             tcgen05.ld (TMEM -> registers)            UTCBAR  tcgen05.commit -> mbarrier
     SYNCS            mbarrier arrive / try_wait               UTCATOMSWS  tcgen05.alloc / dealloc
     ACQBULK / PREEXIT griddepcontrol.wait / .launch_dependents (programmatic dependent launch)
@@ -15,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "scal_sdt_b200", "_build", "libsdt_b200.so")
-KEYS = ["UTCHMMA.2CTA", "UTCHMMA", "UTMALDG", "UTMACCTL", "LDTM", "UTCBAR", "SYNCS", "UTCATOMSWS", "ACQBULK", "PREEXIT", "RED", "ATOM",
+KEYS = ["UTCHMMA.2CTA", "UTCHMMA", "UTCCP", "UTMALDG", "UTMASTG", "UTMACCTL", "LDTM", "UTCBAR", "SYNCS", "UTCATOMSWS", "ACQBULK", "PREEXIT", "RED", "ATOM",
         "HMMA", "FFMA", "MUFU"]
 
 

@@ -56,11 +56,15 @@ __device__ __forceinline__ void commit2_both(uint64_t* bar) {
 }
 
 struct RateOut { long long cycles; };
-enum { SS = 0, TS = 1, CPTS_STEP = 2, CPTS_BLOCK = 3, CP_ONLY = 4 };
+enum { SS = 0, TS = 1, CPTS_STEP = 2, CPTS_BLOCK = 3, CP_ONLY = 4, SS_ALT = 5, N_MODES = 6 };
 
-// smem per CTA: A [128 x 64] bf16 SW128 (16 KiB) | B [128 x 64] bf16 SW128 (16 KiB, the first N/2 rows are this CTA's half)
+// smem per CTA: A [128 x 64] bf16 SW128 (16 KiB) | B [128 x 64] bf16 SW128 (16 KiB, the first N/2 rows are this CTA's half).
+// MODE is a template argument and every descriptor is formed before the timed loop: the loop body is the UMMAs / copies and nothing
+// else.  (A first version chose the mode with run-time branches inside the loop; a lone issuing thread then needed ~113 cycles per
+// UMMA for the branches alone and every N up to 224 "cost" 113 cycles -- an artefact of the benchmark, not of the tensor core.)
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-pair_rate_kernel(int N, int mode, int iters, RateOut* out, float* dump) {
+pair_rate_kernel(int N, int iters, RateOut* out, float* dump) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_s = smem;
@@ -88,22 +92,44 @@ pair_rate_kernel(int N, int mode, int iters, RateOut* out, float* dump) {
     constexpr uint64_t d_sw128 = make_smem_desc_base(16, 1024, kLayoutSW128);
     long long t0 = 0;
     if (elect_one()) {
+      uint64_t ad[4], bd[4];
+      for (int k = 0; k < 4; ++k) {
+        ad[k] = smem_desc(d_sw128, smem_u32(a_s) + k * 32);
+        bd[k] = smem_desc(d_sw128, smem_u32(b_s) + k * 32);
+      }
       // defined contents for the TS-only mode
-      for (int k = 0; k < 4; ++k) cp2_128x256b(a_tm + k * 8, smem_desc(d_sw128, smem_u32(a_s) + k * 32));
-      for (int k = 0; k < 4; ++k) cp2_128x256b(a_tm + 32 + k * 8, smem_desc(d_sw128, smem_u32(a_s) + k * 32));
-      t0 = clock64();
-      for (int it = 0; it < iters; ++it) {
-        const uint32_t slot = a_tm + (it & 1) * 32;
-        if (mode == CPTS_BLOCK)
-          for (int k = 0; k < 4; ++k) cp2_128x256b(slot + k * 8, smem_desc(d_sw128, smem_u32(a_s) + k * 32));
-#pragma unroll
+      for (int k = 0; k < 4; ++k) cp2_128x256b(a_tm + k * 8, ad[k]);
+      for (int k = 0; k < 4; ++k) cp2_128x256b(a_tm + 32 + k * 8, ad[k]);
+      if (dump != nullptr) {
+        // layout check: ONE k-block, accumulate off on the first UMMA
+        if (MODE == CPTS_BLOCK)
+          for (int k = 0; k < 4; ++k) cp2_128x256b(a_tm + k * 8, ad[k]);
         for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = smem_desc(d_sw128, smem_u32(a_s) + k * 32);
-          const uint64_t bd = smem_desc(d_sw128, smem_u32(b_s) + k * 32);
-          const uint32_t acc = (it | k) != 0;
-          if (mode == SS) umma2_ss(tmem_base, ad, bd, idesc, acc);
-          if (mode == CPTS_STEP || mode == CP_ONLY) cp2_128x256b(slot + k * 8, ad);
-          if (mode == TS || mode == CPTS_STEP || mode == CPTS_BLOCK) umma2_ts(tmem_base, slot + k * 8, bd, idesc, acc);
+          if (MODE == SS || MODE == SS_ALT) umma2_ss(tmem_base, ad[k], bd[k], idesc, k != 0);
+          if (MODE == CPTS_STEP) cp2_128x256b(a_tm + k * 8, ad[k]);
+          if (MODE == TS || MODE == CPTS_STEP || MODE == CPTS_BLOCK) umma2_ts(tmem_base, a_tm + k * 8, bd[k], idesc, k != 0);
+        }
+      } else {
+        t0 = clock64();
+#pragma unroll 1
+        for (int it = 0; it < iters; it += 2) {
+          // two k-blocks per trip, A staging slots 0 / 1 in turn
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t slot = a_tm + h * 32;
+            if (MODE == CPTS_BLOCK) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) cp2_128x256b(slot + k * 8, ad[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (MODE == SS) umma2_ss(tmem_base, ad[k], bd[k], idesc, 1u);
+              // two independent accumulators in turn (N <= 176): is the floor a dependent-accumulate latency or an issue interval?
+              if (MODE == SS_ALT) umma2_ss(tmem_base + (k & 1) * 176, ad[k], bd[k], idesc, 1u);
+              if (MODE == CPTS_STEP || MODE == CP_ONLY) cp2_128x256b(slot + k * 8, ad[k]);
+              if (MODE == TS || MODE == CPTS_STEP || MODE == CPTS_BLOCK) umma2_ts(tmem_base, slot + k * 8, bd[k], idesc, 1u);
+            }
+          }
         }
       }
       commit2_both(&done_bar);
@@ -132,27 +158,39 @@ pair_rate_kernel(int N, int mode, int iters, RateOut* out, float* dump) {
   if (warp == 0) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
 }
 
+typedef void (*KernelFn)(int, int, RateOut*, float*);
+static KernelFn kernel_of(int mode) {
+  switch (mode) {
+    case SS: return pair_rate_kernel<SS>;
+    case TS: return pair_rate_kernel<TS>;
+    case CPTS_STEP: return pair_rate_kernel<CPTS_STEP>;
+    case CPTS_BLOCK: return pair_rate_kernel<CPTS_BLOCK>;
+    case CP_ONLY: return pair_rate_kernel<CP_ONLY>;
+    default: return pair_rate_kernel<SS_ALT>;
+  }
+}
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 int main() {
   const int smem = 1024 + 32768;
-  CK(cudaFuncSetAttribute(pair_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int m = 0; m < N_MODES; ++m) CK(cudaFuncSetAttribute(kernel_of(m), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   RateOut* out;
   CK(cudaMalloc(&out, 74 * sizeof(RateOut)));
   float* dump;
   CK(cudaMalloc(&dump, 256 * 256 * 4));
-  const char* names[] = {"SS", "TS (A resident)", "CP+TS per k-step", "CP+TS per k-block", "CP only"};
+  const char* names[] = {"SS", "TS (A resident)", "CP+TS per k-step", "CP+TS per k-block", "CP only", "SS, 2 accumulators"};
   // ---- layout check: one k-block, accumulate off on the first UMMA
   {
     std::vector<float> ref(256 * 256), got(256 * 256);
     const int N = 160;
     CK(cudaMemset(dump, 0, 256 * 256 * 4));
-    pair_rate_kernel<<<2, 128, smem>>>(N, SS, 1, out, dump);
+    kernel_of(SS)<<<2, 128, smem>>>(N, 1, out, dump);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(ref.data(), dump, ref.size() * 4, cudaMemcpyDeviceToHost));
     for (int mode : {CPTS_STEP, CPTS_BLOCK}) {
       CK(cudaMemset(dump, 0, 256 * 256 * 4));
-      pair_rate_kernel<<<2, 128, smem>>>(N, mode, 1, out, dump);
+      kernel_of(mode)<<<2, 128, smem>>>(N, 1, out, dump);
       CK(cudaDeviceSynchronize());
       CK(cudaMemcpy(got.data(), dump, got.size() * 4, cudaMemcpyDeviceToHost));
       double maxd = 0, maxref = 0;
@@ -167,9 +205,10 @@ int main() {
   // ---- rates
   const int iters = 2000;
   for (int grid_pairs : {1, 74})
-    for (int N : {64, 128, 160, 176, 224, 240, 256})
-      for (int mode : {SS, TS, CPTS_STEP, CPTS_BLOCK, CP_ONLY}) {
-        pair_rate_kernel<<<2 * grid_pairs, 128, smem>>>(N, mode, iters, out, nullptr);
+    for (int N : {16, 32, 64, 96, 128, 160, 176, 208, 224, 240, 256})
+      for (int mode = 0; mode < N_MODES; ++mode) {
+        if (mode == SS_ALT && N > 176) continue;
+        kernel_of(mode)<<<2 * grid_pairs, 128, smem>>>(N, iters, out, nullptr);
         CK(cudaDeviceSynchronize());
         std::vector<RateOut> h(grid_pairs);
         CK(cudaMemcpy(h.data(), out, grid_pairs * sizeof(RateOut), cudaMemcpyDeviceToHost));
