@@ -835,16 +835,17 @@ int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scali
 #define SDT_PAIR(BN, R, G) return launch_pair<BN, R, G, 1>(probs, n_probs, scaling, M, K, N, f16, st)
 #define SDT_PAIR_R(BN, G)                                                                     \
   switch (r) { case 16: SDT_PAIR(BN, 16, G); case 32: SDT_PAIR(BN, 32, G); default: SDT_PAIR(BN, 64, G); }
-  // wide tiles (more FLOP per byte brought into the SM) when the rank accumulators still fit next to two 224-column
-  // main accumulators (2*224 + 2*R <= 512), the ragged last tile wastes little and there are enough tiles to keep every
-  // pair busy: N >= 2048, or N >= 1280 with at least four rounds of tiles (measured: 32768x320x1280 41.3 -> 36.7 us, while
-  // 2048x*x1280 -- 48 tiles on 74 pairs -- is faster with 160-wide tiles)
-  const int64_t n224 = (N + 223) / 224 * 224;
-  const int64_t tiles224 = ((M + 255) / 256) * (n224 / 224);
-  const int64_t wide_min_n = debug_get(22) ? (int64_t)debug_get(22) : ((N >= 1280 && tiles224 >= 4 * (num_sms() / 2)) ? 1280 : 2048);
-  const bool wide = r <= 32 && N >= wide_min_n && n224 * 100 <= N * 106 && debug_get(12) == 0;
+  // wide tiles (more FLOP per byte brought into the SM) when the rank accumulators still fit next to two main accumulators
+  // (2 * (BW + R) <= 512 TMEM columns: 224-wide up to rank 32, 192-wide at rank 64), the ragged last tile wastes little and there
+  // are enough tiles to keep every pair busy: N >= 2048, or N >= 1280 with at least four rounds of tiles (measured: 32768x320x1280
+  // 41.3 -> 36.7 us, while 2048x*x1280 -- 48 tiles on 74 pairs -- is faster with 160-wide tiles)
+  const int64_t BW = r <= 32 ? 224 : 192;
+  const int64_t n_wide = (N + BW - 1) / BW * BW;
+  const int64_t tiles_wide = ((M + 255) / 256) * (n_wide / BW);
+  const int64_t wide_min_n = debug_get(22) ? (int64_t)debug_get(22) : ((N >= 1280 && tiles_wide >= 4 * (num_sms() / 2)) ? 1280 : 2048);
+  const bool wide = N >= wide_min_n && n_wide * 100 <= N * 106 && debug_get(12) == 0;
   if (n_probs == 1) {
-    if (wide) { switch (r) { case 0: SDT_PAIR(224, 0, 1); case 16: SDT_PAIR(224, 16, 1); default: SDT_PAIR(224, 32, 1); } }
+    if (wide) { switch (r) { case 0: SDT_PAIR(224, 0, 1); case 16: SDT_PAIR(224, 16, 1); case 32: SDT_PAIR(224, 32, 1); default: SDT_PAIR(192, 64, 1); } }
     if (r == 0) { if (bn160) SDT_PAIR(160, 0, 1); else SDT_PAIR(128, 0, 1); }
     if (bn160) { SDT_PAIR_R(160, 1) } else { SDT_PAIR_R(128, 1) }
   }

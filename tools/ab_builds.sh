@@ -8,8 +8,8 @@ lib=scal_sdt_b200/_build/libsdt_b200.so
 cp $lib /tmp/lib_new.so
 mkdir -p gpurun_out
 for i in $(seq 1 $rounds); do
-  cp $other $lib; python bench.py --no-cpu-baseline --no-torch-baseline > gpurun_out/${tag}_other_$i.json 2>/dev/null
-  cp /tmp/lib_new.so $lib; python bench.py --no-cpu-baseline --no-torch-baseline > gpurun_out/${tag}_new_$i.json 2>/dev/null
+  cp $other $lib; python bench.py --workload ${WORKLOAD:-cfg2} --no-cpu-baseline --no-torch-baseline > gpurun_out/${tag}_other_$i.json 2>/dev/null
+  cp /tmp/lib_new.so $lib; python bench.py --workload ${WORKLOAD:-cfg2} --no-cpu-baseline --no-torch-baseline > gpurun_out/${tag}_new_$i.json 2>/dev/null
 done
 cp /tmp/lib_new.so $lib
 python - "$tag" <<'PY'

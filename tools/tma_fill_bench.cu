@@ -46,7 +46,7 @@ struct Out { long long cycles; };
 
 // CL = cluster size (1, 2, 4); MC = multicast; shared = the CTAs of a cluster read the same tiles
 template <int CL, bool MC>
-__global__ void __launch_bounds__(32, 1) fill_kernel(const __grid_constant__ CUtensorMap full_map, const __grid_constant__ CUtensorMap part_map,
+__global__ void __launch_bounds__(64, 1) fill_kernel(const __grid_constant__ CUtensorMap full_map, const __grid_constant__ CUtensorMap part_map,
                                                     int shared, int iters, Out* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -60,26 +60,40 @@ __global__ void __launch_bounds__(32, 1) fill_kernel(const __grid_constant__ CUt
   }
   __syncthreads();
   if (CL > 1) cluster_sync_all();
-  if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    for (int it = 0; it < iters + kStages; ++it) {
-      const int s = it % kStages;
-      if (it >= kStages) {
-        mbar_wait(&full[s], ((it / kStages) - 1) & 1);               // the tile of the previous round has landed here
-        if (MC) {
-          for (uint32_t r = 0; r < CL; ++r) remote_arrive(&empty[s], r);   // my stage s may be overwritten by anyone
-          mbar_wait(&empty[s], ((it / kStages) - 1) & 1);                   // ... and everyone's may be overwritten by me
+  if (!MC) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int it = 0; it < iters + kStages; ++it) {
+        const int s = it % kStages;
+        if (it >= kStages) mbar_wait(&full[s], ((it / kStages) - 1) & 1);               // the tile of the previous round has landed here
+        if (it < iters) {
+          const int row0 = (group * kTilesPerGroup + it % kTilesPerGroup) * kTileRows;
+          mbar_arrive_expect_tx(&full[s], kTileBytes);
+          tma_load_2d(smem + s * kTileBytes, &full_map, 0, row0, &full[s]);
         }
       }
-      if (it < iters) {
-        const int row0 = (group * kTilesPerGroup + it % kTilesPerGroup) * kTileRows;
-        mbar_arrive_expect_tx(&full[s], kTileBytes);
-        if (MC) tma_load_2d_mc(smem + s * kTileBytes + rank * (kTileBytes / CL), &part_map, 0, row0 + (int)rank * (kTileRows / CL), &full[s],
-                               (uint16_t)((1u << CL) - 1));
-        else    tma_load_2d(smem + s * kTileBytes, &full_map, 0, row0, &full[s]);
-      }
+      out[blockIdx.x].cycles = clock64() - t0;
     }
+  } else if (threadIdx.x == 0) {
+    // producer: my 1 / CL of the tile goes to every CTA of the cluster once all of them have released the stage
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % kStages;
+      if (it >= kStages) mbar_wait(&empty[s], ((it / kStages) - 1) & 1);
+      const int row0 = (group * kTilesPerGroup + it % kTilesPerGroup) * kTileRows;
+      mbar_arrive_expect_tx(&full[s], kTileBytes);
+      tma_load_2d_mc(smem + s * kTileBytes + rank * (kTileBytes / CL), &part_map, 0, row0 + (int)rank * (kTileRows / CL), &full[s],
+                     (uint16_t)((1u << CL) - 1));
+    }
+    for (int it = iters - kStages; it < iters; ++it) mbar_wait(&empty[it % kStages], (it / kStages) & 1);     // everything has landed everywhere
     out[blockIdx.x].cycles = clock64() - t0;
+  } else if (threadIdx.x == 32) {
+    // consumer: a landed stage is handed straight back to every producer of the cluster
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % kStages;
+      mbar_wait(&full[s], (it / kStages) & 1);
+      for (uint32_t r = 0; r < CL; ++r) remote_arrive(&empty[s], r);
+    }
   }
   __syncthreads();
   if (CL > 1) cluster_sync_all();
@@ -105,7 +119,7 @@ static void run(const char* name, void* base, uint64_t rows, int shared, Out* ou
   CK(cudaFuncSetAttribute(fill_kernel<CL, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const CUtensorMap full_map = make_map(base, rows, kTileRows), part_map = make_map(base, rows, kTileRows / CL);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
