@@ -130,7 +130,11 @@ using namespace pair;
 // S = number of SOURCES whose products are summed into one output (S = 1: a plain projection; S = 3: the input gradient of
 // q / k / v, dX = sum_s dY_s W_s + (s dY_s B_s) A_s, as ONE K loop over the concatenated contraction).  Every source has its own
 // rank-R accumulator, lora-up tile and slice of the tail's A operand.
-template <int BN_, int R_, int S_ = 1>
+// DT ("double tile"): the two column tiles of a work item run ONE joint K loop -- every X k-block is brought into the SM once and
+// feeds both accumulator buffers (stage = X | W of tile A | lora-down | W of tile B).  The K loop is bound by the bytes an SM can
+// land from L2 (~55 B/clk, profiles/r02_tma_fill_rate.txt): 2 x 26.6 KB per k-block pair become 36.9 KB.  The price: both TMEM
+// buffers belong to the item, so its epilogue no longer overlaps the next item's K loop -- for long K loops only.
+template <int BN_, int R_, int S_ = 1, bool DT_ = false>
 struct PairCfg {
   static constexpr int BM = 128, BN = BN_, BK = 64, R = R_, HN = BN_ / 2, HR = R_ / 2, S = S_;
   static constexpr int X_BYTES = BM * BK * 2;                       // own 128 rows of X
@@ -138,13 +142,14 @@ struct PairCfg {
   // own half of the lora-down k-block; with S sources a block of S HR rows in which only the current source's rows are non-zero
   static constexpr int LA_ROWS = S * HR;
   static constexpr int LA_BYTES = ((LA_ROWS * BK * 2 + 1023) / 1024) * 1024;
-  static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + LA_BYTES;
+  static constexpr bool DT = DT_;
+  static constexpr int STAGE_BYTES = X_BYTES + W_BYTES + LA_BYTES + (DT ? W_BYTES : 0);
   static constexpr int LB_TILE = (((HN + LA_ROWS) * R * 2 + 1023) / 1024) * 1024;    // own half of one lora-up tile [BN/2, R] + S HR zero rows
   static constexpr int LB_BYTES = S * LB_TILE;
   static constexpr int KEXT = S * R + 16;
   static constexpr int T_SBO = (KEXT / 8) * 128;
   static constexpr int T_BYTES = (BM / 8) * T_SBO;
-  static constexpr int BIAS_BYTES = (((HN + HR) * 32 + 1023) / 1024) * 1024;   // own half of the bias operand [BN/2, 16] + HR zero rows
+  static constexpr int BIAS_BYTES = (((HN + HR) * 32 + 255) / 256) * 256;      // own half of the bias operand [BN/2, 16] + HR zero rows (un-swizzled: no 1 KiB alignment; the 256 bytes saved are the fourth stage of the rank-16 double-tile kernel)
   static constexpr int BAR_BYTES = 256;
   // 64-column blocks of staging per epilogue warp.  2 (a warp's whole share of a <= 160-wide tile: the accumulator is handed
   // back before the stores, which pays for K = 320) or 1 (224-wide tiles: a pipeline stage is worth more there -- measured)
@@ -174,6 +179,7 @@ struct PairCfg {
   static_assert(R == 0 || R == 16 || R == 32 || R == 64, "rank must be padded to 16/32/64");
   static_assert(kStages >= 3, "pipeline depth");
   static_assert(W_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
+  static_assert(!DT || S == 1, "double tiles: one source");
 };
 
 constexpr int kPairThreads = 15 * 32;      // producer, UMMA issuer, 4 side warps, 8 epilogue warps, tail issuer
@@ -191,6 +197,7 @@ struct PairParams {
   int geglu_I;
   uint8_t* act_out;
   int mixed;              // problems have their own output width (GemmGroup::n / tile_begin); one column tile per work item
+  int dt_items;           // double-tile kernel: every work item is exactly two column tiles (checked by the launcher)
   int ts;                 // A operand through tensor memory (tcgen05.cp of each k-block, then TS-mode UMMAs); needs C::A_SLOTS >= 1
   long long* trace;       // debug: clock64 stamps of CTA 0 (null in production)
 };
@@ -227,10 +234,11 @@ __device__ __forceinline__ PairItem decode_pair_item(int item, const PairParams&
   return c;
 }
 
-template <int BN, int R, int G, int S, bool GEGLU = false>
+template <int BN, int R, int G, int S, bool GEGLU = false, bool DT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams p) {
-  using C = PairCfg<BN, R, S>;
+  using C = PairCfg<BN, R, S, DT>;
+  static_assert(!DT || (G == 1 && S == 1 && !GEGLU), "double tiles: one plain problem");
   static_assert(S == 1 || (G >= S && R > 0), "summed sources live in the entries of the group");
   static_assert(!GEGLU || (G == 1 && S == 1 && R > 0 && C::STG_BLOCKS >= 2 && C::HN % 8 == 0), "GEGLU epilogue: one merged problem, <= 160-wide tiles");
   const int n_src = S == 1 ? 1 : p.n_src;
@@ -327,6 +335,33 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         const int g = ic.g;
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, ic.n_tiles);
+        if (DT) {
+          // tiles nt0 (A: carries the rank projection) and nt0 + 1 (B) in one joint K loop: X once per k-block
+          const int nA = nt0 * C::BN + (int)rank * C::HN, nB = nA + C::BN;
+          const uint32_t tx = 2u * (C::X_BYTES + 2 * C::W_BYTES + (R > 0 ? C::LA_ROWS * C::BK * 2 : 0));
+          for (int kb = 0; kb < nk; ++kb, ++it) {
+            const int s = it % C::kStages;
+            mbar_wait(&empty[s], ((it / C::kStages) & 1) ^ 1);
+            uint8_t* st = smem + s * C::STAGE_BYTES;
+            const uint32_t full_leader = map_to_rank(&full[s], 0);
+            if (leader) mbar_arrive_expect_tx(&full[s], tx);
+            if (it == 0) SDT_TRACE2(2);
+            tma_load_2d_pair(st, &gm.x[0], kb * C::BK, m0, full_leader);
+            tma_load_2d_pair(st + C::X_BYTES, &gm.w[0], kb * C::BK, nA, full_leader);
+            if (R > 0) tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES, &gm.la[0], kb * C::BK, (int)rank * C::HR, full_leader);
+            tma_load_2d_pair(st + C::X_BYTES + C::W_BYTES + C::LA_BYTES, &gm.w[0], kb * C::BK, nB, full_leader);
+          }
+          if (R > 0) {
+            for (int h = 0; h < 2; ++h, ++tile_ctr) {
+              mbar_wait(lb_empty, (tile_ctr & 1) ^ 1);
+              if (leader) mbar_arrive_expect_tx(lb_full, 2u * C::HN * R * 2);
+              tma_load_2d_pair(lb_smem, &gm.lb[0], 0, h == 0 ? nA : nB, lb_full_leader);
+            }
+          } else {
+            tile_ctr += 2;
+          }
+          continue;
+        }
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
           // rows of W / lora-up this CTA contributes to the tile.  cta_group::2 runs the N index over CTA 0's rows, then CTA 1's:
@@ -375,6 +410,43 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
         const int g = ic.g;
         const int nt0 = g * p.group_size;
         const int nt1 = min(nt0 + p.group_size, ic.n_tiles);
+        if (DT) {
+          // joint K loop of the item's two tiles: buffer 0 <- tile A ([W ; lora-down], N = BN + R), buffer 1 <- tile B; both buffers
+          // must have been drained (tile_ctr is even at every item)
+          const uint32_t ph = ((tile_ctr >> 1) & 1) ^ 1;
+          mbar_wait(&acc_empty[0], ph);
+          mbar_wait(&acc_empty[1], ph);
+          tc_fence_after();
+          if (lane == 0 && tile_ctr < 6) SDT_TRACE2(8 + 4 * tile_ctr);
+          const uint32_t dA = tmem_base, dB = tmem_base + C::ACC1_COL;
+          for (int kb = 0; kb < nk; ++kb, ++it) {
+            const int s = it % C::kStages;
+            mbar_wait(&full[s], (it / C::kStages) & 1);
+            if (lane == 0 && tile_ctr < 6 && kb == 0) SDT_TRACE2(9 + 4 * tile_ctr);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t xa = smem_u32(smem + s * C::STAGE_BYTES);
+              const uint32_t wa = xa + C::X_BYTES, wb = wa + C::W_BYTES + C::LA_BYTES;
+#pragma unroll
+              for (int k = 0; k < C::BK / 16; ++k) {
+                const uint64_t a_desc = smem_desc(d_sw128, xa + k * 32);
+                umma2_f16_ss(dA, a_desc, smem_desc(d_sw128, wa + k * 32), R > 0 ? idesc_both : idesc_main, (kb | k) != 0);
+                umma2_f16_ss(dB, a_desc, smem_desc(d_sw128, wb + k * 32), idesc_main, (kb | k) != 0);
+              }
+              umma2_commit_both(&empty[s]);
+            }
+            __syncwarp();
+          }
+          if (lane == 0 && tile_ctr < 6) SDT_TRACE2(10 + 4 * tile_ctr);
+          if (elect_one()) {
+            if (R > 0) umma2_commit_both(t_full);
+            if (has_tail) { umma2_commit_leader(&kdone[0]); umma2_commit_leader(&kdone[1]); }
+            else          { umma2_commit_both(&acc_full[0]); umma2_commit_both(&acc_full[1]); }
+          }
+          __syncwarp();
+          tile_ctr += 2;
+          continue;
+        }
         for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
           const bool first = (nt == nt0) && R > 0;
           const uint32_t buf = tile_ctr & 1;
@@ -757,13 +829,13 @@ static void choose_groups_pair(int m_tiles, int n_tiles, int BN, int R, int pair
 }
 
 // n_probs problems as independent work items (S == 1), or n_probs SOURCES summed into probs[0].y (S > 1)
-template <int BN, int R, int G, int S, bool GEGLU = false>
+template <int BN, int R, int G, int S, bool GEGLU = false, bool DT = false>
 static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int64_t M, int64_t K, int64_t N, bool f16, cudaStream_t st,
                        void* act_out = nullptr) {
-  using C = PairCfg<BN, R, S>;
+  using C = PairCfg<BN, R, S, DT>;
   static bool attr_set = false;
   if (!attr_set) {
-    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R, G, S, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SDT_CUDA_OK(cudaFuncSetAttribute(lora_gemm_pair_kernel<BN, R, G, S, GEGLU, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   GemmGroup<G> gm;
@@ -821,9 +893,15 @@ static int launch_pair(const LoraProblem* probs, int n_probs, float scaling, int
     p.group_size = (int)debug_get(20);
     p.n_groups = (p.n_tiles + p.group_size - 1) / p.group_size;
   }
+  p.dt_items = DT ? 1 : 0;
+  if (DT) {                                                         // every item = two FULL column tiles (the dispatcher checked N % (2 BN) == 0)
+    if (N % (2 * BN) != 0) { set_error("lora_gemm_pair(double tile): N = %lld is not a multiple of %d", (long long)N, 2 * BN); return SDT_ERR_UNSUPPORTED; }
+    p.group_size = 2;
+    p.n_groups = p.n_tiles / 2;
+  }
   p.n_items = m_tiles * p.n_probs * p.n_groups;
   const int pairs = p.n_items < pairs_max ? p.n_items : pairs_max;
-  SDT_CUDA_OK(launch_kernel(lora_gemm_pair_kernel<BN, R, G, S, GEGLU>, dim3(2 * pairs), dim3(kPairThreads), C::SMEM_BYTES, st, true, gm, p));
+  SDT_CUDA_OK(launch_kernel(lora_gemm_pair_kernel<BN, R, G, S, GEGLU, DT>, dim3(2 * pairs), dim3(kPairThreads), C::SMEM_BYTES, st, true, gm, p));
   SDT_LAUNCH_OK("lora_gemm_pair");
   return SDT_OK;
 }
@@ -844,6 +922,17 @@ int lora_gemm_pair_group_bf16(const LoraProblem* probs, int n_probs, float scali
   const int64_t tiles_wide = ((M + 255) / 256) * (n_wide / BW);
   const int64_t wide_min_n = debug_get(22) ? (int64_t)debug_get(22) : ((N >= 1280 && tiles_wide >= 4 * (num_sms() / 2)) ? 1280 : 2048);
   const bool wide = N >= wide_min_n && n_wide * 100 <= N * 106 && debug_get(12) == 0;
+  // double tiles (one joint K loop for the two column tiles of an item, X landed once): long K loops whose items still fill the
+  // machine.  sdt_debug_set(31, k): minimum K (default 1280); 1 = never.
+  const int64_t dt_min_k = debug_get(31) ? (int64_t)debug_get(31) : 1280;
+  const int64_t dt_items = ((M + 255) / 256) * (N / 320);
+  if (n_probs == 1 && !wide && bn160 && r > 0 && N % 320 == 0 && dt_min_k > 1 && K >= dt_min_k && dt_items * 10 >= (num_sms() / 2) * 8) {
+    switch (r) {
+      case 16: return launch_pair<160, 16, 1, 1, false, true>(probs, n_probs, scaling, M, K, N, f16, st);
+      case 32: return launch_pair<160, 32, 1, 1, false, true>(probs, n_probs, scaling, M, K, N, f16, st);
+      default: return launch_pair<160, 64, 1, 1, false, true>(probs, n_probs, scaling, M, K, N, f16, st);
+    }
+  }
   if (n_probs == 1) {
     if (wide) { switch (r) { case 0: SDT_PAIR(224, 0, 1); case 16: SDT_PAIR(224, 16, 1); case 32: SDT_PAIR(224, 32, 1); default: SDT_PAIR(192, 64, 1); } }
     if (r == 0) { if (bn160) SDT_PAIR(160, 0, 1); else SDT_PAIR(128, 0, 1); }

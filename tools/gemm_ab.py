@@ -52,7 +52,7 @@ def case(M, K, N, R, G, settings):
     out = []
     ref_out = None
     for name, kv in settings:
-        for k in (11, 12, 13, 14, 20, 22, 30):
+        for k in (11, 12, 13, 14, 20, 22, 30, 31):
             lib.sdt_debug_set(k, 0)
         for k, v in kv.items():
             lib.sdt_debug_set(k, v)
@@ -64,7 +64,7 @@ def case(M, K, N, R, G, settings):
         else:
             same = " bit-equal to the first setting" if all(torch.equal(a, b) for a, b in zip(ref_out, ys + ts)) else " DIFFERS from the first setting"
         out.append(f"{name}: warm {warm:6.1f} us {fl / warm / 1e6:6.0f} TF/s | cold {cold:6.1f} us {fl / cold / 1e6:6.0f} TF/s [{kn}]{same}")
-    for k in (11, 12, 13, 14, 20, 22, 30):
+    for k in (11, 12, 13, 14, 20, 22, 30, 31):
         lib.sdt_debug_set(k, 0)
     print(f"M={M} K={K} N={N} R={R} G={G}")
     for o in out:
@@ -76,6 +76,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "wide":
     SET = [("auto    ", {}), ("160-wide", {12: 1}), ("224 >=1280", {22: 1280}), ("224 >=1280 gs1", {22: 1280, 20: 1})]
 if len(sys.argv) > 1 and sys.argv[1] == "ts":        # A operand through tensor memory (tcgen05.cp + TS-mode UMMAs) vs shared memory
     SET = [("SS", {}), ("TS", {30: 1}), ("SS", {}), ("TS", {30: 1})]
+if len(sys.argv) > 1 and sys.argv[1] == "dt":        # double tiles (joint K loop of two column tiles, X landed once) vs one tile at a time
+    SET = [("single tiles", {31: 1}), ("double, K>=1280", {31: 1280}), ("single tiles", {31: 1}), ("double, K>=1280", {31: 1280})]
+    for shp in [(32768, 1280, 320, 16, 1), (8192, 2560, 640, 16, 1), (32768, 2560, 320, 16, 1), (8192, 5120, 640, 16, 1), (8192, 1280, 640, 16, 1),
+                (98304, 2560, 320, 16, 1), (8192, 2560, 640, 64, 1), (32768, 2560, 320, 64, 1)]:
+        case(*shp, SET)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "groups":
     SET = [("auto", {}), ("gs1 ", {20: 1}), ("gs2 ", {20: 2}), ("gs3 ", {20: 3}), ("gs4 ", {20: 4}), ("gs6 ", {20: 6})]
 SHAPES_BWD = [(32768, 320, 1280, 16, 1), (8192, 640, 2560, 16, 1), (2048, 1280, 5120, 16, 1), (32768, 2560, 320, 16, 1),
