@@ -15,6 +15,9 @@
 #include "sm100_ptx.cuh"
 #include "lora_gemm.cuh"
 
+// the double-tile instantiations leave their work-item loop early (`continue` in front of the per-tile loop)
+#pragma nv_diag_suppress 128
+
 namespace sdt {
 
 using namespace ptx;
@@ -157,7 +160,10 @@ struct PairCfg {
   static constexpr int STG_BYTES = 8 * STG_BLOCKS * 4096;           // 8 epilogue warps x their [32 rows x 128 B] transpose buffers
   static constexpr int FIXED_BYTES = 1024 + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
   static constexpr int kStagesMax = (232448 - FIXED_BYTES) / STAGE_BYTES;
-  static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
+#ifndef SDT_STAGE_CAP
+#define SDT_STAGE_CAP 8              // experiments: -DSDT_STAGE_CAP=n builds the kernels with a shallower ring
+#endif
+  static constexpr int kStages = kStagesMax > SDT_STAGE_CAP ? SDT_STAGE_CAP : kStagesMax;
   static constexpr int SMEM_BYTES = FIXED_BYTES + kStages * STAGE_BYTES;
   static constexpr int TMEM_COLS = 512;
   // TMEM: two accumulator buffers of BN + R columns.  On the first tile of an item ONE UMMA of N = BN + R computes the base
