@@ -157,7 +157,11 @@ struct PairCfg {
   // 64-column blocks of staging per epilogue warp.  2 (a warp's whole share of a <= 160-wide tile: the accumulator is handed
   // back before the stores, which pays for K = 320) or 1 (224-wide tiles: a pipeline stage is worth more there -- measured)
   static constexpr int STG_BLOCKS = BN <= 160 ? 2 : 1;
-  static constexpr int STG_BYTES = 8 * STG_BLOCKS * 4096;           // 8 epilogue warps x their [32 rows x 128 B] transpose buffers
+  // per epilogue warp: [32 rows x 128 B] transpose buffers.  A 160-wide tile gives a warp one full 64-column block and at most one odd
+  // 32-column block, staged as [32 x 64 B]: 4 + 2 KiB instead of 2 x 4 -- the 16 KiB are a pipeline stage (5 -> 6 at rank 16; a
+  // ring capped at 4 stages measured 7 % slower than 5, profiles/r02_pipeline_depth_ab.txt)
+  static constexpr int STG_WARP = STG_BLOCKS == 2 && BN == 160 ? 6144 : STG_BLOCKS * 4096;
+  static constexpr int STG_BYTES = 8 * STG_WARP;
   static constexpr int FIXED_BYTES = 1024 + LB_BYTES + STG_BYTES + T_BYTES + BIAS_BYTES + BAR_BYTES;
   static constexpr int kStagesMax = (232448 - FIXED_BYTES) / STAGE_BYTES;
 #ifndef SDT_STAGE_CAP
@@ -635,7 +639,7 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
     const int q = warp & 3;
     const int half = e >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t stg = smem_u32(stg_smem + e * C::STG_BLOCKS * 4096);
+    const uint32_t stg = smem_u32(stg_smem + e * C::STG_WARP);
     uint32_t acc_empty_leader[2] = {map_to_rank(&acc_empty[0], 0), map_to_rank(&acc_empty[1], 0)};
     uint32_t tile_ctr = 0;
     for (int item = pair_id; item < p.n_items; item += n_pairs) {
@@ -688,9 +692,10 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
               uint32_t pk[16];
               pack_acc32(v, pk, f16);
               // a full 64-column block is one [32 x 128 B] box in the 128-byte swizzle -- the layout the register path stages in;
-              // the odd 32-column block of a tile is a [32 x 64 B] box in the 64-byte swizzle
-              if (tma_out && subs == 1) stage_row_sw64(stg + slot * 4096, lane, pk);
-              else                      stage_row_chunk(stg + slot * 4096, lane, h, pk);
+              // the odd 32-column block of a tile is a [32 x 64 B] box in the 64-byte swizzle (for the register path too: the
+              // second slot of a warp has room for exactly that)
+              if (subs == 1) stage_row_sw64(stg + slot * 4096, lane, pk);
+              else           stage_row_chunk(stg + slot * 4096, lane, h, pk);
             }
           }
           tc_fence_before();
@@ -718,12 +723,12 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
             if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(80 + tile_ctr);
             {
-              const uint32_t stg_q = smem_u32(stg_smem) + (uint32_t)(e & 3) * (C::STG_BLOCKS * 4096);     // half 0's staging of this quarter
+              const uint32_t stg_q = smem_u32(stg_smem) + (uint32_t)(e & 3) * C::STG_WARP;     // half 0's staging of this quarter
               constexpr int kSlots = C::HN / 8;                                      // 16-byte slots per output row (64 columns: 8)
               auto staged = [&](int r, int tile_col) -> uint4 {
                 const int cb = tile_col >> 6, sl = (tile_col & 63) >> 3;
                 const uint32_t owner = (uint32_t)((cb + tile_ctr) & 1);               // which half staged block cb of this tile
-                const uint32_t base = stg_q + owner * (4u * C::STG_BLOCKS * 4096u) + (uint32_t)(cb >> 1) * 4096u;
+                const uint32_t base = stg_q + owner * (4u * C::STG_WARP) + (uint32_t)(cb >> 1) * 4096u;
                 return ld_shared_v4(base + r * 128 + ((sl ^ (r & 7)) << 4));
               };
               for (int task = lane; task < 16 * kSlots; task += 32) {
@@ -763,7 +768,8 @@ lora_gemm_pair_kernel(const __grid_constant__ GemmGroup<G> gm, const PairParams 
             // Phase 2: stream the staged blocks out (full 128-byte lines); the next tile's phase 1 follows in program order
             slot = 0;
             for (int cb = (tile_ctr + half) & 1; 2 * cb < n_sub; cb += 2, ++slot)
-              write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, ic.N, 4 * min(2, n_sub - 2 * cb), rp, f16);
+              write_staged_block(stg + slot * 4096, lane, yp, m0 + q * 32, p.M, n0 + cb * 64, ic.N, 4 * min(2, n_sub - 2 * cb), rp, f16,
+                                 /*rows of 64 bytes*/ n_sub - 2 * cb < 2);
           }
           __syncwarp();
           if (warp == 6 && lane == 0 && tile_ctr < 6) SDT_TRACE2(70 + tile_ctr);

@@ -213,19 +213,21 @@ __device__ __forceinline__ uint32_t add_packed_pair(uint32_t a, uint32_t b, bool
 }
 
 // write the staged block out: rows [row0, row0 + 32) x 16-byte slots [0, n_slots) starting at column col0 of a row-major
-// bf16 matrix with N columns (N % 8 == 0); rows >= M and columns >= N are clipped.  res (optional, same shape as y): the
+// bf16 matrix with N columns (N % 8 == 0); rows >= M and columns >= N are clipped (sw64: n_slots <= 4).  res (optional, same shape as y): the
 // residual stream the projection's output is added to (x + ff(h), y + res of a transformer block) -- read here, added to the
 // rounded output and rounded again, exactly torch's separate add, without that add's pass over both tensors.
 __device__ __forceinline__ void write_staged_block(uint32_t stg, int lane, uint8_t* y, int row0, int M, int col0, int N, int n_slots,
-                                                   const uint8_t* res = nullptr, bool f16 = false) {
+                                                   const uint8_t* res = nullptr, bool f16 = false, bool sw64 = false) {
   const int c = lane & 7;
+  // staged as [32 x 128 B] (16-byte slot c of row r at c ^ (r & 7)) or, the odd 32-column block, as [32 x 64 B] (slot c at c ^ ((r >> 1) & 3))
+  auto slot_addr = [&](int rl) -> uint32_t { return sw64 ? stg + rl * 64 + ((c ^ ((rl >> 1) & 3)) << 4) : stg + rl * 128 + ((c ^ (rl & 7)) << 4); };
   const bool col_ok = c < n_slots && col0 + 8 * c < N;
   if (res == nullptr) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rl = 4 * i + (lane >> 3);
       if (col_ok && row0 + rl < M) {
-        const uint4 v = ld_shared_v4(stg + rl * 128 + ((c ^ (rl & 7)) << 4));
+        const uint4 v = ld_shared_v4(slot_addr(rl));
         asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(y + ((size_t)(row0 + rl) * N + col0 + 8 * c) * 2), "r"(v.x),
                      "r"(v.y), "r"(v.z), "r"(v.w)
                      : "memory");
@@ -246,7 +248,7 @@ __device__ __forceinline__ void write_staged_block(uint32_t stg, int lane, uint8
   for (int i = 0; i < 8; ++i) {
     const int rl = 4 * i + (lane >> 3);
     if (col_ok && row0 + rl < M) {
-      const uint4 v = ld_shared_v4(stg + rl * 128 + ((c ^ (rl & 7)) << 4));
+      const uint4 v = ld_shared_v4(slot_addr(rl));
       asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(y + ((size_t)(row0 + rl) * N + col0 + 8 * c) * 2),
                    "r"(add_packed_pair(v.x, r[i].x, f16)), "r"(add_packed_pair(v.y, r[i].y, f16)), "r"(add_packed_pair(v.z, r[i].z, f16)),
                    "r"(add_packed_pair(v.w, r[i].w, f16))
