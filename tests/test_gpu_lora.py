@@ -491,3 +491,43 @@ def test_multi_width_projection_of_the_text_context(sdt_lib, rank, bias, dtype):
         assert torch.equal(mods[g](xo), yos[g]), f"multi-width launch differs from the single launch (site {g})"
         assert rel(mods[g].lora_A.grad, pairs[g][0].lora_A.grad) <= 2e-2 and rel(mods[g].lora_B.grad, pairs[g][0].lora_B.grad) <= 2e-2, g
     assert not multi_projectable(mods, xo.reshape(-1, 768).clone().requires_grad_(True))     # inputs that need dX go per site
+
+
+@pytest.mark.parametrize("M,K,N,rank,bias", [(8192, 1280, 640, 16, True), (15300, 2560, 320, 16, False), (8192 + 77, 1344, 640, 64, True),
+                                             (16384, 1280, 320, 32, True)])
+def test_double_tiles_equal_single_tiles(sdt_lib, M, K, N, rank, bias):
+    """K >= 1280 and N % 320 == 0 with enough row tiles selects the double-tile kernel (the two column tiles of a work item in one
+    joint K loop, X landed once).  Same UMMAs in the same order per tile: the output and the saved rank intermediate must be
+    bit-identical to the single-tile kernel (``sdt_debug_set(31, 1)`` switches double tiles off), forward and backward, for ragged
+    M, a K that is not a multiple of the 64-deep k-block, and every padded rank."""
+    from scal_sdt_b200 import _lib, get_lora
+    lib = _lib.load()
+    torch.manual_seed(M + K)
+    base = nn.Linear(K, N, bias=bias).to(DEV).requires_grad_(False)
+    mod = get_lora(base, rank=rank, alpha=rank)
+    with torch.no_grad():
+        mod.lora_B.normal_(0.0, 0.1)
+    x = torch.randn(M, K, device=DEV).bfloat16()
+    dy = torch.randn(M, N, device=DEV).bfloat16()
+
+    def run():
+        xi = x.clone().requires_grad_(True)
+        mod.lora_A.grad = mod.lora_B.grad = None
+        y = mod(xi)
+        y.backward(dy)
+        return y.detach().clone(), xi.grad.clone(), mod.lora_A.grad.clone(), mod.lora_B.grad.clone()
+    try:
+        lib.sdt_debug_set(31, 1)
+        single = run()
+        lib.sdt_debug_set(31, 0)
+        double = run()
+    finally:
+        lib.sdt_debug_set(31, 0)
+    for name, a, b in zip(("y", "dx", "dA", "dB"), single, double):
+        assert torch.equal(a, b), f"{name}: double tiles differ from single tiles"
+    # and the pair is right: a stratified sample of rows against the fp64 oracle
+    rows = torch.arange(0, M, 97, device=DEV)
+    w, b, A, B = (t.detach().double() for t in (mod.weight, mod.bias if bias else torch.zeros(N, device=DEV), mod.lora_A, mod.lora_B))
+    xr = x[rows].double()
+    ref = xr @ w.T + b + mod.scaling * (xr @ A.T) @ B.T
+    assert rel(double[0][rows], ref) <= 2e-2
