@@ -320,6 +320,9 @@ int sdt_simt_gemm_f32(const float* A, int64_t lda_m, int64_t lda_k, const float*
  *   14     K threshold above which the CTA-pair kernel is used (default 256)
  *   15     weight-gradient grid: min 64-token chunks per CTA | CTAs per SM << 8
  *   20     force the number of column tiles per work item in the CTA-pair kernel (tools/gemm_ab.py groups)
+ *   22     minimum N for 224-wide (192-wide at rank 64) tiles            24  programmatic dependent launch: 1 off, 2 on
+ *   30     1: A operand of the CTA-pair kernel through tensor memory (tcgen05.cp + TS-mode UMMAs; measured slower: tools/gemm_ab.py ts)
+ *   31     double tiles (two column tiles of a work item in one joint K loop): minimum K (default 1280); 1 = never (tools/gemm_ab.py dt)
  */
 int sdt_debug_set(int key, uint64_t value);
 
